@@ -1,0 +1,151 @@
+/*
+ * vqseg.h -- C ABI of libvqseg.so: the B200 (sm_100a) kernels behind VQ_SEG's VectorQuantizer.
+ *
+ * The reference (chaeyeongyun/VQ_SEG) is pure PyTorch: its "FFI" for this path is the torch ops
+ * that vector_quantizer/vq_img.py calls.  Each entry point below names the reference call sites
+ * it replaces (file:line relative to the reference root).  Host code binds these with ctypes
+ * (vq_seg_b200/_native.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative VQSEG_E* code;
+ *   - all pointers are DEVICE pointers unless the name ends in _host; tensors stay owned by the
+ *     caller, the kernels borrow them;
+ *   - no cudaMalloc, no host synchronisation and no global state inside (except cached
+ *     cudaFuncSetAttribute calls); everything is enqueued on `stream`;
+ *   - latent vectors are described as a logical (B, P, D) array with ELEMENT strides
+ *     (sB, sP, sD): NCHW feature maps are (B, H*W, C) with sB=C*H*W, sP=1, sD=H*W (the view made
+ *     by `rearrange(x,'b c h w -> b (h w) c')`, vq_img.py:232); packed row-major samples are
+ *     B=1, sP=D, sD=1.  Row id n = b*P + p.
+ *   - indices and counts are int64 (what torch.argmin / torch.bincount return).
+ */
+#ifndef VQSEG_H_
+#define VQSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQSEG_VERSION 100            /* 0.1.0 */
+
+#define VQSEG_EINVAL    (-1)         /* bad argument (null pointer, negative size, ...)          */
+#define VQSEG_EWORKSPACE (-2)        /* workspace too small: call vqseg_*_workspace_bytes        */
+#define VQSEG_EUNSUPPORTED (-3)      /* shape not supported by the requested algorithm           */
+#define VQSEG_EARCH     (-4)         /* device is not sm_100 (Blackwell B200)                    */
+
+/* assign algorithms */
+#define VQSEG_ALGO_AUTO   0          /* tensor-core filter + exact rescoring when the shape allows */
+#define VQSEG_ALGO_EXACT  1          /* exact fp32 scorer on every (row, code) pair                */
+#define VQSEG_ALGO_TC     2          /* tcgen05 fp16 filter + exact fp32 rescoring (error if unsupported) */
+
+/* gather modes */
+#define VQSEG_MODE_EVAL        0     /* quantize = E[idx]                          (vq_img.py:170)     */
+#define VQSEG_MODE_TRAIN       1     /* quantize = x + (E[idx] - x), two roundings (vq_img.py:236)     */
+#define VQSEG_MODE_TRAIN_AMP   2     /* as TRAIN with E[idx] rounded through fp16 (autocast matmul)    */
+#define VQSEG_MODE_EVAL_AMP    3
+
+int         vqseg_version(void);
+const char* vqseg_error_string(int code);
+
+/* ---- codebook preparation --------------------------------------------------------------------
+ * Replaces the per-call `x2.pow(2).sum(-1)` + operand building inside torch.cdist
+ * (ATen _euclidean_dist, reached from vq_img.py:167 and :39).  Fills an opaque, reusable
+ * "prepared codebook" blob: fp32 |e_k|^2 in torch's CPU summation order, max |e_k|, the fp16
+ * power-of-two prescale and the fp16 (-2 * s * E) image laid out as tcgen05 SWIZZLE_128B K-major
+ * shared-memory tiles (one bulk copy per pipeline stage).  Must be re-run whenever E changes.  */
+size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D);
+int    vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D,
+                                  void* blob, size_t blob_bytes, void* stream);
+
+/* ---- nearest-code assignment -----------------------------------------------------------------
+ * Replaces `torch.cdist(flatten_x, weight, p=2)` + `torch.argmin(distance, -1)`
+ * (vq_img.py:167-168) and `-torch.cdist` + `torch.argmax` inside kmeans (vq_img.py:39-41).
+ * The N x K distance matrix is never written.  idx_out[n] is the FIRST index minimising
+ * sqrt(max(|x|^2 - 2 x.e + |e|^2, 0)) evaluated in fp32 exactly as ATen's CPU path does
+ * (one FMA chain over the D+2 augmented terms, split every `kblock` terms).
+ * counts_out (nullable, K int64, must be zeroed by the caller) receives bincount(idx)
+ * (vq_img.py:173 / batched_bincount :22-27).  code_base is added to every written index and
+ * best_key_out (nullable, N uint64) receives (float_bits(dist) << 32 | global index) for the
+ * codebook-sharded mode (min-reduce across ranks keeps the lowest index on ties).            */
+size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int algo);
+int    vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                        int64_t sB, int64_t sP, int64_t sD,
+                        const float* E, int64_t K, const void* blob,
+                        int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
+                        int64_t code_base, int kblock, int algo,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* unpack the keys of the sharded mode after the cross-rank min: idx = key & 0xffffffff           */
+int    vqseg_unpack_keys(const uint64_t* keys, int64_t n, int64_t* idx_out, float* dist_out,
+                         int64_t* counts_out, int64_t K, void* stream);
+
+/* ---- gather + straight-through estimator + commitment loss -----------------------------------
+ * Replaces `F.one_hot(idx) -> matmul(onehot.float(), weight)` (vq_img.py:169-170), the STE
+ * `x + (quantize - x).detach()` (:236) and `F.mse_loss(quantize.detach(), x)` (:239).
+ * q_out has the same (B,P,D) logical shape with its own strides.  loss_out (nullable) receives
+ * sum((q_ste - x)^2) / (B*P*D) as ONE fp32 (deterministic two-stage reduction through `ws`).   */
+size_t vqseg_gather_workspace_bytes(int64_t n_rows, int64_t D);
+int    vqseg_gather_ste_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                            int64_t sB, int64_t sP, int64_t sD,
+                            const float* E, int64_t K, const int64_t* idx,
+                            float* q_out, int64_t qB, int64_t qP, int64_t qD,
+                            float* loss_out, int mode, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- backward of the training forward w.r.t. x -----------------------------------------------
+ * Replaces autograd through vq_img.py:236-240:  gx = g_q + coef * (x - q_ste), with
+ * coef = g_loss * commitment_weight * 2 / numel read from device memory (coef_dev, 1 float) so no
+ * host sync is needed.  g_q may be null (treated as zeros), coef_dev may be null (no loss term).
+ * All tensors share the (B,P,D) logical shape; each has its own strides.                        */
+int    vqseg_ste_bwd_f32(const float* g_q, int64_t gB, int64_t gP, int64_t gD,
+                         const float* x, int64_t sB, int64_t sP, int64_t sD,
+                         const float* q_ste, int64_t qB, int64_t qP, int64_t qD,
+                         const float* coef_dev, float coef_scale,
+                         float* gx, int64_t oB, int64_t oP, int64_t oD,
+                         int64_t B, int64_t P, int64_t D, void* stream);
+
+/* gradient of the eval-mode gather w.r.t. the codebook: gE[idx[n], :] += g_q[n, :]              */
+int    vqseg_gather_bwd_codebook_f32(const float* g_q, int64_t B, int64_t P, int64_t D,
+                                     int64_t gB, int64_t gP, int64_t gD,
+                                     const int64_t* idx, float* gE, int64_t K, void* stream);
+
+/* ---- per-code statistics (k-means update) ----------------------------------------------------
+ * Replaces batched_bincount (vq_img.py:22-27, :42) and
+ * `new_means.scatter_add_(1, repeat(buckets,'h n -> h n d'), samples)` (:47-51).
+ * counts (K int64) and sums (K*D fp32) must be zeroed by the caller (so ranks can accumulate).
+ * deterministic=1: per-code sums are accumulated in ascending row order, one fp32 chain per
+ * (code, d) -- the order of the reference's sequential CPU scatter_add_ -- via a stable counting
+ * sort; deterministic=0: warp-aggregated fp32 atomics (fast, order not fixed).                  */
+size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int deterministic);
+int    vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                            int64_t sB, int64_t sP, int64_t sD,
+                            const int64_t* idx, int64_t K,
+                            int64_t* counts, float* sums, int deterministic,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* means = where(counts == 0, means, sums / max(counts,1))  [then l2norm rows if cosine]
+ * (vq_img.py:44-45, :53-61).                                                                    */
+int    vqseg_kmeans_finalize_f32(const float* sums, const int64_t* counts, float* means_inout,
+                                 int64_t K, int64_t D, int cosine, void* stream);
+
+/* code_usage = 100 * (#counts == 0) / K as one fp32 (vq_img.py:174-175)                         */
+int    vqseg_code_usage(const int64_t* counts, int64_t K, float* usage_out, void* stream);
+
+/* rows[i,:] = x[row_ids[i], :] packed (K,D): initial k-means means (sample_vectors, vq_img.py:10-17) */
+int    vqseg_gather_rows_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                             int64_t sB, int64_t sP, int64_t sD,
+                             const int64_t* row_ids, int64_t n_ids, float* out, void* stream);
+
+/* ---- cosine codebook helpers (CosinesimCodebook, vq_img.py:93-107) ----------------------------
+ * out[n,:] = x[n,:] / max(|x[n,:]|, 1e-12)  (F.normalize, vq_img.py:7-8,:97,:100), packed (N,D). */
+int    vqseg_l2norm_rows_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                             int64_t sB, int64_t sP, int64_t sD, float* out, void* stream);
+/* idx = first argmax_k <x_n, e_k> over packed unit rows (einsum + argmax, vq_img.py:104-107)    */
+int    vqseg_assign_cosine_f32(const float* xn, int64_t N, int64_t D, const float* E, int64_t K,
+                               int64_t* idx_out, int64_t* counts_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VQSEG_H_ */

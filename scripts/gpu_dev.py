@@ -1,0 +1,134 @@
+"""Developer diagnostics on the GPU box (not a test, not the bench): python scripts/gpu_dev.py <stage>.
+Each stage prints PASS/FAIL lines and timings; run under `timeout` from gpurun."""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import cases  # noqa: E402
+from oracle import vq_oracle as O  # noqa: E402
+import vq_seg_b200 as V  # noqa: E402
+from vq_seg_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+GOLD = torch.load(os.path.join(ROOT, "tests", "golden", "golden_v1.pt"), weights_only=False)
+
+
+def view(x):
+    b, c, h, w = x.shape
+    return x.reshape(b, c, h * w).permute(0, 2, 1)
+
+
+def timeit(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for a, b in ev:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2] * 1e3, ts[0] * 1e3      # us
+
+
+def stage_exact():
+    names = sys.argv[2:] or list(cases.FORWARD_CASES)
+    for name in names:
+        x, e = cases.FORWARD_CASES[name]()
+        rec = GOLD["forward"][name]
+        xd, ed = x.to(dev), e.to(dev)
+        idx, counts = ops.assign(view(xd), ed, None, ops.ALGO_EXACT)
+        torch.cuda.synchronize()
+        gi = rec["idx"].reshape(idx.shape).to(torch.int64)
+        mism = (idx.cpu() != gi).sum().item()
+        cm = (counts.cpu() != rec["counts"]).sum().item()
+        print(f"[exact] {name:16s} idx mismatches {mism}/{gi.numel()} counts mism {cm}  {'PASS' if mism == 0 and cm == 0 else 'FAIL'}", flush=True)
+
+
+def stage_tc():
+    names = sys.argv[2:] or list(cases.FORWARD_CASES)
+    for name in names:
+        x, e = cases.FORWARD_CASES[name]()
+        rec = GOLD["forward"][name]
+        xd, ed = x.to(dev), e.to(dev)
+        blob = ops.prepare_codebook(ed)
+        torch.cuda.synchronize()
+        idx_e, counts_e = ops.assign(view(xd), ed, None, ops.ALGO_EXACT)
+        idx, counts = ops.assign(view(xd), ed, blob, ops.ALGO_TC)
+        torch.cuda.synchronize()
+        gi = rec["idx"].reshape(idx.shape).to(torch.int64)
+        mism = (idx.cpu() != gi).sum().item()
+        mism_e = (idx != idx_e).sum().item()
+        cm = (counts != counts_e).sum().item()
+        print(f"[tc] {name:16s} vs golden {mism}/{gi.numel()}  vs exact {mism_e}  counts mism {cm}  {'PASS' if mism_e == 0 and cm == 0 else 'FAIL'}", flush=True)
+
+
+def stage_ops():
+    for name in ["d64", "c1_l4", "r448_l5", "odd_7x7", "c2_randn"]:
+        x, e = cases.FORWARD_CASES[name]()
+        rec = GOLD["forward"][name]
+        m = V.VectorQuantizer(dim=x.shape[1], num_embeddings=e.shape[0]).to(dev)
+        m.codebook.embedding.weight.data.copy_(e)
+        m.codebook.algo = ops.ALGO_EXACT
+        m.eval()
+        with torch.no_grad():
+            q, idx, loss, usage = m(x.to(dev))
+        ok_e = cases.sha(q.cpu()) == rec["q_eval_sha"] and torch.equal(usage.cpu(), rec["usage"]) and torch.equal(loss.cpu(), rec["loss_eval"])
+        m.train()
+        xg = x.to(dev).requires_grad_(True)
+        q, idx, loss, usage = m(xg)
+        ok_t = cases.sha(q.detach().cpu()) == rec["q_train_sha"]
+        rel = ((loss.detach().cpu() - rec["loss_train"]).abs() / rec["loss_train"].abs()).item()
+        g = torch.Generator().manual_seed(999)
+        gq = torch.randn(q.shape, generator=g).to(dev)
+        ((q * gq).sum() + 1.5 * loss.sum()).backward()
+        ref = O.vq_backward(x, O.vq_forward(x, e, True, 1)["quantize"], gq.cpu(), torch.tensor(1.5), 1)
+        gerr = ((xg.grad.cpu() - ref).abs().max() / ref.abs().max()).item()
+        print(f"[ops] {name:12s} eval-bitexact {ok_e} train-q-bitexact {ok_t} loss rel {rel:.2e} grad relmax {gerr:.2e} "
+              f"wgrad None {m.codebook.embedding.weight.grad is None} loss.shape {tuple(loss.shape)} rg {loss.requires_grad}", flush=True)
+    for name in cases.KMEANS_CASES:
+        x, k, iters, init_idx, use_cos = cases.kmeans_case(name)
+        rec = GOLD["kmeans"][name]
+        xv = view(x.to(dev))
+        src = ops.l2norm_rows(xv) if use_cos else xv
+        means, bins = V.kmeans(src, k, iters, use_cosine_sim=use_cos, init_indices=init_idx, algo=ops.ALGO_EXACT)
+        torch.cuda.synchronize()
+        be = torch.equal(bins[0].cpu(), rec["bins"])
+        me = torch.equal(means[0].cpu(), rec["means"])
+        err = (means[0].cpu() - rec["means"]).abs().max().item()
+        print(f"[kmeans] {name:12s} bins exact {be} means bit-exact {me} maxabs {err:.3e}", flush=True)
+
+
+def stage_time():
+    x, e = cases.FORWARD_CASES["c2_randn"]()
+    xd, ed = x.to(dev), e.to(dev)
+    xv = view(xd)
+    blob = ops.prepare_codebook(ed)
+    for algo, nm in [(ops.ALGO_EXACT, "exact"), (ops.ALGO_TC, "tc+rescore")]:
+        if algo == ops.ALGO_TC and "notc" in sys.argv:
+            continue
+        med, best = timeit(lambda: ops.assign(xv, ed, blob, algo), n=10 if algo == ops.ALGO_EXACT else 50)
+        print(f"[time] assign {nm:10s} C2: median {med:9.1f} us best {best:9.1f} us -> {32768 / med:.3f} Gvec/s... {2*32768*512*256/med/1e6:.1f} TFLOP/s", flush=True)
+    idx, _ = ops.assign(xv, ed, blob, ops.ALGO_EXACT)
+    med, best = timeit(lambda: ops.prepare_codebook(ed), n=50)
+    print(f"[time] prepare_codebook: median {med:.1f} us best {best:.1f}")
+    med, best = timeit(lambda: ops.gather_ste(xv, ed, idx, ops.MODE_TRAIN), n=50)
+    print(f"[time] gather_ste train: median {med:.1f} us best {best:.1f} -> {(8*32768*256+8*32768)/med/1e3:.1f} GB/s")
+    q, _ = ops.gather_ste(xv, ed, idx, ops.MODE_TRAIN)
+    gq = torch.randn_like(q)
+    gm = torch.ones(1, device=dev)
+    med, best = timeit(lambda: ops.ste_bwd(gq, xv, q, gm, 2.0 / xv.numel()), n=50)
+    print(f"[time] ste_bwd: median {med:.1f} us best {best:.1f} -> {(16*32768*256)/med/1e3:.1f} GB/s")
+    for det in (True, False):
+        med, best = timeit(lambda: ops.code_stats(xv, idx, 512, det), n=20)
+        print(f"[time] code_stats det={det}: median {med:.1f} us best {best:.1f}")
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time}[sys.argv[1]]()
+    print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

@@ -1,0 +1,62 @@
+"""ctypes binding of libvqseg.so (C ABI declared in include/vqseg.h).
+
+There is NO CPU fallback: if the shared library is missing or the device is not a B200 the
+calls raise.  Build with `python -m vq_seg_b200.build` (or `__graft_entry__.build()`).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvqseg.so")
+_lib = None
+
+i64, f32, vp, sz, ci = ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/vqseg.h one to one
+SIGNATURES = {
+    "vqseg_version": (ci, []),
+    "vqseg_error_string": (ctypes.c_char_p, [ci]),
+    "vqseg_codebook_blob_bytes": (sz, [i64, i64]),
+    "vqseg_codebook_prepare_f32": (ci, [vp, i64, i64, vp, sz, vp]),
+    "vqseg_assign_workspace_bytes": (sz, [i64, i64, i64, ci]),
+    "vqseg_assign_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp]),
+    "vqseg_unpack_keys": (ci, [vp, i64, vp, vp, vp, i64, vp]),
+    "vqseg_gather_workspace_bytes": (sz, [i64, i64]),
+    "vqseg_gather_ste_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, i64, i64, i64, vp, ci, vp, sz, vp]),
+    "vqseg_ste_bwd_f32": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, f32,
+                               vp, i64, i64, i64, i64, i64, i64, vp]),
+    "vqseg_gather_bwd_codebook_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, vp]),
+    "vqseg_code_stats_workspace_bytes": (sz, [i64, i64, i64, ci]),
+    "vqseg_code_stats_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, ci, vp, sz, vp]),
+    "vqseg_kmeans_finalize_f32": (ci, [vp, vp, vp, i64, i64, ci, vp]),
+    "vqseg_code_usage": (ci, [vp, i64, vp, vp]),
+    "vqseg_gather_rows_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp]),
+    "vqseg_l2norm_rows_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, vp]),
+    "vqseg_assign_cosine_f32": (ci, [vp, i64, i64, vp, i64, vp, vp, vp]),
+}
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libvqseg.so once; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} not found: build it with `python -m vq_seg_b200.build`. "
+                "vq_seg_b200 has no CPU / PyTorch fallback for its kernels.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().vqseg_error_string(rc).decode()
+        raise RuntimeError(f"libvqseg {what} failed ({rc}): {msg}")

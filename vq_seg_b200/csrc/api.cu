@@ -1,0 +1,183 @@
+// C ABI entry points for codebook preparation and nearest-code assignment (see include/vqseg.h).
+#include "common.cuh"
+#include <string.h>
+
+namespace vqseg {
+// exact.cu
+struct ExactArgs {
+  Rows x;
+  const float* E; int K;
+  const float* enorm;
+  int kblock;
+  const int* work_rows; const int* work_count;
+  const int* cand_idx; const int* cand_cnt; int cand_cap;
+  long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
+};
+int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st);
+int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st);
+// assign_tc.cu
+struct TcArgs {
+  Rows x;
+  const unsigned char* blob;
+  long long n_rows;
+  int n_tiles, n_cc, n_dc;
+  int K;
+  float tau;
+  long long* idx_out; unsigned long long* counts_out; long long code_base;
+  int force_rescore;
+  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
+};
+int launch_pack(const float* E, int K, int D, unsigned char* blob, cudaStream_t st);
+int launch_assign_tc(const TcArgs& a, cudaStream_t st);
+constexpr int kCandCapHost = 8;
+
+__global__ void blob_init_kernel(BlobHeader* h, int K, int D, int K_pad, int D_pad, unsigned long long off_enorm,
+                                 unsigned long long off_image) {
+  h->magic = kBlobMagic; h->K = K; h->D = D; h->K_pad = K_pad; h->D_pad = D_pad;
+  h->scale = 1.f; h->max_enorm = 0.f; h->max_enorm_bits = 0u; h->max_abs_bits = 0u;
+  h->off_enorm = off_enorm; h->off_image = off_image;
+}
+
+// MKL's sgemm K-blocking as probed on the reference CPU path: one chain up to
+// 384 terms, two halves up to 768, 384-blocks beyond.
+static int auto_kblock(long long D) {
+  long long L = D + 2;
+  if (L <= 384) return 0;
+  if (L <= 768) return (int)((L + 1) / 2);
+  return 384;
+}
+}  // namespace vqseg
+
+using namespace vqseg;
+
+extern "C" {
+
+int vqseg_version(void) { return VQSEG_VERSION; }
+
+const char* vqseg_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case VQSEG_EINVAL: return "vqseg: invalid argument";
+    case VQSEG_EWORKSPACE: return "vqseg: workspace too small";
+    case VQSEG_EUNSUPPORTED: return "vqseg: shape not supported by the requested algorithm";
+    case VQSEG_EARCH: return "vqseg: device is not sm_100 (B200)";
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "vqseg: unknown error";
+}
+
+static void blob_geometry(int64_t K, int64_t D, long long* K_pad, long long* D_pad, size_t* off_enorm, size_t* off_image,
+                          size_t* total) {
+  *K_pad = round_up(K, 256);
+  *D_pad = round_up(D, kDChunk);
+  *off_enorm = 1024;
+  *off_image = *off_enorm + (size_t)round_up(2 * *K_pad * sizeof(float), 1024);
+  *total = *off_image + (size_t)(*K_pad / kCodeBlock) * (size_t)(*D_pad / kDChunk) * kTileBytes;
+}
+
+size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D) {
+  if (K <= 0 || D <= 0) return 0;
+  long long kp, dp; size_t oe, oi, tot;
+  blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot);
+  return tot;
+}
+
+int vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D, void* blob, size_t blob_bytes, void* stream) {
+  if (!E || !blob || K <= 0 || D <= 0 || K >= (1ll << 30) || D >= (1ll << 20)) return VQSEG_EINVAL;
+  long long kp, dp; size_t oe, oi, tot;
+  blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot);
+  if (blob_bytes < tot) return VQSEG_EWORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(blob) & 1023) != 0) return VQSEG_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* b = (unsigned char*)blob;
+  blob_init_kernel<<<1, 1, 0, st>>>((BlobHeader*)b, (int)K, (int)D, (int)kp, (int)dp, oe, oi);
+  VQSEG_LAUNCH_CHECK();
+  int rc = launch_enorm(E, (int)K, (int)D, (int)kp, (float*)(b + oe), (BlobHeader*)b, st);
+  if (rc) return rc;
+  return launch_pack(E, (int)K, (int)D, b, st);
+}
+
+size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int algo) {
+  (void)D; (void)algo;
+  size_t b = 256;                                              // work counter
+  b += (size_t)round_up(n_rows * sizeof(int), 256);            // work_rows
+  b += (size_t)round_up(n_rows * sizeof(int), 256);            // cand_cnt
+  b += (size_t)round_up(n_rows * kCandCapHost * sizeof(int), 256);   // cand_idx
+  b += (size_t)round_up(round_up(K, 256) * sizeof(float), 256);      // enorm when no blob is given
+  return b;
+}
+
+int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                     const float* E, int64_t K, const void* blob,
+                     int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
+                     int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream) {
+  if (!x || !E || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
+  if (!idx_out && !best_key_out) return VQSEG_EINVAL;
+  const long long n_rows = B * P;
+  if (n_rows == 0) return 0;
+  if (n_rows >= (1ll << 31) || K >= (1ll << 31) - 1 || D >= (1ll << 20)) return VQSEG_EUNSUPPORTED;
+  if (!ws || ws_bytes < vqseg_assign_workspace_bytes(n_rows, D, K, algo)) return VQSEG_EWORKSPACE;
+  int rc = check_arch();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kblock == 0) kblock = auto_kblock(D);
+
+  char* p = (char*)ws;
+  int* work_count = (int*)p;   p += 256;
+  int* work_rows = (int*)p;    p += round_up(n_rows * sizeof(int), 256);
+  int* cand_cnt = (int*)p;     p += round_up(n_rows * sizeof(int), 256);
+  int* cand_idx = (int*)p;     p += round_up(n_rows * kCandCapHost * sizeof(int), 256);
+  float* enorm_ws = (float*)p;
+
+  const BlobHeader* hdr = (const BlobHeader*)blob;
+  const float* enorm = nullptr;
+  long long kp = 0, dp = 0;
+  if (blob) {
+    size_t oe, oi, tot;
+    blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot);
+    enorm = (const float*)((const char*)blob + oe);
+  } else {
+    rc = launch_enorm(E, (int)K, (int)D, (int)K, enorm_ws, nullptr, st);
+    if (rc) return rc;
+    enorm = enorm_ws;
+  }
+  (void)hdr;
+
+  bool use_tc = false;
+  if (algo == VQSEG_ALGO_TC) {
+    if (!blob) return VQSEG_EINVAL;
+    use_tc = true;
+  } else if (algo == VQSEG_ALGO_AUTO) {
+    use_tc = blob != nullptr && n_rows >= 64 && K >= 32;
+  } else if (algo != VQSEG_ALGO_EXACT) {
+    return VQSEG_EINVAL;
+  }
+
+  Rows xr{x, B, P, D, sB, sP, sD};
+  ExactArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.x = xr; ea.E = E; ea.K = (int)K; ea.enorm = enorm; ea.kblock = kblock;
+  ea.idx_out = (long long*)idx_out; ea.counts_out = (unsigned long long*)counts_out;
+  ea.key_out = (unsigned long long*)best_key_out; ea.code_base = code_base;
+
+  if (!use_tc) return launch_exact(ea, n_rows, st);
+
+  cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  TcArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.x = xr; ta.blob = (const unsigned char*)blob; ta.n_rows = n_rows;
+  ta.n_tiles = (int)((n_rows + 127) / 128); ta.n_cc = (int)(kp / 256); ta.n_dc = (int)(dp / kDChunk);
+  ta.K = (int)K;
+  ta.tau = 0.00390625f * 1.015625f;          // 2^-8 (two fp16 roundings per operand pair, both sides) + margin
+  ta.idx_out = (long long*)idx_out; ta.counts_out = (unsigned long long*)counts_out; ta.code_base = code_base;
+  ta.force_rescore = (best_key_out != nullptr || idx_out == nullptr) ? 1 : 0;
+  ta.cand_idx = cand_idx; ta.cand_cnt = cand_cnt; ta.work_rows = work_rows; ta.work_count = work_count;
+  rc = launch_assign_tc(ta, st);
+  if (rc) return rc;
+  ea.work_rows = work_rows; ea.work_count = work_count;
+  ea.cand_idx = cand_idx; ea.cand_cnt = cand_cnt; ea.cand_cap = kCandCapHost;
+  return launch_exact(ea, n_rows, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Shared device/host helpers for libvqseg (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/vqseg.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libvqseg is written for sm_100a (B200) only"
+#endif
+
+namespace vqseg {
+
+// Logical (B, P, D) view with element strides; row n = b*P + p.
+struct Rows {
+  const float* ptr;
+  long long B, P, D, sB, sP, sD;
+  __host__ __device__ inline long long n_rows() const { return B * P; }
+  __device__ inline const float* row(long long n) const {
+    long long b = n / P, p = n - b * P;
+    return ptr + b * sB + p * sP;
+  }
+};
+struct RowsOut {
+  float* ptr;
+  long long B, P, D, sB, sP, sD;
+  __device__ inline float* row(long long n) const {
+    long long b = n / P, p = n - b * P;
+    return ptr + b * sB + p * sP;
+  }
+};
+
+// ---- prepared-codebook blob layout (all offsets 1024-byte aligned) ----------------------------
+// [0]    BlobHeader
+// [1024] enorm  : K_pad fp32, |e_k|^2 in torch's CPU pow(2).sum(-1) order (pads = +inf marker 3e38)
+// [..]   image  : fp16 (-2*s*E) as SWIZZLE_128B K-major tiles of 128 codes x 64 dims (16 KiB each),
+//                 ordered [code_block][d_chunk]
+struct BlobHeader {
+  uint32_t magic;        // 'VQSB'
+  int32_t  K, D, K_pad, D_pad;      // K_pad multiple of 256, D_pad multiple of 64
+  float    scale;        // power-of-two prescale s applied to x and E before fp16 rounding
+  float    max_enorm;    // max_k |e_k|^2  (fp32, >= true value)
+  uint32_t max_enorm_bits;          // written with atomicMax on the float bits
+  uint32_t max_abs_bits;            // max |e_kd| bits
+  uint64_t off_enorm, off_image;
+};
+constexpr uint32_t kBlobMagic = 0x42535156u;
+constexpr int kCodeBlock = 128;     // codes per packed tile
+constexpr int kDChunk = 64;         // dims per packed tile (64 fp16 = one 128-byte swizzle row)
+constexpr int kTileBytes = kCodeBlock * kDChunk * 2;
+
+__host__ __device__ inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// ---- torch-CPU-order sum of squares ------------------------------------------------------------
+// ATen's CPU sum kernel (aten/src/ATen/native/cpu/SumKernel.cpp, vectorized_inner_sum) reduces a
+// contiguous row with 4 ILP accumulators of 8-lane vectors and a 4-level cascade that spills
+// every 16 "rows" of 32 elements; element j goes to accumulator t = j % 32.  A warp reproduces it
+// with lane t <-> accumulator t.  `sq(j)` must return fl(v_j * v_j).
+// All 32 lanes must call this; returns the sum on every lane.
+template <typename F>
+__device__ inline float torch_order_sumsq_warp(F sq, long long D, int lane) {
+  const long long vec_size = D / 8;              // number of 8-wide vectors
+  const long long size_ilp = vec_size / 4;       // rows of 4 vectors
+  int level_power = 4;
+  {
+    int cl = 0;
+    while ((1ll << cl) < size_ilp) ++cl;         // CeilLog2(size_ilp)
+    if (cl / 4 > level_power) level_power = cl / 4;
+  }
+  const long long level_step = 1ll << level_power, level_mask = level_step - 1;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  long long i = 0;
+  for (; i + level_step <= size_ilp;) {
+    for (long long j = 0; j < level_step; ++j, ++i) acc0 = __fadd_rn(acc0, sq(i * 32 + lane));
+    // cascade
+    acc1 = __fadd_rn(acc1, acc0); acc0 = 0.f;
+    if ((i & (level_mask << level_power)) == 0) {
+      acc2 = __fadd_rn(acc2, acc1); acc1 = 0.f;
+      if ((i & (level_mask << (2 * level_power))) == 0) { acc3 = __fadd_rn(acc3, acc2); acc2 = 0.f; }
+    }
+  }
+  for (; i < size_ilp; ++i) acc0 = __fadd_rn(acc0, sq(i * 32 + lane));
+  acc0 = __fadd_rn(acc0, acc1); acc0 = __fadd_rn(acc0, acc2); acc0 = __fadd_rn(acc0, acc3);
+  // leftover whole vectors (vec_size % 4) go to partial_sums[0] == lanes 0..7
+  for (long long v = size_ilp * 4; v < vec_size; ++v) {
+    float s = (lane < 8) ? sq(v * 8 + lane) : 0.f;
+    if (lane < 8) acc0 = __fadd_rn(acc0, s);
+  }
+  // partial_sums[0] += partial_sums[k], k = 1..3   (vector adds, lane l of vector k = lane k*8+l)
+  float p = acc0;
+  p = __fadd_rn(p, __shfl_sync(0xffffffffu, acc0, (lane & 7) + 8));
+  p = __fadd_rn(p, __shfl_sync(0xffffffffu, acc0, (lane & 7) + 16));
+  p = __fadd_rn(p, __shfl_sync(0xffffffffu, acc0, (lane & 7) + 24));
+  // final_acc = 0 + scalar tail + partials[0..7] sequentially
+  float f = 0.f;
+  for (long long k = vec_size * 8; k < D; ++k) f = __fadd_rn(f, sq(k));
+#pragma unroll
+  for (int l = 0; l < 8; ++l) f = __fadd_rn(f, __shfl_sync(0xffffffffu, p, l));
+  return f;
+}
+
+__device__ inline float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int check_arch() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return (int)e;
+  return major == 10 ? 0 : VQSEG_EARCH;
+}
+
+inline int num_sms() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+
+#define VQSEG_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+}  // namespace vqseg

@@ -1,0 +1,238 @@
+// Exact fp32 scorer: the arithmetic of ATen's CPU `_euclidean_dist` + argmin, restated for the GPU.
+//
+// Reference call sites: torch.cdist + torch.argmin (vector_quantizer/vq_img.py:167-168) and
+// -torch.cdist + torch.argmax in kmeans (vq_img.py:39-41).
+//
+// d(x, e_k) = sqrt(max(c, 0)) where c is the fp32 result of the (D+2)-term augmented dot product
+//   [-2x_0 .. -2x_{D-1}, |x|^2, 1] . [e_k0 .. e_k,D-1, 1, |e_k|^2]
+// evaluated as MKL's sgemm evaluates it on CPU: one FMA chain per output in increasing term order,
+// restarted every `kblock` terms with the partial results added in order (probed: kblock = inf for
+// D+2 <= 384, 384-blocks beyond).  Because scaling by -2 commutes with fp32
+// rounding, the chain over (-2 x_j) e_j equals -2 * chain over x_j e_j bit for bit.
+//
+// One warp owns one row: lane t loads x[t::32] (and is accumulator t of the torch-order |x|^2), then
+// every lane runs the chain for its own candidate code(s).  The same kernel is (a) the brute-force
+// exact path over all K codes, (b) the rescoring pass over the short-list written by the tcgen05
+// filter (assign_tc.cu).  Ties: the lowest code index wins, like torch.argmin.
+#include "common.cuh"
+
+namespace vqseg {
+
+// ---- |e_k|^2 in torch order, one warp per code -------------------------------------------------
+__global__ void enorm_kernel(const float* __restrict__ E, int K, int D, int K_pad,
+                             float* __restrict__ enorm, BlobHeader* hdr) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= K_pad) return;
+  if (warp >= K) { if (lane == 0) enorm[warp] = 3.0e38f; return; }
+  const float* row = E + (long long)warp * D;
+  float s = torch_order_sumsq_warp([&](long long j) { float v = row[j]; return __fmul_rn(v, v); }, D, lane);
+  float amax = 0.f;
+  for (int j = lane; j < D; j += 32) amax = fmaxf(amax, fabsf(row[j]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) {
+    enorm[warp] = s;
+    if (hdr) {
+      atomicMax(&hdr->max_enorm_bits, __float_as_uint(s));
+      atomicMax(&hdr->max_abs_bits, __float_as_uint(amax));
+    }
+  }
+}
+
+// one augmented chain, generic block size. xs: shared x row, e: global code row
+__device__ __forceinline__ float chain_dist2(const float* __restrict__ xs, const float* __restrict__ e,
+                                             int D, float xnorm, float enorm, int kb, bool vec4) {
+  const int L = D + 2;
+  if (kb <= 0 || kb > L) kb = L;
+  float c = 0.f;
+  bool first = true;
+  for (int blk = 0; blk < L; blk += kb) {
+    int end = min(blk + kb, L);
+    int dend = min(end, D);
+    float t = 0.f;
+    int j = blk;
+    if (vec4) {
+      for (; j < dend && (j & 3); ++j) t = __fmaf_rn(xs[j], __ldg(e + j), t);
+      for (; j + 4 <= dend; j += 4) {
+        float4 ev = __ldg(reinterpret_cast<const float4*>(e + j));
+        float4 xv = *reinterpret_cast<const float4*>(xs + j);
+        t = __fmaf_rn(xv.x, ev.x, t); t = __fmaf_rn(xv.y, ev.y, t);
+        t = __fmaf_rn(xv.z, ev.z, t); t = __fmaf_rn(xv.w, ev.w, t);
+      }
+    }
+    for (; j < dend; ++j) t = __fmaf_rn(xs[j], __ldg(e + j), t);
+    float s = -2.f * t;                                   // exact
+    if (end > D) {
+      if (blk <= D) s = __fadd_rn(s, xnorm);              // term D   : |x|^2 * 1
+      if (end > D + 1) s = __fadd_rn(s, enorm);           // term D+1 : 1 * |e|^2
+    }
+    c = first ? s : __fadd_rn(c, s);
+    first = false;
+  }
+  return c;
+}
+
+// four independent chains per lane (codes k0 + 32*q), used by the all-codes path for ILP
+__device__ __forceinline__ void chain_dist2_x4(const float* __restrict__ xs, const float* __restrict__ E,
+                                               int D, int K, int k0, float xnorm,
+                                               const float* __restrict__ enorm, int kb, float out[4]) {
+  const int L = D + 2;
+  if (kb <= 0 || kb > L) kb = L;
+  const float* e[4];
+  bool ok[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { int k = k0 + 32 * q; ok[q] = k < K; e[q] = E + (long long)(ok[q] ? k : 0) * D; }
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  bool first = true;
+  for (int blk = 0; blk < L; blk += kb) {
+    int end = min(blk + kb, L);
+    int dend = min(end, D);
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    int j = blk;
+    for (; j < dend && (j & 3); ++j) {
+      float xv = xs[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) t[q] = __fmaf_rn(xv, __ldg(e[q] + j), t[q]);
+    }
+    for (; j + 4 <= dend; j += 4) {
+      float4 xv = *reinterpret_cast<const float4*>(xs + j);
+      float4 ev[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ev[q] = __ldg(reinterpret_cast<const float4*>(e[q] + j));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        t[q] = __fmaf_rn(xv.x, ev[q].x, t[q]); t[q] = __fmaf_rn(xv.y, ev[q].y, t[q]);
+        t[q] = __fmaf_rn(xv.z, ev[q].z, t[q]); t[q] = __fmaf_rn(xv.w, ev[q].w, t[q]);
+      }
+    }
+    for (; j < dend; ++j) {
+      float xv = xs[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) t[q] = __fmaf_rn(xv, __ldg(e[q] + j), t[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float s = -2.f * t[q];
+      if (end > D) {
+        if (blk <= D) s = __fadd_rn(s, xnorm);
+        if (end > D + 1) s = __fadd_rn(s, enorm[ok[q] ? k0 + 32 * q : 0]);
+      }
+      c[q] = first ? s : __fadd_rn(c[q], s);
+    }
+    first = false;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[q] = c[q];
+}
+
+__device__ __forceinline__ void lexmin(float& d, int& k, float d2, int k2) {
+  if (d2 < d || (d2 == d && k2 < k)) { d = d2; k = k2; }
+}
+
+struct ExactArgs {
+  Rows x;
+  const float* E; int K;
+  const float* enorm;
+  int kblock;
+  // candidate mode (null -> all rows x all codes)
+  const int* work_rows; const int* work_count;        // flagged row ids, device counter
+  const int* cand_idx; const int* cand_cnt; int cand_cap;   // per row: up to cand_cap codes; cnt > cap => all codes
+  long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
+};
+
+constexpr int kExactWarps = 8;
+
+__global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs a) {
+  extern __shared__ __align__(16) float smem_x[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int D = (int)a.x.D;
+  float* xs = smem_x + (size_t)wib * ((D + 3) & ~3);
+  const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.E) & 15) == 0);
+  const long long n_rows = a.x.n_rows();
+  long long n_work = a.work_rows ? (long long)*a.work_count : n_rows;
+  if (a.work_rows && n_work > n_rows) n_work = n_rows;
+  for (long long w = (long long)blockIdx.x * kExactWarps + wib; w < n_work; w += (long long)gridDim.x * kExactWarps) {
+    const long long n = a.work_rows ? a.work_rows[w] : w;
+    const float* xr = a.x.row(n);
+    __syncwarp();
+    for (int j = lane; j < D; j += 32) xs[j] = xr[(long long)j * a.x.sD];
+    __syncwarp();
+    const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
+    float best = __int_as_float(0x7f800000);   // +inf
+    int best_k = 0x7fffffff;
+    int cnt = a.cand_cnt ? a.cand_cnt[n] : -1;
+    if (cnt >= 0 && cnt <= a.cand_cap) {
+      const int* cl = a.cand_idx + n * a.cand_cap;
+      for (int c0 = 0; c0 < cnt; c0 += 32) {
+        int c = c0 + lane;
+        if (c < cnt) {
+          int k = cl[c];
+          float c2 = chain_dist2(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, vec4);
+          float d = __fsqrt_rn(fmaxf(c2, 0.f));
+          lexmin(best, best_k, d, k);
+        }
+      }
+    } else {
+      for (int k0 = lane; k0 < a.K; k0 += 128) {
+        float c4[4];
+        if (vec4) {
+          chain_dist2_x4(xs, a.E, D, a.K, k0, xnorm, a.enorm, a.kblock, c4);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            int k = k0 + 32 * q;
+            c4[q] = k < a.K ? chain_dist2(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, false) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int k = k0 + 32 * q;
+          if (k < a.K) lexmin(best, best_k, __fsqrt_rn(fmaxf(c4[q], 0.f)), k);
+        }
+      }
+    }
+    // NaN distances never win above; torch.argmin would return the first NaN -- documented divergence.
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float d2 = __shfl_xor_sync(0xffffffffu, best, o);
+      int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
+      lexmin(best, best_k, d2, k2);
+    }
+    if (lane == 0) {
+      if (best_k == 0x7fffffff) best_k = 0;
+      if (a.idx_out) a.idx_out[n] = (long long)best_k + a.code_base;
+      if (a.counts_out) atomicAdd(a.counts_out + best_k, 1ull);
+      if (a.key_out)
+        a.key_out[n] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(uint32_t)(best_k + a.code_base);
+    }
+  }
+}
+
+int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st) {
+  int warps = K_pad;
+  int threads = 256, blocks = (warps * 32 + threads - 1) / threads;
+  enorm_kernel<<<blocks, threads, 0, st>>>(E, K, D, K_pad, enorm, hdr);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st) {
+  if (max_work <= 0) return 0;
+  const int D = (int)a.x.D;
+  size_t smem = (size_t)kExactWarps * ((D + 3) & ~3) * sizeof(float);
+  if (smem > 200 * 1024) return VQSEG_EUNSUPPORTED;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(exact_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  long long blocks = (max_work + kExactWarps - 1) / kExactWarps;
+  long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  exact_score_kernel<<<(unsigned)blocks, kExactWarps * 32, smem, st>>>(a);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vqseg

@@ -1,0 +1,636 @@
+// HBM-bound kernels of the VQ bottleneck: codebook gather + straight-through estimator + commitment
+// loss, its backward, per-code statistics for k-means, and small helpers.
+// Reference call sites are cited per kernel (paths relative to the reference root).
+#include "common.cuh"
+
+namespace vqseg {
+
+// =================================================================================================
+// gather + STE + commitment loss      (vq_img.py:169-170 one_hot+matmul, :236 STE, :239 mse_loss)
+// =================================================================================================
+// Pixel-contiguous layout (NCHW: sP == 1).  A block owns a 64-pixel x 64-dim tile: codebook rows
+// are read along d (coalesced 128 B per code row segment) into a padded smem tile, then x / q are
+// streamed along pixels (coalesced).  algorithmic bytes: 4ND (x) + 4ND (q) + 8N (idx) + 4KD (E).
+constexpr int kGTile = 64;
+
+__device__ __forceinline__ float round_fp16(float v) { return __half2float(__float2half_rn(v)); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float* __restrict__ E, int K,
+                                                             const long long* __restrict__ idx, RowsOut q,
+                                                             float* __restrict__ partial) {
+  __shared__ float tile[kGTile][kGTile + 1];
+  __shared__ int s_idx[kGTile];
+  __shared__ float s_red[8];
+  const int D = (int)x.D;
+  const long long n_rows = x.n_rows();
+  const long long n0 = (long long)blockIdx.x * kGTile;
+  const int d0 = blockIdx.y * kGTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < kGTile) {
+    long long n = n0 + threadIdx.x;
+    long long k = n < n_rows ? idx[n] : 0;
+    s_idx[threadIdx.x] = (int)(k < 0 ? 0 : (k >= K ? K - 1 : k));
+  }
+  __syncthreads();
+  // phase 1: gather code row segments, lanes along d
+  for (int p = warp; p < kGTile; p += 8) {
+    const float* er = E + (long long)s_idx[p] * D + d0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int d = lane + 32 * h;
+      float v = (d0 + d < D) ? __ldg(er + d) : 0.f;
+      if (MODE == VQSEG_MODE_TRAIN_AMP || MODE == VQSEG_MODE_EVAL_AMP) v = round_fp16(v);
+      tile[d][p] = v;
+    }
+  }
+  __syncthreads();
+  // phase 2: stream pixels, lanes along p
+  float acc = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h;
+    const long long n = n0 + p;
+    if (n < n_rows) {
+      const long long b = n / x.P, pp = n - b * x.P;
+      const float* xb = x.ptr + b * x.sB + pp * x.sP;
+      float* qb = q.ptr + b * q.sB + pp * q.sP;
+      for (int d = warp; d < kGTile; d += 8) {
+        if (d0 + d < D) {
+          float e = tile[d][p];
+          if (MODE == VQSEG_MODE_EVAL || MODE == VQSEG_MODE_EVAL_AMP) {
+            qb[(long long)(d0 + d) * q.sD] = e;
+          } else {
+            float xv = __ldg(xb + (long long)(d0 + d) * x.sD);
+            float qs = __fadd_rn(xv, __fsub_rn(e, xv));          // x + (q - x): two roundings (:236)
+            qb[(long long)(d0 + d) * q.sD] = qs;
+            float df = __fsub_rn(qs, xv);
+            acc = __fmaf_rn(df, df, acc);
+          }
+        }
+      }
+    }
+  }
+  if (partial) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += s_red[w];
+      partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
+// Generic strides (row-major samples etc.): one warp per row, lanes along d.
+template <int MODE>
+__global__ void __launch_bounds__(256) gather_ste_generic_kernel(Rows x, const float* __restrict__ E, int K,
+                                                                 const long long* __restrict__ idx, RowsOut q,
+                                                                 float* __restrict__ partial) {
+  __shared__ float s_red[8];
+  const int D = (int)x.D;
+  const long long n_rows = x.n_rows();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc = 0.f;
+  for (long long n = (long long)blockIdx.x * 8 + warp; n < n_rows; n += (long long)gridDim.x * 8) {
+    long long k = idx[n];
+    k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+    const float* er = E + k * D;
+    const float* xr = x.row(n);
+    float* qr = q.row(n);
+    for (int d = lane; d < D; d += 32) {
+      float e = __ldg(er + d);
+      if (MODE == VQSEG_MODE_TRAIN_AMP || MODE == VQSEG_MODE_EVAL_AMP) e = round_fp16(e);
+      if (MODE == VQSEG_MODE_EVAL || MODE == VQSEG_MODE_EVAL_AMP) {
+        qr[(long long)d * q.sD] = e;
+      } else {
+        float xv = __ldg(xr + (long long)d * x.sD);
+        float qs = __fadd_rn(xv, __fsub_rn(e, xv));
+        qr[(long long)d * q.sD] = qs;
+        float df = __fsub_rn(qs, xv);
+        acc = __fmaf_rn(df, df, acc);
+      }
+    }
+  }
+  if (partial) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += s_red[w];
+      partial[blockIdx.x] = s;
+    }
+  }
+}
+
+// fixed-order final reduction of the per-block partials -> mean
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ partial, int n_partial,
+                                                            double inv_numel, float* __restrict__ loss_out) {
+  __shared__ double s_red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n_partial; i += 256) s += (double)partial[i];
+  s_red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss_out = (float)(s_red[0] * inv_numel);
+}
+
+template <int MODE>
+static int launch_gather(const Rows& x, const float* E, int K, const long long* idx, const RowsOut& q,
+                         float* loss_out, float* partial, size_t partial_cap, cudaStream_t st) {
+  const long long n_rows = x.n_rows();
+  const bool train = (MODE == VQSEG_MODE_TRAIN || MODE == VQSEG_MODE_TRAIN_AMP);
+  const bool want_loss = train && loss_out != nullptr;
+  int n_partial = 0;
+  if (x.sP == 1 && q.sP == 1) {
+    dim3 grid((unsigned)((n_rows + kGTile - 1) / kGTile), (unsigned)((x.D + kGTile - 1) / kGTile));
+    n_partial = (int)(grid.x * grid.y);
+    if (want_loss && (size_t)n_partial > partial_cap) return VQSEG_EWORKSPACE;
+    gather_ste_pxc_kernel<MODE><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr);
+  } else {
+    long long blocks = (n_rows + 7) / 8;
+    long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    n_partial = (int)blocks;
+    if (want_loss && (size_t)n_partial > partial_cap) return VQSEG_EWORKSPACE;
+    gather_ste_generic_kernel<MODE><<<(unsigned)blocks, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr);
+  }
+  VQSEG_LAUNCH_CHECK();
+  if (want_loss) {
+    loss_finalize_kernel<<<1, 256, 0, st>>>(partial, n_partial, 1.0 / ((double)n_rows * (double)x.D), loss_out);
+    VQSEG_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// =================================================================================================
+// backward w.r.t. x of the training forward (autograd through vq_img.py:236-240)
+// gx = g_q + coef * (x - q_ste),  coef = coef_scale * (*coef_dev)
+// =================================================================================================
+struct View { const float* ptr; long long sB, sP, sD; };
+__global__ void __launch_bounds__(256) ste_bwd_kernel(View g, View x, View q, const float* __restrict__ coef_dev,
+                                                      float coef_scale, RowsOut o, bool px_fast) {
+  const long long total = o.B * o.P * o.D;
+  const float coef = coef_dev ? coef_scale * __ldg(coef_dev) : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long b, p, d;
+    if (px_fast) { p = i % o.P; long long t = i / o.P; d = t % o.D; b = t / o.D; }
+    else         { d = i % o.D; long long t = i / o.D; p = t % o.P; b = t / o.P; }
+    float gv = g.ptr ? __ldg(g.ptr + b * g.sB + p * g.sP + d * g.sD) : 0.f;
+    float r = gv;
+    if (coef_dev) {
+      float xv = __ldg(x.ptr + b * x.sB + p * x.sP + d * x.sD);
+      float qv = __ldg(q.ptr + b * q.sB + p * q.sP + d * q.sD);
+      r = __fmaf_rn(coef, __fsub_rn(xv, qv), gv);
+    }
+    o.ptr[b * o.sB + p * o.sP + d * o.sD] = r;
+  }
+}
+
+// gE[idx[n], :] += g[n, :]   (eval-mode gather backward; the reference's one_hot matmul gives the
+// codebook a gradient only in eval mode, SURVEY.md §8b "autograd contract")
+__global__ void __launch_bounds__(256) gather_bwd_codebook_kernel(Rows g, const long long* __restrict__ idx,
+                                                                  float* __restrict__ gE, int K) {
+  const int D = (int)g.D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_rows = g.n_rows();
+  for (long long n = (long long)blockIdx.x * 8 + warp; n < n_rows; n += (long long)gridDim.x * 8) {
+    long long k = idx[n];
+    if (k < 0 || k >= K) continue;
+    const float* gr = g.row(n);
+    for (int d = lane; d < D; d += 32) atomicAdd(gE + k * D + d, gr[(long long)d * g.sD]);
+  }
+}
+
+// =================================================================================================
+// per-code statistics      (batched_bincount vq_img.py:22-27,:42; scatter_add_ :47-51)
+// =================================================================================================
+// fast path: fp32 atomics (RED.ADD.F32), order not fixed.
+__global__ void __launch_bounds__(256) code_stats_atomic_kernel(Rows x, const long long* __restrict__ idx, int K,
+                                                                unsigned long long* __restrict__ counts,
+                                                                float* __restrict__ sums, bool px_fast) {
+  const long long n_rows = x.n_rows();
+  const int D = (int)x.D;
+  const long long total = n_rows * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long n; int d;
+    if (px_fast) {     // consecutive threads -> consecutive pixels of one image at fixed d
+      long long p = i % x.P; long long t = i / x.P; d = (int)(t % D); long long b = t / D; n = b * x.P + p;
+    } else { d = (int)(i % D); n = i / D; }
+    long long k = idx[n];
+    if (k < 0 || k >= K) continue;
+    atomicAdd(sums + k * D + d, x.row(n)[(long long)d * x.sD]);
+    if (d == 0) atomicAdd(counts + k, 1ull);
+  }
+}
+
+// deterministic path ---------------------------------------------------------------------------
+constexpr int kSortBlock = 1024;   // rows per ranking block
+
+// (1) per-block histogram
+__global__ void __launch_bounds__(1024) stats_hist_kernel(const long long* __restrict__ idx, long long n_rows, int K,
+                                                          int* __restrict__ hist /* [nblk][K] */) {
+  long long n = (long long)blockIdx.x * kSortBlock + threadIdx.x;
+  if (n < n_rows) {
+    long long k = idx[n];
+    if (k >= 0 && k < K) atomicAdd(hist + (long long)blockIdx.x * K + k, 1);
+  }
+}
+// (2) per code: exclusive scan over blocks (in place), total count out
+__global__ void __launch_bounds__(256) stats_scan_blocks_kernel(int* __restrict__ hist, int nblk, int K,
+                                                                unsigned long long* __restrict__ counts,
+                                                                long long* __restrict__ code_total) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  long long run = 0;
+  for (int b = 0; b < nblk; ++b) {
+    int h = hist[(long long)b * K + k];
+    hist[(long long)b * K + k] = (int)run;     // rows per code < 2^31 per rank
+    run += h;
+  }
+  code_total[k] = run;
+  if (counts) atomicAdd(counts + k, (unsigned long long)run);
+}
+// (3) exclusive scan over codes (single block)
+__global__ void __launch_bounds__(1024) stats_scan_codes_kernel(const long long* __restrict__ code_total, int K,
+                                                                long long* __restrict__ code_start /* K+1 */) {
+  __shared__ long long s_part[1024];
+  const int per = (K + 1023) / 1024;
+  const int k0 = threadIdx.x * per;
+  long long s = 0;
+  for (int i = 0; i < per && k0 + i < K; ++i) s += code_total[k0 + i];
+  s_part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int t = 0; t < 1024; ++t) { long long v = s_part[t]; s_part[t] = run; run += v; }
+    code_start[K] = run;
+  }
+  __syncthreads();
+  long long run = s_part[threadIdx.x];
+  for (int i = 0; i < per && k0 + i < K; ++i) { code_start[k0 + i] = run; run += code_total[k0 + i]; }
+}
+// (4) stable scatter: perm[code_start[k] + hist[blk][k] + rank_in_block] = n
+__global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __restrict__ idx, long long n_rows, int K,
+                                                             const int* __restrict__ hist,
+                                                             const long long* __restrict__ code_start,
+                                                             int* __restrict__ perm) {
+  extern __shared__ int s_run[];    // K running counters
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_run[k] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n = (long long)blockIdx.x * kSortBlock + threadIdx.x;
+  long long k = n < n_rows ? idx[n] : -1;
+  const bool valid = k >= 0 && k < K;
+  const int kk = valid ? (int)k : -1 - lane;            // unique key for invalid lanes
+  const unsigned peers = __match_any_sync(0xffffffffu, kk);
+  const int rank_in_warp = __popc(peers & ((1u << lane) - 1));
+  const int group = __popc(peers);
+  const bool leader = rank_in_warp == 0;
+  for (int w = 0; w < 32; ++w) {          // warps take turns in row order -> stable
+    if (warp == w && valid) {
+      int base = s_run[kk];
+      __syncwarp(peers);
+      if (leader) s_run[kk] = base + group;
+      long long pos = code_start[kk] + hist[(long long)blockIdx.x * K + kk] + base + rank_in_warp;
+      perm[pos] = (int)n;
+    }
+    __syncthreads();
+  }
+}
+// (5) ordered per-code sums: one warp per (code, 32-dim slab); ascending-row fp32 chain per (k, d)
+__global__ void __launch_bounds__(256) stats_ordered_sum_kernel(Rows x, const int* __restrict__ perm,
+                                                                const long long* __restrict__ code_start, int K,
+                                                                float* __restrict__ sums) {
+  const int D = (int)x.D;
+  const int slabs = (D + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)K * slabs) return;
+  const int k = (int)(wid / slabs), d = (int)(wid % slabs) * 32 + lane;
+  const long long beg = code_start[k], end = code_start[k + 1];
+  if (d >= D) return;
+  float s = sums[(long long)k * D + d];     // accumulate on top (caller zeroes; ranks chain)
+  long long j = beg;
+  for (; j + 8 <= end; j += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(x.row(perm[j + u]) + (long long)d * x.sD);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
+  }
+  for (; j < end; ++j) s = __fadd_rn(s, __ldg(x.row(perm[j]) + (long long)d * x.sD));
+  sums[(long long)k * D + d] = s;
+}
+
+// means = where(counts==0, means, sums / max(counts,1)) [ + l2norm ]      (vq_img.py:44-45,:53-61)
+__global__ void __launch_bounds__(256) kmeans_finalize_kernel(const float* __restrict__ sums,
+                                                              const long long* __restrict__ counts,
+                                                              float* __restrict__ means, int K, int D, int cosine) {
+  const int lane = threadIdx.x & 31;
+  const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= K) return;
+  const long long c = counts[k];
+  if (c == 0) return;                                   // empty cluster keeps its old mean
+  const float cf = __ll2float_rn(c);
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float m = __fdiv_rn(sums[k * D + d], cf);
+    means[k * D + d] = m;
+    ss = __fmaf_rn(m, m, ss);
+  }
+  if (cosine) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float nrm = fmaxf(__fsqrt_rn(ss), 1e-12f);
+    for (int d = lane; d < D; d += 32) means[k * D + d] = __fdiv_rn(means[k * D + d], nrm);
+  }
+}
+
+__global__ void __launch_bounds__(256) code_usage_kernel(const long long* __restrict__ counts, int K, float* out) {
+  __shared__ int s_red[256];
+  int z = 0;
+  for (int k = threadIdx.x; k < K; k += 256) z += counts[k] == 0;
+  s_red[threadIdx.x] = z;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) *out = __fmul_rn(100.f, __fdiv_rn((float)s_red[0], (float)K));   // 100 * (zero / K)
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(Rows x, const long long* __restrict__ ids, long long n_ids,
+                                                          float* __restrict__ out) {
+  const int D = (int)x.D;
+  const long long total = n_ids * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / D; int d = (int)(i % D);
+    long long n = ids[r];
+    out[i] = (n >= 0 && n < x.n_rows()) ? x.row(n)[(long long)d * x.sD] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_keys_kernel(const unsigned long long* __restrict__ keys, long long n,
+                                                          long long* __restrict__ idx_out, float* __restrict__ dist_out,
+                                                          unsigned long long* __restrict__ counts, long long K) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long key = keys[i];
+    long long k = (long long)(key & 0xffffffffull);
+    if (idx_out) idx_out[i] = k;
+    if (dist_out) dist_out[i] = __uint_as_float((unsigned)(key >> 32));
+    if (counts && k < K) atomicAdd(counts + k, 1ull);
+  }
+}
+
+// F.normalize(x, p=2, dim=-1): x / max(|x|_2, 1e-12), packed (N, D) output    (vq_img.py:7-8)
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(Rows x, float* __restrict__ out) {
+  const int D = (int)x.D;
+  const int lane = threadIdx.x & 31;
+  const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= x.n_rows()) return;
+  const float* xr = x.row(n);
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { float v = xr[(long long)d * x.sD]; ss = __fmaf_rn(v, v, ss); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float nrm = fmaxf(__fsqrt_rn(ss), 1e-12f);
+  for (int d = lane; d < D; d += 32) out[n * D + d] = __fdiv_rn(xr[(long long)d * x.sD], nrm);
+}
+
+// first argmax_k <x_n, e_k>: one warp per row, lanes over codes, sequential FMA chain over d
+__global__ void __launch_bounds__(256) assign_cosine_kernel(const float* __restrict__ xn, long long N, int D,
+                                                            const float* __restrict__ E, int K,
+                                                            long long* __restrict__ idx_out,
+                                                            unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) float s_x[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* xs = s_x + (size_t)warp * D;
+  for (long long n = (long long)blockIdx.x * 8 + warp; n < N; n += (long long)gridDim.x * 8) {
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) xs[d] = xn[n * D + d];
+    __syncwarp();
+    float best = -__int_as_float(0x7f800000);
+    int best_k = 0x7fffffff;
+    for (int k = lane; k < K; k += 32) {
+      const float* er = E + (long long)k * D;
+      float t = 0.f;
+      for (int d = 0; d < D; ++d) t = __fmaf_rn(xs[d], __ldg(er + d), t);
+      if (t > best || (t == best && k < best_k)) { best = t; best_k = k; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+      int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
+      if (b2 > best || (b2 == best && k2 < best_k)) { best = b2; best_k = k2; }
+    }
+    if (lane == 0) {
+      if (best_k == 0x7fffffff) best_k = 0;
+      idx_out[n] = best_k;
+      if (counts) atomicAdd(counts + best_k, 1ull);
+    }
+  }
+}
+
+static inline unsigned grid_for(long long total, int threads, int waves = 8) {
+  long long blocks = (total + threads - 1) / threads;
+  long long cap = (long long)num_sms() * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace vqseg
+
+using namespace vqseg;
+
+extern "C" {
+
+size_t vqseg_gather_workspace_bytes(int64_t n_rows, int64_t D) {
+  long long tiles = ((n_rows + kGTile - 1) / kGTile) * ((D + kGTile - 1) / kGTile);
+  long long generic = (long long)num_sms() * 16;
+  long long n = tiles > generic ? tiles : generic;
+  return (size_t)round_up(n * sizeof(float), 256);
+}
+
+int vqseg_gather_ste_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                         const float* E, int64_t K, const int64_t* idx,
+                         float* q_out, int64_t qB, int64_t qP, int64_t qD,
+                         float* loss_out, int mode, void* ws, size_t ws_bytes, void* stream) {
+  if (!E || !idx || !q_out || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
+  const bool train = mode == VQSEG_MODE_TRAIN || mode == VQSEG_MODE_TRAIN_AMP;
+  if (train && !x) return VQSEG_EINVAL;
+  if (B * P == 0) return 0;
+  Rows xr{x, B, P, D, sB, sP, sD};
+  if (!train) { xr.ptr = nullptr; xr.sB = qB; xr.sP = qP; xr.sD = qD; }
+  RowsOut qr{q_out, B, P, D, qB, qP, qD};
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = (float*)ws;
+  size_t cap = ws ? ws_bytes / sizeof(float) : 0;
+  const long long* ix = (const long long*)idx;
+  switch (mode) {
+    case VQSEG_MODE_EVAL:      return launch_gather<VQSEG_MODE_EVAL>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st);
+    case VQSEG_MODE_EVAL_AMP:  return launch_gather<VQSEG_MODE_EVAL_AMP>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st);
+    case VQSEG_MODE_TRAIN:     return launch_gather<VQSEG_MODE_TRAIN>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st);
+    case VQSEG_MODE_TRAIN_AMP: return launch_gather<VQSEG_MODE_TRAIN_AMP>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st);
+  }
+  return VQSEG_EINVAL;
+}
+
+int vqseg_ste_bwd_f32(const float* g_q, int64_t gB, int64_t gP, int64_t gD,
+                      const float* x, int64_t sB, int64_t sP, int64_t sD,
+                      const float* q_ste, int64_t qB, int64_t qP, int64_t qD,
+                      const float* coef_dev, float coef_scale,
+                      float* gx, int64_t oB, int64_t oP, int64_t oD,
+                      int64_t B, int64_t P, int64_t D, void* stream) {
+  if (!gx || B < 0 || P < 0 || D <= 0) return VQSEG_EINVAL;
+  if (coef_dev && (!x || !q_ste)) return VQSEG_EINVAL;
+  if (B * P == 0) return 0;
+  View g{g_q, gB, gP, gD}, xv{x, sB, sP, sD}, qv{q_ste, qB, qP, qD};
+  RowsOut o{gx, B, P, D, oB, oP, oD};
+  bool px_fast = (oP == 1);
+  ste_bwd_kernel<<<grid_for(B * P * D, 256, 16), 256, 0, (cudaStream_t)stream>>>(g, xv, qv, coef_dev, coef_scale, o, px_fast);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int vqseg_gather_bwd_codebook_f32(const float* g_q, int64_t B, int64_t P, int64_t D, int64_t gB, int64_t gP, int64_t gD,
+                                  const int64_t* idx, float* gE, int64_t K, void* stream) {
+  if (!g_q || !idx || !gE || D <= 0 || K <= 0) return VQSEG_EINVAL;
+  if (B * P == 0) return 0;
+  Rows g{g_q, B, P, D, gB, gP, gD};
+  gather_bwd_codebook_kernel<<<grid_for(B * P * 32, 256, 16), 256, 0, (cudaStream_t)stream>>>(g, (const long long*)idx, gE, (int)K);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int deterministic) {
+  (void)D;
+  if (!deterministic) return 256;
+  long long nblk = (n_rows + kSortBlock - 1) / kSortBlock;
+  size_t b = 0;
+  b += round_up(nblk * K * sizeof(int), 256);          // hist
+  b += round_up(K * sizeof(long long), 256);           // code_total
+  b += round_up((K + 1) * sizeof(long long), 256);     // code_start
+  b += round_up(n_rows * sizeof(int), 256);            // perm
+  return b + 256;
+}
+
+int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                         const int64_t* idx, int64_t K, int64_t* counts, float* sums, int deterministic,
+                         void* ws, size_t ws_bytes, void* stream) {
+  if (!x || !idx || !counts || !sums || D <= 0 || K <= 0 || B < 0 || P < 0) return VQSEG_EINVAL;
+  const long long n_rows = B * P;
+  if (n_rows == 0) return 0;
+  if (n_rows >= (1ll << 31)) return VQSEG_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  Rows xr{x, B, P, D, sB, sP, sD};
+  if (!deterministic) {
+    code_stats_atomic_kernel<<<grid_for(n_rows * D, 256, 16), 256, 0, st>>>(xr, (const long long*)idx, (int)K,
+                                                                            (unsigned long long*)counts, sums, sP == 1);
+    VQSEG_LAUNCH_CHECK();
+    return 0;
+  }
+  if (ws_bytes < vqseg_code_stats_workspace_bytes(n_rows, D, K, 1) || !ws) return VQSEG_EWORKSPACE;
+  if (K * sizeof(int) > 200 * 1024) return VQSEG_EUNSUPPORTED;
+  const long long nblk = (n_rows + kSortBlock - 1) / kSortBlock;
+  char* p = (char*)ws;
+  int* hist = (int*)p;                    p += round_up(nblk * K * sizeof(int), 256);
+  long long* code_total = (long long*)p;  p += round_up(K * sizeof(long long), 256);
+  long long* code_start = (long long*)p;  p += round_up((K + 1) * sizeof(long long), 256);
+  int* perm = (int*)p;
+  cudaError_t e = cudaMemsetAsync(hist, 0, nblk * K * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  stats_hist_kernel<<<(unsigned)nblk, kSortBlock, 0, st>>>((const long long*)idx, n_rows, (int)K, hist);
+  VQSEG_LAUNCH_CHECK();
+  stats_scan_blocks_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(hist, (int)nblk, (int)K,
+                                                                         (unsigned long long*)counts, code_total);
+  VQSEG_LAUNCH_CHECK();
+  stats_scan_codes_kernel<<<1, 1024, 0, st>>>(code_total, (int)K, code_start);
+  VQSEG_LAUNCH_CHECK();
+  size_t smem = (size_t)K * sizeof(int);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    e = cudaFuncSetAttribute(stats_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>((const long long*)idx, n_rows, (int)K, hist, code_start, perm);
+  VQSEG_LAUNCH_CHECK();
+  const long long warps = K * ((D + 31) / 32);
+  stats_ordered_sum_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(xr, perm, code_start, (int)K, sums);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int vqseg_kmeans_finalize_f32(const float* sums, const int64_t* counts, float* means_inout, int64_t K, int64_t D,
+                              int cosine, void* stream) {
+  if (!sums || !counts || !means_inout || K <= 0 || D <= 0) return VQSEG_EINVAL;
+  kmeans_finalize_kernel<<<(unsigned)((K * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      sums, (const long long*)counts, means_inout, (int)K, (int)D, cosine);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int vqseg_code_usage(const int64_t* counts, int64_t K, float* usage_out, void* stream) {
+  if (!counts || !usage_out || K <= 0) return VQSEG_EINVAL;
+  code_usage_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const long long*)counts, (int)K, usage_out);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int vqseg_gather_rows_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                          const int64_t* row_ids, int64_t n_ids, float* out, void* stream) {
+  if (!x || !row_ids || !out || D <= 0) return VQSEG_EINVAL;
+  if (n_ids == 0) return 0;
+  Rows xr{x, B, P, D, sB, sP, sD};
+  gather_rows_kernel<<<grid_for(n_ids * D, 256), 256, 0, (cudaStream_t)stream>>>(xr, (const long long*)row_ids, n_ids, out);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int vqseg_unpack_keys(const uint64_t* keys, int64_t n, int64_t* idx_out, float* dist_out, int64_t* counts_out,
+                      int64_t K, void* stream) {
+  if (!keys || n < 0) return VQSEG_EINVAL;
+  if (n == 0) return 0;
+  unpack_keys_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned long long*)keys, n, (long long*)idx_out, dist_out, (unsigned long long*)counts_out, K);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int vqseg_l2norm_rows_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                          float* out, void* stream) {
+  if (!x || !out || D <= 0) return VQSEG_EINVAL;
+  if (B * P == 0) return 0;
+  Rows xr{x, B, P, D, sB, sP, sD};
+  l2norm_rows_kernel<<<(unsigned)((B * P * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xr, out);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int vqseg_assign_cosine_f32(const float* xn, int64_t N, int64_t D, const float* E, int64_t K,
+                            int64_t* idx_out, int64_t* counts_out, void* stream) {
+  if (!xn || !E || !idx_out || D <= 0 || K <= 0) return VQSEG_EINVAL;
+  if (N == 0) return 0;
+  size_t smem = 8 * (size_t)D * sizeof(float);
+  if (smem > 200 * 1024) return VQSEG_EUNSUPPORTED;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(assign_cosine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  assign_cosine_kernel<<<grid_for(N * 32, 256), 256, smem, (cudaStream_t)stream>>>(
+      xn, N, (int)D, E, (int)K, (long long*)idx_out, (unsigned long long*)counts_out);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+"""torch.library custom ops over the libvqseg C ABI + the straight-through autograd.Function.
+
+Every op takes latent vectors as a logical (B, P, D) tensor with arbitrary strides -- the view
+`rearrange(x, 'b c h w -> b (h w) c')` of the reference (vq_img.py:232) -- so NCHW feature maps are
+consumed in place, never copied.  All ops run on the current CUDA stream and never synchronise.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native
+
+ALGO_AUTO, ALGO_EXACT, ALGO_TC = 0, 1, 2
+MODE_EVAL, MODE_TRAIN, MODE_TRAIN_AMP, MODE_EVAL_AMP = 0, 1, 2, 3
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vq_seg_b200 kernels run on a B200 GPU only; got a CPU tensor "
+                               "(there is no CPU fallback)")
+
+
+def _bpd(t: torch.Tensor):
+    assert t.dim() == 3, "expected a (B, P, D) view"
+    return (t.shape[0], t.shape[1], t.shape[2], t.stride(0), t.stride(1), t.stride(2))
+
+
+def _aligned_bytes(nbytes: int, device) -> torch.Tensor:
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+# -------------------------------------------------------------------------------------------------
+@torch.library.custom_op("vqseg::prepare_codebook", mutates_args=())
+def prepare_codebook(codebook: torch.Tensor) -> torch.Tensor:
+    """fp32 |e|^2 (torch CPU summation order) + fp16 tcgen05 operand image; see vqseg.h."""
+    _require_cuda(codebook)
+    L = _native.lib()
+    cb = codebook.detach().contiguous().float()
+    k, d = cb.shape
+    n = L.vqseg_codebook_blob_bytes(k, d)
+    blob = _aligned_bytes(n, cb.device)
+    with torch.cuda.device(cb.device):
+        _native.check(L.vqseg_codebook_prepare_f32(cb.data_ptr(), k, d, blob.data_ptr(), n, _stream()), "codebook_prepare")
+    return blob
+
+
+@prepare_codebook.register_fake
+def _(codebook):
+    k, d = codebook.shape
+    kp, dp = (k + 255) // 256 * 256, (d + 63) // 64 * 64
+    return codebook.new_empty(1024 + ((2 * kp * 4 + 1023) // 1024) * 1024 + kp * dp * 2, dtype=torch.uint8)
+
+
+@torch.library.custom_op("vqseg::assign", mutates_args=())
+def assign(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], algo: int = 0,
+           kblock: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(idx (B,P) int64, counts (K,) int64): first-index argmin of the reference's fp32 cdist."""
+    _require_cuda(x, codebook, blob)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    cb = codebook.detach().contiguous().float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    k = cb.shape[0]
+    if cb.shape[1] != d:
+        raise RuntimeError(f"X1 and X2 must have the same number of columns. X1: {d} X2: {cb.shape[1]}")
+    idx = torch.empty((b, p), dtype=torch.int64, device=x.device)
+    counts = torch.zeros(k, dtype=torch.int64, device=x.device)
+    nws = L.vqseg_assign_workspace_bytes(b * p, d, k, algo)
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_assign_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
+                                         blob.data_ptr() if blob is not None else None,
+                                         idx.data_ptr(), counts.data_ptr(), None, 0, kblock, algo,
+                                         ws.data_ptr(), nws, _stream()), "assign")
+    return idx, counts
+
+
+@assign.register_fake
+def _(x, codebook, blob, algo=0, kblock=0):
+    return (x.new_empty((x.shape[0], x.shape[1]), dtype=torch.int64),
+            x.new_empty((codebook.shape[0],), dtype=torch.int64))
+
+
+@torch.library.custom_op("vqseg::assign_keys", mutates_args=())
+def assign_keys(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], code_base: int,
+                algo: int = 0, kblock: int = 0) -> torch.Tensor:
+    """Sharded mode: per row the packed key (float_bits(dist) << 32 | code_base + local idx) as int64."""
+    _require_cuda(x, codebook, blob)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    cb = codebook.detach().contiguous().float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    k = cb.shape[0]
+    keys = torch.empty((b, p), dtype=torch.int64, device=x.device)
+    nws = L.vqseg_assign_workspace_bytes(b * p, d, k, algo)
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_assign_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
+                                         blob.data_ptr() if blob is not None else None,
+                                         None, None, keys.data_ptr(), code_base, kblock, algo,
+                                         ws.data_ptr(), nws, _stream()), "assign_keys")
+    return keys
+
+
+@assign_keys.register_fake
+def _(x, codebook, blob, code_base, algo=0, kblock=0):
+    return x.new_empty((x.shape[0], x.shape[1]), dtype=torch.int64)
+
+
+@torch.library.custom_op("vqseg::unpack_keys", mutates_args=())
+def unpack_keys(keys: torch.Tensor, num_codes: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    _require_cuda(keys)
+    L = _native.lib()
+    keys = keys.contiguous()
+    n = keys.numel()
+    idx = torch.empty(keys.shape, dtype=torch.int64, device=keys.device)
+    dist = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
+    counts = torch.zeros(num_codes, dtype=torch.int64, device=keys.device)
+    with torch.cuda.device(keys.device):
+        _native.check(L.vqseg_unpack_keys(keys.data_ptr(), n, idx.data_ptr(), dist.data_ptr(), counts.data_ptr(),
+                                          num_codes, _stream()), "unpack_keys")
+    return idx, dist, counts
+
+
+@unpack_keys.register_fake
+def _(keys, num_codes):
+    return (keys.new_empty(keys.shape), keys.new_empty(keys.shape, dtype=torch.float32),
+            keys.new_empty((num_codes,)))
+
+
+@torch.library.custom_op("vqseg::gather_ste", mutates_args=())
+def gather_ste(x: torch.Tensor, codebook: torch.Tensor, idx: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(q (B,P,D) laid out like an NCHW map, mse (1,)): E[idx] (eval) or x + (E[idx] - x) (train)
+    and mean((q - x)^2) in one pass."""
+    _require_cuda(x, codebook, idx)
+    L = _native.lib()
+    cb = codebook.detach().contiguous().float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    k = cb.shape[0]
+    # output in the layout of the NCHW map the module returns: memory (B, D, P), logical (B, P, D)
+    q = torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=x.device)
+    loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+    nws = L.vqseg_gather_workspace_bytes(b * p, d)
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+    idx = idx.contiguous()
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_gather_ste_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k, idx.data_ptr(),
+                                             q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+                                             loss.data_ptr(), mode, ws.data_ptr(), nws, _stream()), "gather_ste")
+    return q, loss
+
+
+@gather_ste.register_fake
+def _(x, codebook, idx, mode):
+    b, p, d = x.shape
+    return (torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=x.device),
+            x.new_empty((1,), dtype=torch.float32))
+
+
+@torch.library.custom_op("vqseg::ste_bwd", mutates_args=())
+def ste_bwd(grad_q: Optional[torch.Tensor], x: torch.Tensor, q_ste: torch.Tensor,
+            grad_mse: Optional[torch.Tensor], coef_scale: float) -> torch.Tensor:
+    """gx = grad_q + coef_scale * grad_mse * (x - q_ste)   (coef_scale = 2 / numel)."""
+    _require_cuda(x, q_ste, grad_q, grad_mse)
+    L = _native.lib()
+    b, p, d, sb, sp, sd = _bpd(x)
+    gx = torch.empty_strided(x.shape, x.stride(), dtype=torch.float32, device=x.device) \
+        if x.is_non_overlapping_and_dense() else torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    gq = grad_q
+    if gq is not None and gq.dtype != torch.float32:
+        gq = gq.float()
+    g = (gq.data_ptr(), gq.stride(0), gq.stride(1), gq.stride(2)) if gq is not None else (None, 0, 0, 0)
+    gm = grad_mse.reshape(-1)[:1].float().contiguous() if grad_mse is not None else None
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_ste_bwd_f32(g[0], g[1], g[2], g[3], x.data_ptr(), sb, sp, sd,
+                                          q_ste.data_ptr(), q_ste.stride(0), q_ste.stride(1), q_ste.stride(2),
+                                          gm.data_ptr() if gm is not None else None, coef_scale,
+                                          gx.data_ptr(), gx.stride(0), gx.stride(1), gx.stride(2),
+                                          b, p, d, _stream()), "ste_bwd")
+    return gx
+
+
+@ste_bwd.register_fake
+def _(grad_q, x, q_ste, grad_mse, coef_scale):
+    return torch.empty_like(x, dtype=torch.float32)
+
+
+@torch.library.custom_op("vqseg::gather_bwd_codebook", mutates_args=())
+def gather_bwd_codebook(grad_q: torch.Tensor, idx: torch.Tensor, num_codes: int) -> torch.Tensor:
+    _require_cuda(grad_q, idx)
+    L = _native.lib()
+    gq = grad_q.float()
+    b, p, d, sb, sp, sd = _bpd(gq)
+    ge = torch.zeros((num_codes, d), dtype=torch.float32, device=gq.device)
+    idx = idx.contiguous()
+    with torch.cuda.device(gq.device):
+        _native.check(L.vqseg_gather_bwd_codebook_f32(gq.data_ptr(), b, p, d, sb, sp, sd, idx.data_ptr(),
+                                                      ge.data_ptr(), num_codes, _stream()), "gather_bwd_codebook")
+    return ge
+
+
+@gather_bwd_codebook.register_fake
+def _(grad_q, idx, num_codes):
+    return grad_q.new_empty((num_codes, grad_q.shape[2]), dtype=torch.float32)
+
+
+@torch.library.custom_op("vqseg::code_stats", mutates_args=())
+def code_stats(x: torch.Tensor, idx: torch.Tensor, num_codes: int, deterministic: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(counts (K,) int64, sums (K, D) fp32) of the rows assigned to each code."""
+    _require_cuda(x, idx)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    counts = torch.zeros(num_codes, dtype=torch.int64, device=x.device)
+    sums = torch.zeros((num_codes, d), dtype=torch.float32, device=x.device)
+    nws = L.vqseg_code_stats_workspace_bytes(b * p, d, num_codes, int(deterministic))
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+    idx = idx.contiguous()
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_code_stats_f32(x.data_ptr(), b, p, d, sb, sp, sd, idx.data_ptr(), num_codes,
+                                             counts.data_ptr(), sums.data_ptr(), int(deterministic),
+                                             ws.data_ptr(), nws, _stream()), "code_stats")
+    return counts, sums
+
+
+@code_stats.register_fake
+def _(x, idx, num_codes, deterministic=True):
+    return x.new_empty((num_codes,), dtype=torch.int64), x.new_empty((num_codes, x.shape[2]), dtype=torch.float32)
+
+
+@torch.library.custom_op("vqseg::kmeans_finalize", mutates_args=("means",))
+def kmeans_finalize(sums: torch.Tensor, counts: torch.Tensor, means: torch.Tensor, cosine: bool = False) -> None:
+    _require_cuda(sums, counts, means)
+    L = _native.lib()
+    assert means.is_contiguous() and sums.is_contiguous() and counts.is_contiguous()
+    k, d = means.shape
+    with torch.cuda.device(means.device):
+        _native.check(L.vqseg_kmeans_finalize_f32(sums.data_ptr(), counts.data_ptr(), means.data_ptr(), k, d,
+                                                  int(cosine), _stream()), "kmeans_finalize")
+
+
+@torch.library.custom_op("vqseg::code_usage", mutates_args=())
+def code_usage(counts: torch.Tensor) -> torch.Tensor:
+    """0-dim fp32: percent of UNUSED codes (vq_img.py:173-175)."""
+    _require_cuda(counts)
+    L = _native.lib()
+    counts = counts.contiguous()
+    out = torch.empty((), dtype=torch.float32, device=counts.device)
+    with torch.cuda.device(counts.device):
+        _native.check(L.vqseg_code_usage(counts.data_ptr(), counts.numel(), out.data_ptr(), _stream()), "code_usage")
+    return out
+
+
+@code_usage.register_fake
+def _(counts):
+    return counts.new_empty((), dtype=torch.float32)
+
+
+@torch.library.custom_op("vqseg::gather_rows", mutates_args=())
+def gather_rows(x: torch.Tensor, row_ids: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, row_ids)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    ids = row_ids.to(torch.int64).contiguous()
+    out = torch.empty((ids.numel(), d), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_gather_rows_f32(x.data_ptr(), b, p, d, sb, sp, sd, ids.data_ptr(), ids.numel(),
+                                              out.data_ptr(), _stream()), "gather_rows")
+    return out
+
+
+@gather_rows.register_fake
+def _(x, row_ids):
+    return x.new_empty((row_ids.numel(), x.shape[2]), dtype=torch.float32)
+
+
+@torch.library.custom_op("vqseg::l2norm_rows", mutates_args=())
+def l2norm_rows(x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(x, dim=-1) packed as (B, P, D) contiguous."""
+    _require_cuda(x)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    out = torch.empty((b, p, d), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_l2norm_rows_f32(x.data_ptr(), b, p, d, sb, sp, sd, out.data_ptr(), _stream()), "l2norm_rows")
+    return out
+
+
+@l2norm_rows.register_fake
+def _(x):
+    return x.new_empty(x.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("vqseg::assign_cosine", mutates_args=())
+def assign_cosine(xn: torch.Tensor, codebook: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _require_cuda(xn, codebook)
+    L = _native.lib()
+    xn = xn.contiguous().float()
+    cb = codebook.detach().contiguous().float()
+    b, p, d = xn.shape
+    k = cb.shape[0]
+    idx = torch.empty((b, p), dtype=torch.int64, device=xn.device)
+    counts = torch.zeros(k, dtype=torch.int64, device=xn.device)
+    with torch.cuda.device(xn.device):
+        _native.check(L.vqseg_assign_cosine_f32(xn.data_ptr(), b * p, d, cb.data_ptr(), k, idx.data_ptr(),
+                                                counts.data_ptr(), _stream()), "assign_cosine")
+    return idx, counts
+
+
+@assign_cosine.register_fake
+def _(xn, codebook):
+    return xn.new_empty(xn.shape[:2], dtype=torch.int64), xn.new_empty((codebook.shape[0],), dtype=torch.int64)
+
+
+# -------------------------------------------------------------------------------------------------
+class _StraightThrough(torch.autograd.Function):
+    """Training forward of vq_img.py:235-240: q_ste = x + (E[idx] - x), mse = mean((q_ste - x)^2).
+    Gradients: d q_ste / dx = I (straight-through), d mse / dx = 2 (x - q_ste) / numel; the codebook
+    gets none (the reference detaches it)."""
+
+    @staticmethod
+    def forward(ctx, x, codebook, idx, mode):
+        q, mse = gather_ste(x, codebook, idx, mode)
+        ctx.save_for_backward(x, q)
+        ctx.mark_non_differentiable(idx)
+        return q, mse
+
+    @staticmethod
+    def backward(ctx, grad_q, grad_mse):
+        x, q = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        gx = ste_bwd(grad_q, x, q, grad_mse, 2.0 / x.numel())
+        return gx, None, None, None
+
+
+class _EvalGather(torch.autograd.Function):
+    """Eval forward: q = E[idx].  Like the reference's one_hot matmul (vq_img.py:169-170) the gradient
+    goes to the codebook only."""
+
+    @staticmethod
+    def forward(ctx, codebook, x_like, idx, mode):
+        q, _ = gather_ste(x_like, codebook, idx, mode)
+        ctx.save_for_backward(idx)
+        ctx.num_codes = codebook.shape[0]
+        return q
+
+    @staticmethod
+    def backward(ctx, grad_q):
+        (idx,) = ctx.saved_tensors
+        ge = gather_bwd_codebook(grad_q, idx, ctx.num_codes) if ctx.needs_input_grad[0] else None
+        return ge, None, None, None
+
+
+def straight_through(x, codebook, idx, amp_fp16=False):
+    return _StraightThrough.apply(x, codebook, idx, MODE_TRAIN_AMP if amp_fp16 else MODE_TRAIN)
+
+
+def eval_gather(codebook, x_like, idx, amp_fp16=False):
+    return _EvalGather.apply(codebook, x_like, idx, MODE_EVAL_AMP if amp_fp16 else MODE_EVAL)

@@ -1,0 +1,218 @@
+"""Drop-in replacement of VQ_SEG's vector_quantizer/vq_img.py on B200.
+
+Same classes, constructor arguments (names, order, defaults), attributes, state_dict keys and
+forward outputs as the reference:
+
+    VectorQuantizer(dim, num_embeddings, embedding_dim=None, decay=0.8, eps=1e-5, kmeans_init=False,
+                    kmeans_iters=10, distance='euclidean', commitment_weight=1, num_codebook=1)
+    forward(x: (B,C,H,W)) -> (quantize (B,C,H,W) fp32, embed_index (B,H,W) int64,
+                              loss (1,) fp32 [requires_grad == training], code_usage () fp32)
+
+(reference: vq_img.py:193-244; EuclideanCodebook :133-190; CosinesimCodebook :65-130; kmeans :29-63).
+The arithmetic runs in hand-written sm_100a kernels (libvqseg.so) through torch.library custom ops;
+there is no CPU path: CPU tensors raise.
+"""
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+
+__all__ = ["VectorQuantizer", "EuclideanCodebook", "CosinesimCodebook", "kmeans", "sample_vectors",
+           "batched_sample_vectors", "batched_bincount", "l2norm"]
+
+
+def l2norm(t: torch.Tensor) -> torch.Tensor:
+    """vq_img.py:7-8.  (B, P, D) -> packed unit rows."""
+    lead = t.shape[:-1]
+    return ops.l2norm_rows(t.reshape(1, -1, t.shape[-1]) if t.dim() != 3 else t).reshape(*lead, t.shape[-1])
+
+
+def sample_vectors(sample: torch.Tensor, num: int, indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """vq_img.py:10-17: randperm(N)[:num] rows if N >= num, else randint with replacement.
+    `indices` injects the choice (the device RNG stream differs from the CPU one)."""
+    num_samples, device = sample.shape[0], sample.device
+    if indices is None:
+        if num_samples >= num:
+            indices = torch.randperm(num_samples, device=device)[:num]
+        else:
+            indices = torch.randint(0, num_samples, (num,), device=device)
+    return ops.gather_rows(sample.unsqueeze(0), indices.to(device))
+
+
+def batched_sample_vectors(samples: torch.Tensor, num: int) -> torch.Tensor:
+    """vq_img.py:19-20"""
+    return torch.stack([sample_vectors(s, num) for s in samples.unbind(dim=0)], dim=0)
+
+
+def batched_bincount(x: torch.Tensor, minlength: int) -> torch.Tensor:
+    """vq_img.py:22-27 for (1, N) int64 input -> (1, minlength) int64."""
+    return torch.stack([ops.unpack_keys(row, minlength)[2] for row in x.unbind(dim=0)], dim=0)
+
+
+def kmeans(flatten_x: torch.Tensor, num_clusters: int, num_iters: int, use_cosine_sim: bool = False,
+           init_indices: Optional[torch.Tensor] = None, deterministic: bool = True, algo: int = ops.ALGO_AUTO,
+           reduce_fn=None):
+    """Lloyd iterations of vq_img.py:29-63 on the (B, P, D) view (or (N, D) samples) WITHOUT copying it.
+
+    Per iteration: fused distance+argmin (tcgen05 filter + exact rescoring), per-code counts and
+    ordered per-code sums, then means = where(count==0, means, sums/count) [l2norm if cosine].
+    `reduce_fn(counts, sums)` is the data-parallel hook: it must all-reduce both in place
+    (vq_seg_b200.distributed.allreduce_code_stats).  Returns (means (1,K,D), bins (1,K) int64) like the
+    reference; bins belong to the LAST assignment."""
+    x = flatten_x if flatten_x.dim() == 3 else flatten_x.reshape(1, -1, flatten_x.shape[-1])
+    x = x.detach()
+    n = x.shape[0] * x.shape[1]
+    if init_indices is None:
+        if n >= num_clusters:
+            init_indices = torch.randperm(n, device=x.device)[:num_clusters]
+        else:
+            init_indices = torch.randint(0, n, (num_clusters,), device=x.device)
+    means = ops.gather_rows(x, init_indices.to(x.device))
+    bins = torch.zeros(num_clusters, dtype=torch.int64, device=x.device)
+    for _ in range(num_iters):
+        if use_cosine_sim:
+            buckets, _ = ops.assign_cosine(x, means)
+        else:
+            blob = ops.prepare_codebook(means) if algo != ops.ALGO_EXACT else None
+            buckets, _ = ops.assign(x, means, blob, algo)
+        bins, sums = ops.code_stats(x, buckets, num_clusters, deterministic)
+        if reduce_fn is not None:
+            reduce_fn(bins, sums)
+        ops.kmeans_finalize(sums, bins, means, use_cosine_sim)
+    return means.unsqueeze(0), bins.unsqueeze(0)
+
+
+class _CodebookBase(nn.Module):
+    """Shared constructor of EuclideanCodebook (vq_img.py:134-159) / CosinesimCodebook (:66-92)."""
+
+    def __init__(self, embedding_dim, num_embeddings, kmeans_init, kmeans_iters, decay, eps, num_codebook):
+        super().__init__()
+        self.kmeans_init = kmeans_init
+        self.kmeans_iters = kmeans_iters
+        self.initted = False                    # plain attribute, NOT in the state_dict (like the reference)
+        self.num_codebook = num_codebook
+        self.decay = decay                      # accepted and stored, never read (the reference has no EMA)
+        self.embedding = nn.Embedding(num_embeddings, embedding_dim)
+        self.num_embeddings = num_embeddings
+        self.embedding_dim = embedding_dim
+        if not kmeans_init:
+            self.embedding.weight.data.uniform_(-1 / self.num_embeddings, 1 / self.num_embeddings)
+            self.initted = True
+        # B200 knobs (not in the reference signature)
+        self.algo = ops.ALGO_AUTO
+        self.kmeans_init_indices = None         # test hook: inject the k-means init rows
+        self.kmeans_reduce_fn = None            # data-parallel hook: all-reduce (counts, sums)
+        self._blob = None
+        self._blob_key = None
+
+    def _prepared(self):
+        w = self.embedding.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if self._blob is None or self._blob_key != key:
+            self._blob = ops.prepare_codebook(w.detach())
+            self._blob_key = key
+        return self._blob
+
+    def invalidate(self):
+        self._blob = None
+
+    def _kmeans_init(self, flatten_x, cosine):
+        if self.initted:
+            return
+        embed, _ = kmeans(flatten_x, self.num_embeddings, self.kmeans_iters, use_cosine_sim=cosine,
+                          init_indices=self.kmeans_init_indices, reduce_fn=self.kmeans_reduce_fn, algo=self.algo)
+        self.embedding.weight.data.copy_(embed[0])
+        self.invalidate()                       # .data.copy_ does not bump the version counter
+        self.initted = True
+
+
+class EuclideanCodebook(_CodebookBase):
+    def lookup(self, x: torch.Tensor):
+        """(idx (B,P) int64, counts (K,) int64) -- cdist + argmin + bincount of vq_img.py:167-168,173."""
+        if x.shape[-1] != self.embedding_dim:
+            raise RuntimeError(f"X1 and X2 must have the same number of columns. X1: {x.shape[-1]} X2: {self.embedding_dim}")
+        blob = self._prepared() if self.algo != ops.ALGO_EXACT else None
+        return ops.assign(x, self.embedding.weight.detach(), blob, self.algo)
+
+    def forward(self, x):
+        """x: (B, HxW, C) -> (quantized (B,HW,C), embed_idx (B,HW), code_usage)   [vq_img.py:160-177]"""
+        x = x.float()
+        if x.dim() != 3:
+            x = x.reshape(x.shape[0], -1, x.shape[-1])
+        if self.kmeans_init and self.training:
+            self._kmeans_init(x, cosine=False)
+        idx, counts = self.lookup(x)
+        quantized = ops.eval_gather(self.embedding.weight, x, idx)
+        return quantized, idx, ops.code_usage(counts)
+
+
+class CosinesimCodebook(_CodebookBase):
+    def forward(self, x):
+        """vq_img.py:93-113: l2norm(x); in-place renormalise the weights EVERY forward (:100); argmax of
+        the cosine similarity; gather."""
+        x = x.float()
+        if x.dim() != 3:
+            x = x.reshape(x.shape[0], -1, x.shape[-1])
+        xn = ops.l2norm_rows(x)
+        if self.kmeans_init and self.training:
+            self._kmeans_init(xn, cosine=True)
+        w = self.embedding.weight
+        w.data.copy_(ops.l2norm_rows(w.data.unsqueeze(0))[0])
+        self.invalidate()
+        idx, counts = ops.assign_cosine(xn, w.detach())
+        quantized = ops.eval_gather(w, x, idx)
+        return quantized, idx, ops.code_usage(counts)
+
+    def lookup(self, x):
+        xn = ops.l2norm_rows(x)
+        w = self.embedding.weight
+        w.data.copy_(ops.l2norm_rows(w.data.unsqueeze(0))[0])
+        self.invalidate()
+        return ops.assign_cosine(xn, w.detach())
+
+
+class VectorQuantizer(nn.Module):
+    def __init__(self, dim, num_embeddings, embedding_dim=None, decay=0.8, eps=1e-5, kmeans_init=False,
+                 kmeans_iters=10, distance='euclidean', commitment_weight=1, num_codebook=1):
+        super().__init__()
+        embedding_dim = embedding_dim if embedding_dim != None else dim  # noqa: E711 (reference spelling)
+        self.num_embeddings = num_embeddings
+        self.eps = eps
+        self.commitment_weight = commitment_weight
+        codebook_dict = {'euclidean': EuclideanCodebook, 'cosine': CosinesimCodebook}
+        codebook_class = codebook_dict[distance]          # KeyError on anything else, like vq_img.py:217
+        self.codebook = codebook_class(embedding_dim=embedding_dim, num_embeddings=num_embeddings,
+                                       kmeans_init=kmeans_init, kmeans_iters=kmeans_iters, decay=decay,
+                                       eps=eps, num_codebook=num_codebook)
+        self.amp_compat = True    # under fp16 autocast round the gathered code through fp16 like the reference's matmul
+
+    def forward(self, x):
+        if x.dim() != 4:
+            raise ValueError(f"VectorQuantizer expects a (B, C, H, W) tensor, got shape {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("vq_seg_b200.VectorQuantizer runs on a B200 GPU only (no CPU fallback); "
+                               "move the module and its input to cuda")
+        x = x.to(torch.float32)
+        b, c, h, w = x.shape
+        device = x.device
+        xv = x.reshape(b, c, h * w).permute(0, 2, 1)          # the 'b c h w -> b (h w) c' VIEW, no copy
+        cb = self.codebook
+        amp16 = bool(self.amp_compat and torch.is_autocast_enabled()
+                     and torch.get_autocast_dtype('cuda') == torch.float16)
+        cosine = isinstance(cb, CosinesimCodebook)
+        if cb.kmeans_init and self.training and not cb.initted:
+            cb._kmeans_init(ops.l2norm_rows(xv) if cosine else xv, cosine=cosine)
+        idx, counts = cb.lookup(xv)
+        code_usage = ops.code_usage(counts)
+        loss = torch.tensor([0.], device=device, requires_grad=self.training, dtype=torch.float32)
+        if self.training:
+            quantize, mse = ops.straight_through(xv, cb.embedding.weight.detach(), idx, amp16)
+            if self.commitment_weight > 0:
+                loss = loss + mse * self.commitment_weight
+        else:
+            quantize = ops.eval_gather(cb.embedding.weight, xv, idx, amp16)
+        quantize = quantize.permute(0, 2, 1).reshape(b, c, h, w)     # memory is already (B, C, H*W): a view
+        embed_index = idx.reshape(b, h, w)
+        return quantize, embed_index, loss, code_usage
