@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- VQ lookup throughput on B200 (BASELINE.json metric: "VQ lookup vectors/sec at K=512, D=256").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): N = 8 x 64 x 64 latent vectors, D = 256, K = 512 codebook, fp32, per GPU.
+One "step" = one eval-mode lookup of the whole batch: nearest-code assignment (tcgen05 filter + exact
+rescoring, indices + per-code counts) + codebook gather (quantized NCHW tensor) + code usage -- i.e.
+everything VectorQuantizer.forward returns (vq_img.py:228-244).  Inputs are synthetic (seeded randn).
+  value : whole-job vectors/s with inputs resident in HBM; a ring of input/output batches larger than
+          L2 is cycled so no step finds its input in cache.
+  e2e   : the same metric through the public nn.Module API with HOST (pinned) input, host->device copy
+          and device->host read of indices + usage inside the timed region.
+  roofline : the dominant kernel (assign_tc_kernel): 2*N*K*D flops / its CUDA-event duration vs the
+          measured dense bf16/fp16 tensor peak of MEASURED_PEAKS.json.
+  cpu_baseline : the oracle port of the reference's CPU path on the box's host cores (rank 0, N=1).
+With --impl reference the reference's CPU path itself is timed (oracle port; /root/reference is
+absent on the GPU box) on the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, C, H, W, K = 8, 256, 64, 64, 512
+N_VEC = B * H * W
+METRIC = "vq_lookup_vectors_per_sec"
+WORKLOAD = "VQ codebook lookup microbench: N=8x64x64 latent vectors, D=256, K=512, fp32 (BASELINE.json configs[1])"
+
+
+def make_inputs(seed, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, generator=g)
+    e = torch.randn(K, C, generator=g)
+    return x.to(device), e.to(device)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_step(model, x):
+    with torch.no_grad():
+        return model(x)
+
+
+def build_cpu_model(e):
+    """The reference's CPU path: the live module if /root/reference exists, else the oracle port."""
+    from oracle.ref_loader import load_reference_vq_img
+    ref = load_reference_vq_img()
+    if ref is not None:
+        m, kind = ref.VectorQuantizer(dim=C, num_embeddings=K), "reference"
+    else:
+        from oracle.vq_oracle import OracleVectorQuantizer
+        m, kind = OracleVectorQuantizer(dim=C, num_embeddings=K), "port"
+    m.codebook.embedding.weight.data.copy_(e)
+    m.eval()
+    return m, kind
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    x, e = make_inputs(0)
+    model, kind = build_cpu_model(e)
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_reference_step(model, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(model, x)
+    dt = time.perf_counter() - t0
+    val = N_VEC * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "vectors/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "device": "host CPU, torch eager"},
+            "cpu_baseline": {"value": val, "unit": "vectors/s", "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": f"{args.steps} full eval-mode forwards of the C2 batch ({N_VEC} vectors each)"},
+            "e2e": {"value": val, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ring", type=int, default=8, help="input batches cycled so the working set exceeds L2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.steps > 50:
+            args.steps = 50                       # bounded: ~0.1 s per step on host cores
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import vq_seg_b200 as V
+    from vq_seg_b200 import ops, _native
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 GPU (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.lib()
+    args.warmup = max(args.warmup, 3)
+
+    # ---- inputs: ring of batches (each rank its own data: data-parallel over latent pixels, weak scaling)
+    xs, e = [], None
+    for r in range(args.ring):
+        x, e0 = make_inputs(1000 * rank + r)
+        xs.append(x.to(dev))
+        if e is None:
+            _, e = make_inputs(0)
+    e = e.to(dev)
+    model = V.VectorQuantizer(dim=C, num_embeddings=K).to(dev)
+    model.codebook.embedding.weight.data.copy_(e)
+    model.codebook.invalidate()
+    model.eval()
+    weight = model.codebook.embedding.weight.detach()
+    blob = model.codebook._prepared()              # codebook operand image: built once, weights never change
+    views = [x.reshape(B, C, H * W).permute(0, 2, 1) for x in xs]
+
+    def step(i):
+        xv = views[i % args.ring]
+        idx, counts = ops.assign(xv, weight, blob, ops.ALGO_AUTO)
+        q, _ = ops.gather_ste(xv, weight, idx, ops.MODE_EVAL)
+        if world > 1:
+            dist.all_reduce(counts)                # global code usage (4 KiB): the only exchange of the lookup path
+        usage = ops.code_usage(counts)
+        return q, idx, usage
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    # ---- dominant kernel duration, CUDA events on the launching stream inside the C ABI
+    lib.vqseg_set_kernel_timing(1)
+    kt = []
+    for i in range(min(args.steps, 50)):
+        step(i)
+        torch.cuda.synchronize()
+        kt.append(lib.vqseg_get_kernel_timing_ms(0))
+    lib.vqseg_set_kernel_timing(0)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = N_VEC * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: public module API, pinned host input, H2D + D2H inside the timed region
+    host_x = [x.cpu().pin_memory() for x in xs[:min(4, args.ring)]]
+    host_idx = torch.empty(B, H, W, dtype=torch.int64).pin_memory()
+    host_usage = torch.empty((), dtype=torch.float32).pin_memory()
+    e2e_steps = max(5, min(args.steps, 50))
+
+    def e2e_step(i):
+        xd = host_x[i % len(host_x)].to(dev, non_blocking=True)
+        with torch.no_grad():
+            q, idx, loss, usage = model(xd)
+        host_idx.copy_(idx, non_blocking=True)
+        host_usage.copy_(usage, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return q
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e_val = N_VEC * world * e2e_steps / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops", 1590.0)
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops, burst; fp16 runs at the same rate)" if peaks else "fallback 1.59 PFLOP/s"
+        k_ms = statistics.median(kt) if kt else None
+        flops = 2.0 * N_VEC * K * C
+        roof = None
+        if k_ms:
+            ach = flops / (k_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "assign_tc_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                    "algorithmic_flops_per_launch": flops}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            torch.set_num_threads(os.cpu_count())
+            xc, ec = make_inputs(0)
+            cm, kind = build_cpu_model(ec)
+            cpu_reference_step(cm, xc)
+            reps, t0 = 0, time.perf_counter()
+            while reps < 20 and (time.perf_counter() - t0 < 10.0 or reps < 3):
+                cpu_reference_step(cm, xc); reps += 1
+            dt = time.perf_counter() - t0
+            cpu = {"value": N_VEC * reps / dt, "unit": "vectors/s", "cores": torch.get_num_threads(), "kind": kind,
+                   "sample": f"{reps} full eval-mode forwards of the C2 batch ({N_VEC} vectors each), {dt:.1f} s"}
+        line = {"metric": METRIC, "value": value, "unit": "vectors/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (fp16 tensor-core filter, exact fp32 rescoring)", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "per_gpu_vectors": N_VEC, "l2": f"ring of {args.ring} input batches "
+                           f"({args.ring * N_VEC * C * 4 / 2**20:.0f} MiB) cycled, larger than L2",
+                           "codebook_prepared": "once (weights static)", "parallelism": f"dp{world} over latent pixels"},
+                "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_val, "unit": "vectors/s", "h2d_bytes_per_step": N_VEC * C * 4,
+                        "d2h_bytes_per_step": N_VEC * 8 + 4, "steps": e2e_steps},
+                "gpu_launches": 4 * args.steps, "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,11 @@ extern "C" {
 #define VQSEG_MODE_EVAL_AMP    3
 
 int         vqseg_version(void);
+/* profiling aid for bench.py: when enabled, vqseg_assign_f32 brackets its kernels with CUDA events on
+ * the launching stream; which = 0 -> tcgen05 filter kernel, 1 -> exact rescoring kernel.  The getter
+ * synchronises on the events of the LAST call and returns milliseconds (< 0 if nothing recorded).   */
+void        vqseg_set_kernel_timing(int enable);
+float       vqseg_get_kernel_timing_ms(int which);
 const char* vqseg_error_string(int code);
 
 /* ---- codebook preparation --------------------------------------------------------------------

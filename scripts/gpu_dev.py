@@ -128,7 +128,24 @@ def stage_time():
         print(f"[time] code_stats det={det}: median {med:.1f} us best {best:.1f}")
 
 
+def stage_prof():
+    """one launch of every kernel at C2 (for `ncu --metrics gpu__time_duration.sum`)"""
+    x, e = cases.FORWARD_CASES["c2_randn"]()
+    xd, ed = x.to(dev), e.to(dev)
+    xv = view(xd)
+    for rep in range(3):
+        blob = ops.prepare_codebook(ed)
+        idx, counts = ops.assign(xv, ed, blob, ops.ALGO_TC)
+        q, mse = ops.gather_ste(xv, ed, idx, ops.MODE_TRAIN)
+        gx = ops.ste_bwd(torch.ones_like(q), xv, q, torch.ones(1, device=dev), 2.0 / xv.numel())
+        c, s = ops.code_stats(xv, idx, 512, True)
+        c2, s2 = ops.code_stats(xv, idx, 512, False)
+        u = ops.code_usage(counts)
+        torch.cuda.synchronize()
+    print("prof done", idx.sum().item(), mse.item(), u.item())
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

@@ -1,0 +1,281 @@
+"""GPU parity tests (run on a B200 with -m gpu): the CUDA path through the C ABI vs the committed golden
+vectors (produced by the live reference) and vs the CPU oracle on the same seeded inputs.
+
+Bars (north_star): bit-exact indices and code counts; quantize / loss / gradients within 1e-5 relative
+(in fact quantize and the k-means means come out bit-exact, which the tests assert where it holds by
+construction)."""
+import pytest
+import torch
+
+import cases
+from oracle import vq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from vq_seg_b200 import _native
+    _native.lib()                       # fail loudly if the extension is missing on a GPU box
+    return torch.device("cuda:0")
+
+
+def view(x):
+    b, c, h, w = x.shape
+    return x.reshape(b, c, h * w).permute(0, 2, 1)
+
+
+def near_tie_ok(x, e, idx_gpu, idx_ref):
+    """Contract (ii) of SURVEY §7.4: any disagreement must be a row whose two candidates are within
+    2 ulp in the reference's own fp32 distances."""
+    bad = (idx_gpu != idx_ref).nonzero()
+    if bad.numel() == 0:
+        return True
+    d = O.euclidean_dist(view(x), e)
+    for b, p in bad.tolist():
+        dg, dr = d[b, p, idx_gpu[b, p]], d[b, p, idx_ref[b, p]]
+        if not (dg - dr).abs() <= 2 * torch.finfo(torch.float32).eps * dr.abs():
+            return False
+    return True
+
+
+@pytest.mark.parametrize("algo", ["exact", "tc"])
+@pytest.mark.parametrize("name", list(cases.FORWARD_CASES))
+def test_assign_matches_golden(dev, golden, name, algo):
+    from vq_seg_b200 import ops
+    x, e = cases.FORWARD_CASES[name]()
+    rec = golden["forward"][name]
+    assert cases.sha(x) == rec["x_sha"]
+    xd, ed = x.to(dev), e.to(dev)
+    blob = ops.prepare_codebook(ed) if algo == "tc" else None
+    idx, counts = ops.assign(view(xd), ed, blob, ops.ALGO_TC if algo == "tc" else ops.ALGO_EXACT)
+    gold = rec["idx"].reshape(idx.shape).to(torch.int64)
+    assert torch.equal(idx.cpu(), gold), f"{(idx.cpu() != gold).sum().item()} index mismatches vs the reference"
+    assert torch.equal(counts.cpu(), rec["counts"])
+
+
+@pytest.mark.parametrize("name", ["c2_randn", "c2_relu", "c1_l3", "c1_l4", "c1_l5", "r448_l3", "r448_l5", "odd_7x7",
+                                  "dup_codes", "x_equals_code", "equidistant", "all_zero_x", "n_lt_k", "k_not_tile",
+                                  "d96_k1024", "c1_l5_uniform"])
+def test_module_forward_backward_matches_golden(dev, golden, name):
+    import vq_seg_b200 as V
+    x, e = cases.FORWARD_CASES[name]()
+    rec = golden["forward"][name]
+    m = V.VectorQuantizer(dim=x.shape[1], num_embeddings=e.shape[0]).to(dev)
+    m.codebook.embedding.weight.data.copy_(e)
+    m.eval()
+    with torch.no_grad():
+        q, idx, loss, usage = m(x.to(dev))
+    assert q.shape == x.shape and q.dtype == torch.float32 and q.is_contiguous()
+    assert idx.shape == (x.shape[0], x.shape[2], x.shape[3]) and idx.dtype == torch.int64
+    assert loss.shape == (1,) and not loss.requires_grad and usage.shape == () and usage.device == q.device
+    assert torch.equal(idx.cpu().to(torch.int32), rec["idx"])
+    assert cases.sha(q.cpu()) == rec["q_eval_sha"]                      # quantize == E[idx] bit-exact
+    assert torch.equal(usage.cpu(), rec["usage"]) and torch.equal(loss.cpu(), rec["loss_eval"])
+    m.train()
+    xg = x.to(dev).requires_grad_(True)
+    q, idx, loss, usage = m(xg)
+    assert loss.requires_grad and loss.shape == (1,)
+    assert cases.sha(q.detach().cpu()) == rec["q_train_sha"]            # x + (e - x), two roundings, bit-exact
+    torch.testing.assert_close(loss.detach().cpu(), rec["loss_train"], rtol=1e-5, atol=0)
+    g = torch.Generator().manual_seed(999)
+    gq = torch.randn(q.shape, generator=g)
+    (q * gq.to(dev)).sum().backward(retain_graph=True)
+    assert torch.equal(xg.grad.cpu(), gq)                               # straight-through: identity
+    xg.grad = None
+    (loss * 1.5).sum().backward()
+    step = max(1, x.numel() // 4096)
+    torch.testing.assert_close(xg.grad.cpu().reshape(-1)[::step], rec["gx_l_sample"], rtol=1e-5, atol=1e-12)
+    assert m.codebook.embedding.weight.grad is None                     # the codebook gets no gradient in training
+
+
+@pytest.mark.parametrize("name", cases.KMEANS_CASES)
+def test_kmeans_matches_golden(dev, golden, name):
+    import vq_seg_b200 as V
+    from vq_seg_b200 import ops
+    x, k, iters, init_idx, use_cos = cases.kmeans_case(name)
+    rec = golden["kmeans"][name]
+    xv = view(x.to(dev))
+    src = ops.l2norm_rows(xv) if use_cos else xv
+    means, bins = V.kmeans(src, k, iters, use_cosine_sim=use_cos, init_indices=init_idx)
+    assert means.shape == (1, k, x.shape[1]) and bins.shape == (1, k) and bins.dtype == torch.int64
+    assert torch.equal(bins[0].cpu(), rec["bins"])                      # bit-exact counts after `iters` Lloyd steps
+    if use_cos:
+        torch.testing.assert_close(means[0].cpu(), rec["means"], rtol=1e-5, atol=1e-7)
+    else:
+        assert torch.equal(means[0].cpu(), rec["means"])                # ordered per-code sums -> bit-exact means
+
+
+def test_kmeans_init_module_first_train_forward(dev):
+    """kmeans_init=True: the first TRAINING forward runs k-means on that batch and overwrites the codebook
+    (vq_img.py:165-166,179-190); eval forwards never do; `initted` is a plain attribute."""
+    import vq_seg_b200 as V
+    g = torch.Generator().manual_seed(3)
+    x = torch.relu(torch.randn(2, 64, 16, 16, generator=g))
+    init = torch.randperm(512, generator=g)[:32]
+    m = V.VectorQuantizer(dim=64, num_embeddings=32, kmeans_init=True).to(dev)
+    w0 = m.codebook.embedding.weight.detach().clone()
+    m.eval()
+    with torch.no_grad():
+        m(x.to(dev))
+    assert not m.codebook.initted and torch.equal(m.codebook.embedding.weight, w0)
+    m.train()
+    m.codebook.kmeans_init_indices = init
+    q, idx, loss, usage = m(x.to(dev))
+    assert m.codebook.initted
+    port = O.OracleVectorQuantizer(dim=64, num_embeddings=32, kmeans_init=True)
+    port.kmeans_init_indices = init
+    port.train()
+    qo, io, lo, uo = port(x)
+    assert torch.equal(m.codebook.embedding.weight.detach().cpu(), port.codebook.embedding.weight.detach())
+    assert torch.equal(idx.cpu(), io) and torch.equal(q.detach().cpu(), qo.detach())
+    assert "initted" not in m.state_dict()
+
+
+@pytest.mark.parametrize("name", list(cases.COSINE_CASES))
+def test_cosine_codebook(dev, golden, name):
+    import vq_seg_b200 as V
+    x, e = cases.COSINE_CASES[name]()
+    rec = golden["cosine"][name]
+    m = V.VectorQuantizer(dim=x.shape[1], num_embeddings=e.shape[0], distance="cosine").to(dev)
+    m.codebook.embedding.weight.data.copy_(e)
+    m.train()
+    q, idx, loss, usage = m(x.to(dev))
+    ref_idx = rec["idx"].to(torch.int64)
+    agree = (idx.cpu() == ref_idx).float().mean().item()
+    assert agree >= 0.999, agree                                        # norm rounding differs in the last ulp
+    torch.testing.assert_close(usage.cpu(), rec["usage"])
+    torch.testing.assert_close(loss.detach().cpu(), rec["loss_train"], rtol=1e-4, atol=0)
+    w = m.codebook.embedding.weight.detach()
+    torch.testing.assert_close(w.norm(dim=-1), torch.ones(e.shape[0], device=dev), rtol=1e-5, atol=1e-6)
+
+
+def test_row_major_samples_and_half_inputs(dev):
+    from vq_seg_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 3000, 128, generator=g)            # packed (N, D) rows: sP = D, sD = 1
+    e = torch.randn(200, 128, generator=g)
+    ref = O.assign_euclidean(x, e)
+    for algo in (ops.ALGO_EXACT, ops.ALGO_TC):
+        blob = ops.prepare_codebook(e.to(dev))
+        idx, counts = ops.assign(x.to(dev), e.to(dev), blob, algo)
+        assert near_tie_ok(x.permute(0, 2, 1).reshape(1, 128, 3000, 1), e, idx.cpu(), ref)
+        assert torch.equal(counts.cpu(), torch.bincount(idx.cpu().reshape(-1), minlength=200))
+    import vq_seg_b200 as V
+    xh = torch.randn(2, 64, 12, 12, generator=g).half()
+    m = V.VectorQuantizer(dim=64, num_embeddings=40).to(dev)
+    eh = torch.randn(40, 64, generator=g)
+    m.codebook.embedding.weight.data.copy_(eh)
+    m.train()
+    q, idx, loss, _ = m(xh.to(dev))
+    r = O.vq_forward(xh, eh, True, 1)                      # the reference upcasts with x.to(float32) (vq_img.py:229)
+    assert q.dtype == torch.float32 and torch.equal(idx.cpu(), r["embed_index"]) and torch.equal(q.detach().cpu(), r["quantize"])
+
+
+def test_large_random_sweep_tc_equals_exact(dev):
+    """Size-independent property at BASELINE sizes: the tcgen05 filter + rescoring must equal the exact
+    scorer bit for bit, whatever the data (that is the proof obligation of the short-list bound)."""
+    from vq_seg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for (b, c, hw, k, kind) in [(8, 256, 4096, 512, "randn"), (8, 256, 4096, 512, "relu"), (4, 512, 3136, 512, "relu"),
+                                (1, 64, 20000, 1000, "randn"), (2, 2048, 256, 512, "relu"), (3, 40, 777, 33, "randn"),
+                                (8, 256, 4096, 512, "clustered"), (2, 256, 4096, 512, "tiny"), (2, 256, 4096, 512, "huge")]:
+        x = torch.randn(b, c, hw, generator=g, device=dev)
+        e = torch.randn(k, c, generator=g, device=dev)
+        if kind == "relu":
+            x = torch.relu(x)
+            e = x.permute(0, 2, 1).reshape(-1, c)[torch.randperm(b * hw, device=dev, generator=g)[:k]] \
+                + 0.05 * torch.randn(k, c, generator=g, device=dev)
+        elif kind == "clustered":      # many near-ties: codes are tight perturbations of 16 centres
+            centres = torch.randn(16, c, generator=g, device=dev)
+            e = centres[torch.arange(k, device=dev) % 16] + 1e-3 * torch.randn(k, c, generator=g, device=dev)
+            x = centres[torch.randint(0, 16, (b * hw,), device=dev, generator=g)].reshape(b, hw, c).permute(0, 2, 1) \
+                + 0.1 * torch.randn(b, c, hw, generator=g, device=dev)
+        elif kind == "tiny":
+            x, e = x * 1e-4, e * 1e-4
+        elif kind == "huge":
+            x, e = x * 3e3, e * 3e3
+        xv = x.permute(0, 2, 1)
+        blob = ops.prepare_codebook(e)
+        i1, c1 = ops.assign(xv, e, None, ops.ALGO_EXACT)
+        i2, c2 = ops.assign(xv, e, blob, ops.ALGO_TC)
+        assert torch.equal(i1, i2), (kind, (i1 != i2).sum().item())
+        assert torch.equal(c1, c2) and c1.sum().item() == b * hw
+        # live oracle on the host CPU: bit-exact except provable fp32 near-ties
+        ref = O.assign_euclidean(xv.cpu(), e.cpu())
+        assert near_tie_ok(x.cpu().reshape(b, c, hw, 1), e.cpu(), i2.cpu(), ref), kind
+
+
+def test_fp16_overflow_rows_fall_back_to_exact(dev):
+    from vq_seg_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(1, 64, 512, generator=g)
+    e = torch.randn(64, 64, generator=g)
+    x[0, :, 5] *= 1e7                                   # overflows the fp16 operand of the filter
+    x[0, 3, 100] = 3e6
+    xv = x.permute(0, 2, 1).to(dev)
+    i1, _ = ops.assign(xv, e.to(dev), None, ops.ALGO_EXACT)
+    i2, _ = ops.assign(xv, e.to(dev), ops.prepare_codebook(e.to(dev)), ops.ALGO_TC)
+    assert torch.equal(i1, i2)
+    assert torch.equal(i2.cpu(), O.assign_euclidean(xv.cpu(), e))
+
+
+def test_code_stats_paths(dev):
+    from vq_seg_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(2, 96, 900, generator=g)
+    idx = torch.randint(0, 50, (2, 900), generator=g)
+    xv = x.permute(0, 2, 1)
+    flat = xv.reshape(-1, 96)
+    ref_sums = torch.zeros(50, 96).scatter_add_(0, idx.reshape(-1, 1).expand(-1, 96).contiguous(), flat.contiguous())
+    ref_counts = torch.bincount(idx.reshape(-1), minlength=50)
+    c, s = ops.code_stats(xv.to(dev), idx.to(dev), 50, True)
+    assert torch.equal(c.cpu(), ref_counts) and torch.equal(s.cpu(), ref_sums)       # ordered sums: bit-exact
+    c, s = ops.code_stats(xv.to(dev), idx.to(dev), 50, False)
+    assert torch.equal(c.cpu(), ref_counts)
+    torch.testing.assert_close(s.cpu(), ref_sums, rtol=1e-5, atol=1e-5)               # atomics: order not fixed
+    c, s = ops.code_stats(flat.contiguous().unsqueeze(0).to(dev), idx.reshape(1, -1).to(dev), 50, True)
+    assert torch.equal(s.cpu(), ref_sums)
+
+
+def test_amp_compat_rounds_code_through_fp16(dev):
+    import vq_seg_b200 as V
+    g = torch.Generator().manual_seed(19)
+    x = torch.randn(2, 64, 8, 8, generator=g)
+    e = torch.randn(32, 64, generator=g)
+    m = V.VectorQuantizer(dim=64, num_embeddings=32).to(dev)
+    m.codebook.embedding.weight.data.copy_(e)
+    m.train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        q, idx, loss, _ = m(x.to(dev))
+    r = O.vq_forward(x, e, False)
+    xb = view(x)
+    expect = xb + (e[r["embed_index"].reshape(2, -1)].half().float() - xb)           # SURVEY §5 AMP policy
+    assert q.dtype == torch.float32 and loss.dtype == torch.float32
+    assert torch.equal(q.detach().cpu(), expect.permute(0, 2, 1).reshape(x.shape))
+    assert torch.equal(idx.cpu(), r["embed_index"])
+
+
+def test_eval_mode_gradient_goes_to_codebook(dev):
+    import vq_seg_b200 as V
+    m = V.VectorQuantizer(dim=16, num_embeddings=8).to(dev)
+    m.eval()
+    x = torch.randn(1, 16, 5, 5, device=dev, requires_grad=True)
+    q, idx, _, _ = m(x)
+    assert q.requires_grad
+    q.sum().backward()
+    assert x.grad is None
+    expect = torch.bincount(idx.reshape(-1), minlength=8).float().unsqueeze(1).expand(8, 16)
+    torch.testing.assert_close(m.codebook.embedding.weight.grad, expect)
+
+
+def test_opcheck(dev):
+    from vq_seg_b200 import ops
+    x = torch.randn(2, 16, 50, device=dev).permute(0, 2, 1)
+    e = torch.randn(24, 16, device=dev)
+    torch.library.opcheck(torch.ops.vqseg.assign, (x, e, None, 1, 0), test_utils=("test_schema", "test_faketensor"))
+    idx, _ = ops.assign(x, e, None, 1)
+    torch.library.opcheck(torch.ops.vqseg.gather_ste, (x, e, idx, 1), test_utils=("test_schema", "test_faketensor"))
+    torch.library.opcheck(torch.ops.vqseg.code_stats, (x, idx, 24, True), test_utils=("test_schema", "test_faketensor"))

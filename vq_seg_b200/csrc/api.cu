@@ -50,9 +50,28 @@ static int auto_kblock(long long D) {
 
 using namespace vqseg;
 
+static int g_timing = 0;
+static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static int g_ev_valid[2] = {0, 0};
+static void ev_record(int i, cudaStream_t st) {
+  if (!g_timing) return;
+  if (!g_ev[i]) cudaEventCreate(&g_ev[i]);
+  cudaEventRecord(g_ev[i], st);
+}
+
 extern "C" {
 
 int vqseg_version(void) { return VQSEG_VERSION; }
+
+void vqseg_set_kernel_timing(int enable) { g_timing = enable; g_ev_valid[0] = g_ev_valid[1] = 0; }
+
+float vqseg_get_kernel_timing_ms(int which) {
+  if (which < 0 || which > 1 || !g_ev_valid[which]) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_ev[2 * which + 1]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_ev[2 * which], g_ev[2 * which + 1]) != cudaSuccess) return -1.f;
+  return ms;
+}
 
 const char* vqseg_error_string(int code) {
   switch (code) {
@@ -173,11 +192,18 @@ int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
   ta.idx_out = (long long*)idx_out; ta.counts_out = (unsigned long long*)counts_out; ta.code_base = code_base;
   ta.force_rescore = (best_key_out != nullptr || idx_out == nullptr) ? 1 : 0;
   ta.cand_idx = cand_idx; ta.cand_cnt = cand_cnt; ta.work_rows = work_rows; ta.work_count = work_count;
+  ev_record(0, st);
   rc = launch_assign_tc(ta, st);
+  ev_record(1, st);
   if (rc) return rc;
+  if (g_timing) g_ev_valid[0] = 1;
   ea.work_rows = work_rows; ea.work_count = work_count;
   ea.cand_idx = cand_idx; ea.cand_cnt = cand_cnt; ea.cand_cap = kCandCapHost;
-  return launch_exact(ea, n_rows, st);
+  ev_record(2, st);
+  rc = launch_exact(ea, n_rows, st);
+  ev_record(3, st);
+  if (g_timing) g_ev_valid[1] = 1;
+  return rc;
 }
 
 }  // extern "C"

@@ -173,8 +173,7 @@ def ste_bwd(grad_q: Optional[torch.Tensor], x: torch.Tensor, q_ste: torch.Tensor
     _require_cuda(x, q_ste, grad_q, grad_mse)
     L = _native.lib()
     b, p, d, sb, sp, sd = _bpd(x)
-    gx = torch.empty_strided(x.shape, x.stride(), dtype=torch.float32, device=x.device) \
-        if x.is_non_overlapping_and_dense() else torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    gx = torch.empty_like(x, dtype=torch.float32)      # preserve_format keeps the NCHW-view strides
     gq = grad_q
     if gq is not None and gq.dtype != torch.float32:
         gq = gq.float()
