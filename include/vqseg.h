@@ -52,6 +52,9 @@ int         vqseg_version(void);
  * synchronises on the events of the LAST call and returns milliseconds (< 0 if nothing recorded).   */
 void        vqseg_set_kernel_timing(int enable);
 float       vqseg_get_kernel_timing_ms(int which);
+/* developer tool: per-CTA clock64 stamps of the tcgen05 kernel's pipeline roles into a device buffer
+ * of n_ctas * 4 * 256 int64 (null disables).                                                      */
+void        vqseg_debug_set_trace(void* dev_buf);
 const char* vqseg_error_string(int code);
 
 /* ---- codebook preparation --------------------------------------------------------------------

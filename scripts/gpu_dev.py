@@ -145,7 +145,33 @@ def stage_prof():
     print("prof done", idx.sum().item(), mse.item(), u.item())
 
 
+def stage_trace():
+    from vq_seg_b200 import _native
+    L = _native.lib()
+    x, e = cases.FORWARD_CASES["c2_randn"]()
+    xd, ed = x.to(dev), e.to(dev)
+    xv = view(xd)
+    blob = ops.prepare_codebook(ed)
+    for _ in range(3):
+        ops.assign(xv, ed, blob, ops.ALGO_TC)
+    buf = torch.zeros(148 * 4 * 256, dtype=torch.int64, device=dev)
+    L.vqseg_debug_set_trace(buf.data_ptr())
+    ops.assign(xv, ed, blob, ops.ALGO_TC)
+    torch.cuda.synchronize()
+    L.vqseg_debug_set_trace(None)
+    t = buf.cpu().reshape(148, 4, 256)
+    torch.save(t, os.path.join(ROOT, "gpurun_out", "trace.pt"))
+    for cta in (0, 100):
+        tt = t[cta]
+        t0 = tt[tt > 0].min().item()
+        names = ["producer(w0)", "mma", "epilogue(q0)", "bloader"]
+        for role in range(4):
+            row = tt[role]
+            ev = [(i, row[i].item() - t0) for i in range(256) if row[i] > 0]
+            print(f"cta {cta} {names[role]}: " + " ".join(f"{i}:{v}" for i, v in ev))
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

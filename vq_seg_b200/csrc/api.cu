@@ -26,6 +26,7 @@ struct TcArgs {
   long long* idx_out; unsigned long long* counts_out; long long code_base;
   int force_rescore;
   int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
+  long long* trace;
 };
 int launch_pack(const float* E, int K, int D, unsigned char* blob, cudaStream_t st);
 int launch_assign_tc(const TcArgs& a, cudaStream_t st);
@@ -51,6 +52,7 @@ static int auto_kblock(long long D) {
 using namespace vqseg;
 
 static int g_timing = 0;
+static long long* g_trace = nullptr;
 static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 static int g_ev_valid[2] = {0, 0};
 static void ev_record(int i, cudaStream_t st) {
@@ -62,6 +64,8 @@ static void ev_record(int i, cudaStream_t st) {
 extern "C" {
 
 int vqseg_version(void) { return VQSEG_VERSION; }
+
+void vqseg_debug_set_trace(void* dev_buf) { g_trace = (long long*)dev_buf; }
 
 void vqseg_set_kernel_timing(int enable) { g_timing = enable; g_ev_valid[0] = g_ev_valid[1] = 0; }
 
@@ -192,6 +196,7 @@ int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
   ta.idx_out = (long long*)idx_out; ta.counts_out = (unsigned long long*)counts_out; ta.code_base = code_base;
   ta.force_rescore = (best_key_out != nullptr || idx_out == nullptr) ? 1 : 0;
   ta.cand_idx = cand_idx; ta.cand_cnt = cand_cnt; ta.work_rows = work_rows; ta.work_count = work_count;
+  ta.trace = g_trace;
   ev_record(0, st);
   rc = launch_assign_tc(ta, st);
   ev_record(1, st);

@@ -10,14 +10,14 @@
 // result therefore equals the exact path bit for bit (DESIGN.md §"why the filter is safe").
 //
 // Structure (one CTA per SM, persistent over 128-row tiles; unit = 128 rows x 256 codes):
-//   warps 0-7  A producers : x (fp32, any strides) -> registers -> *s -> fp16 -> SWIZZLE_128B
-//                            K-major smem tile (128 rows x 64 dims), plus sum x^2 per row
+//   warps 0-7  A producers : x (fp32, any strides) -> registers (two chunks of prefetch) -> fp16 ->
+//                            SWIZZLE_128B K-major smem tile (128 rows x 64 dims), plus sum x^2 per row
 //   warp  8    B loader    : cp.async.bulk (TMA bulk engine) of the pre-packed fp16 (-2 s E) tiles
 //   warp  9    MMA issuer  : tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, accumulators in
-//                            TMEM, pre-loaded with s^2 |e_k|^2 so the MMA yields the score itself
+//                            TMEM, pre-loaded with s |e_k|^2 so the MMA yields the (scaled) score itself
 //   warps 10-13 epilogue   : tcgen05.ld -> running row min -> short-list -> tcgen05.st re-init
 // Pipelines: smem full/empty mbarriers (4 stages), TMEM full/empty (2 x 256 columns).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vqseg {
 
@@ -31,14 +31,17 @@ constexpr int kEpiWarp0 = 10;
 constexpr int kTcThreads = 14 * 32;
 constexpr int kCandCap = 8;           // short-list entries kept per row before falling back to "all codes"
 constexpr int kXsqBufs = 8;
+constexpr uint32_t kIdesc = make_idesc_f16(kTileM, kUnitN);
+constexpr int kEnormSmem = 2048;      // codes whose scaled norms are staged in smem (else read from L2)
 
 struct TcSmem {
   // dynamic smem, 1024-aligned base
   static constexpr int off_a = 0;
   static constexpr int off_b = off_a + kStages * kAStageBytes;
-  static constexpr int off_cand = off_b + kStages * kBStageBytes;            // [128][kCandCap] {score, idx}
-  static constexpr int off_xsq = off_cand + kTileM * kCandCap * 8;           // [kXsqBufs][128] float
-  static constexpr int off_bar = off_xsq + kXsqBufs * kTileM * 4;            // mbarriers
+  static constexpr int off_cand = off_b + kStages * kBStageBytes;            // [128][kCandCap] code indices
+  static constexpr int off_xsq = off_cand + kTileM * kCandCap * 4;           // [kXsqBufs][128] float
+  static constexpr int off_enorm = off_xsq + kXsqBufs * kTileM * 4;          // [kEnormSmem] float: s*|e|^2
+  static constexpr int off_bar = off_enorm + kEnormSmem * 4;                 // mbarriers
   static constexpr int off_tmem = off_bar + 8 * (2 * kStages + 4);
   static constexpr int total = off_tmem + 16 + 1024;   // + slack for the runtime 1024-B alignment
 };
@@ -54,86 +57,11 @@ struct TcArgs {
   long long* idx_out; unsigned long long* counts_out; long long code_base;
   int force_rescore;              // 1 -> every row goes to the exact pass (sharded mode needs exact distances)
   int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
+  long long* trace;               // optional (dev tool): [cta][role][256] clock64 stamps
 };
 
-// ---- PTX wrappers --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
-      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]),
-        "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// SWIZZLE_128B K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-//   [0,14) start address >> 4, [16,30) LBO >> 4 (=1, unused for swizzled K-major), [32,46) SBO >> 4
-//   (= 1024 B between 8-row groups), [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  uint32_t lo = ((saddr & 0x3FFFF) >> 4) | (1u << 16);
-  uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-  return ((uint64_t)hi << 32) | lo;
-}
-// instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kUnitN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+#define VQ_TRACE(role, slot) do { if (a.trace && lane == 0 && (slot) < 256) \
+    a.trace[((long long)blockIdx.x * 4 + (role)) * 256 + (slot)] = clock64(); } while (0)
 
 // ---- codebook packing -----------------------------------------------------------------------------
 // image tile (cb, dc): 128 codes x 64 dims of fp16(-2 * s * e), SWIZZLE_128B K-major:
@@ -167,7 +95,7 @@ __global__ void __launch_bounds__(256) pack_codebook_kernel(const float* __restr
     *reinterpret_cast<uint4*>(tile + row * 128 + ((c8 ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h);
   }
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K_pad; k += gridDim.x * blockDim.x)
-    enorm_s[k] = k < K ? enorm[k] * s * s : 3.0e38f;
+    enorm_s[k] = k < K ? enorm[k] * s : 3.0e38f;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     hdr->scale = s;
     hdr->max_enorm = __uint_as_float(hdr->max_enorm_bits);
@@ -175,6 +103,8 @@ __global__ void __launch_bounds__(256) pack_codebook_kernel(const float* __restr
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
+// MODE 0: pixel-contiguous float4 loads (NCHW), 1: dim-contiguous float4 (packed rows), 2: scalar, any strides
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B needs 1024-B tiles
@@ -195,7 +125,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < kXsqBufs * kTileM; i += blockDim.x) xsq[i] = 0.f;
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -210,55 +139,108 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
 
   if (warp < kProducerWarps) {
     // ================= A producers =================
-    // thread (lane q, warp g): rows q + 32 i (i < 4), dims 8 g .. 8 g + 7 of each 64-dim chunk
-    const int g = warp, q = lane;
-    uint32_t it = 0;
-    for (int t = 0; t < my_tiles; ++t) {
-      const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTileM;
-      const float* rp[4];
-      bool rv[4];
+    // lane = quad*8 + g8: dims 8*g8 .. 8*g8+7 of the 64-dim chunk, rows 16*warp + 4*quad + i (i < 4).
+    // The 8 lanes of one STS.128 phase share their rows and differ in g8, so the swizzled 16-byte
+    // chunks (g8 ^ (row & 7)) land in 8 distinct bank groups: conflict-free with static indexing.
+    // Loads run one chunk ahead of the convert/store (2 register buffers) to keep HBM busy.
+    const int g8 = lane & 7, quad = lane >> 3;
+    const int r0 = 16 * warp + 4 * quad;
+    const int total = my_tiles * a.n_cc * a.n_dc;
+    const int per_tile = a.n_cc * a.n_dc;
+    const int D = (int)a.x.D;
+    constexpr int mode = MODE;
+
+    struct LoadState { int it, t, rem, dc; const float* rp[4]; bool rv[4]; };
+    LoadState ls;
+    ls.it = 0; ls.t = -1; ls.rem = 0; ls.dc = 0;
+    auto load_chunk = [&](float (&v)[4][8]) {
+      if (ls.it >= total) return;
+      if (ls.rem == 0) {           // first chunk of a new tile: decode the 4 rows of this lane
+        ls.t += 1; ls.rem = per_tile; ls.dc = 0;
+        const long long n0 = ((long long)blockIdx.x + (long long)ls.t * gridDim.x) * kTileM + r0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        long long n = row0 + q + 32 * i;
-        rv[i] = n < a.n_rows;
-        rp[i] = a.x.row(rv[i] ? n : 0);
-      }
-      float* xs = xsq + (t & (kXsqBufs - 1)) * kTileM;
-      for (int cc = 0; cc < a.n_cc; ++cc) {
-        for (int dc = 0; dc < a.n_dc; ++dc, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          float v[4][8];
-          const int d0 = dc * kDChunk + 8 * g;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              v[i][j] = (rv[i] && d0 + j < a.x.D) ? __ldg(rp[i] + (long long)(d0 + j) * a.x.sD) : 0.f;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          unsigned char* at = smem + TcSmem::off_a + s * kAStageBytes;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = q + 32 * i;
-            float ss = 0.f;
-            uint32_t pk[4];
-            bool ovf = false;
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              float a0 = v[i][j] * scale, a1 = v[i][j + 1] * scale;
-              ss = fmaf(a0, a0, ss); ss = fmaf(a1, a1, ss);
-              ovf |= !(fabsf(a0) <= 65504.f) | !(fabsf(a1) <= 65504.f);
-              __half2 h = __floats2half2_rn(a0, a1);
-              pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(at + r * 128 + ((g ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            if (cc == 0) atomicAdd(xs + r, ovf ? __int_as_float(0x7f800000) : ss);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        for (int i = 0; i < 4; ++i) {
+          ls.rv[i] = n0 + i < a.n_rows;
+          ls.rp[i] = a.x.row(ls.rv[i] ? n0 + i : 0);
         }
       }
+      const int d0 = ls.dc * kDChunk + 8 * g8;
+      if (mode == 0) {
+        const float* p0 = ls.rp[0] + (long long)d0 * a.x.sD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ls.rv[0] && d0 + j < D) f = __ldg(reinterpret_cast<const float4*>(p0 + (long long)j * a.x.sD));
+          v[0][j] = f.x; v[1][j] = f.y; v[2][j] = f.z; v[3][j] = f.w;
+        }
+      } else if (mode == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+          if (ls.rv[i] && d0 + 4 <= D) f0 = __ldg(reinterpret_cast<const float4*>(ls.rp[i] + d0));
+          if (ls.rv[i] && d0 + 8 <= D) f1 = __ldg(reinterpret_cast<const float4*>(ls.rp[i] + d0 + 4));
+          v[i][0] = f0.x; v[i][1] = f0.y; v[i][2] = f0.z; v[i][3] = f0.w;
+          v[i][4] = f1.x; v[i][5] = f1.y; v[i][6] = f1.z; v[i][7] = f1.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[i][j] = (ls.rv[i] && d0 + j < D) ? __ldg(ls.rp[i] + (long long)(d0 + j) * a.x.sD) : 0.f;
+      }
+      ls.it += 1; ls.rem -= 1;
+      ls.dc = (ls.dc + 1 == a.n_dc) ? 0 : ls.dc + 1;
+    };
+
+    int pit = 0, p_in_tile = 0, p_tile = 0;       // chunk being converted, its position in the tile
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+    auto store_chunk = [&](float (&v)[4][8]) {
+      if (pit >= total) return;
+      const int s = pit & (kStages - 1);
+      const uint32_t ph = ((uint32_t)pit / kStages) & 1;
+      const bool first_pass = p_in_tile < a.n_dc;           // code chunk 0: accumulate |x|^2
+      if (warp == 0) VQ_TRACE(0, 2 * pit);
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (warp == 0) VQ_TRACE(0, 2 * pit + 1);
+      unsigned char* at = smem + TcSmem::off_a + s * kAStageBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + i;
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          if (first_pass) { ss[i] = fmaf(v[i][j], v[i][j], ss[i]); ss[i] = fmaf(v[i][j + 1], v[i][j + 1], ss[i]); }
+          __half2 h = __floats2half2_rn(v[i][j], v[i][j + 1]);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(at + r * 128 + ((g8 ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      if (p_in_tile == a.n_dc - 1) {                         // row norms complete: publish before the arrive
+        float* xs = xsq + (p_tile & (kXsqBufs - 1)) * kTileM;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v2 = ss[i];
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
+          // any |x_d| >= 65504 overflows the fp16 operand; it also makes the sum >= 4.29e9
+          if (g8 == 0) xs[r0 + i] = (v2 < 4.0e9f) ? v2 : __int_as_float(0x7f800000);
+          ss[i] = 0.f;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      pit += 1;
+      if (++p_in_tile == per_tile) { p_in_tile = 0; p_tile += 1; }
+    };
+
+    float va[4][8], vb[4][8];
+    load_chunk(va);
+    while (pit < total) {
+      load_chunk(vb); store_chunk(va);
+      load_chunk(va); store_chunk(vb);
     }
   } else if (warp == 8) {
     // ================= B loader (bulk async copies) =================
@@ -270,7 +252,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
           for (int dc = 0; dc < a.n_dc; ++dc, ++it) {
             const int s = it % kStages;
             const uint32_t ph = (it / kStages) & 1;
+            VQ_TRACE(3, 2 * it);
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            VQ_TRACE(3, 2 * it + 1);
             const uint32_t dst = sbase + TcSmem::off_b + s * kBStageBytes;
             mbar_arrive_expect_tx(bar_full + 8 * s, kBStageBytes);
             bulk_g2s(dst, img + ((long long)(2 * cc) * a.n_dc + dc) * kTileBytes, kTileBytes, bar_full + 8 * s);
@@ -283,13 +267,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
     for (int u = 0; u < my_units; ++u) {
       const int buf = u & 1;
       const uint32_t use = (uint32_t)(u >> 1);
+      VQ_TRACE(1, 128 + 2 * u);
       mbar_wait(bar_tempty + 8 * buf, use & 1);          // epilogue drained + re-initialised this buffer
+      VQ_TRACE(1, 128 + 2 * u + 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * kUnitN;
       for (int dc = 0; dc < a.n_dc; ++dc, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
+        VQ_TRACE(1, 2 * it);
         mbar_wait(bar_full + 8 * s, ph);
+        VQ_TRACE(1, 2 * it + 1);
         tc_fence_after();
         if (lane == 0) {
           const uint64_t ad = make_desc(sbase + TcSmem::off_a + s * kAStageBytes);
@@ -308,18 +296,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;                    // row within the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const float* enorm_s = reinterpret_cast<const float*>(a.blob + hdr->off_enorm) + hdr->K_pad;
-    float2* cand = reinterpret_cast<float2*>(smem + TcSmem::off_cand) + r * kCandCap;
-    const float emax = sqrtf(hdr->max_enorm) * scale * 1.0001f;
+    const float* enorm_g = reinterpret_cast<const float*>(a.blob + hdr->off_enorm) + hdr->K_pad;
+    const float* enorm_sm = reinterpret_cast<const float*>(smem + TcSmem::off_enorm);
+    const bool en_smem = hdr->K_pad <= kEnormSmem;
+    int* cand = reinterpret_cast<int*>(smem + TcSmem::off_cand) + r * kCandCap;
+    const float emax = sqrtf(hdr->max_enorm) * 1.0001f;
+    const float e_s = emax * scale;
+    const float sqrt_dpad = sqrtf((float)(a.n_dc * kDChunk));
+
+    if (en_smem) {                                        // s*|e_k|^2 for every code, staged once per CTA
+      float* dst = reinterpret_cast<float*>(smem + TcSmem::off_enorm);
+      for (int i = (warp - kEpiWarp0) * 32 + lane; i < hdr->K_pad; i += 128) dst[i] = __ldg(enorm_g + i);
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+    }
 
     auto init_buf = [&](int buf, int cc) {
-      const float* en = enorm_s + cc * kUnitN;
+      const float* en = (en_smem ? enorm_sm : enorm_g) + cc * kUnitN;
 #pragma unroll 1
       for (int c = 0; c < kUnitN; c += 32) {
         uint32_t vals[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float4 e4 = __ldg(reinterpret_cast<const float4*>(en + c + j));
+          float4 e4 = *reinterpret_cast<const float4*>(en + c + j);
           vals[j] = __float_as_uint(e4.x); vals[j + 1] = __float_as_uint(e4.y);
           vals[j + 2] = __float_as_uint(e4.z); vals[j + 3] = __float_as_uint(e4.w);
         }
@@ -342,15 +340,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
       bool overflow = false;
       for (int cc = 0; cc < a.n_cc; ++cc, ++u) {
         const int buf = u & 1;
+        if (quarter == 0) VQ_TRACE(2, 4 * u);
         mbar_wait(bar_tfull + 8 * buf, (uint32_t)(u >> 1) & 1);
         tc_fence_after();
+        if (quarter == 0) VQ_TRACE(2, 4 * u + 1);
         if (cc == 0) {
-          // all A chunks of this tile's first unit are in: the row's sum of (s x)^2 is complete
-          float* xs = xsq + (t & (kXsqBufs - 1)) * kTileM;
-          const float xn = sqrtf(xs[r]) * 1.0001f;
-          xs[r] = 0.f;
+          // all A chunks of this tile's first unit are in: the row's sum of x^2 has been published
+          const float xn = sqrtf(xsq[(t & (kXsqBufs - 1)) * kTileM + r]) * 1.0001f;
           const float sum = xn + emax;
-          slack = a.tau * xn * emax + (float)(a.x.D + 8) * 2.4e-7f * sum * sum;     // 2^-22 = 2.4e-7
+          // |approx - exact| bound, scaled domain (scores are s * (|e|^2 - 2 x.e)):
+          //   fp16 operand rounding (both sides) + fp16 subnormal floor + fp32 chain error of the exact scorer
+          slack = a.tau * xn * e_s + 2.4e-7f * sqrt_dpad * (e_s + xn) + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum;
           if (!(slack < 3.0e38f)) overflow = true;                                   // fp16 overflow in this row
         }
         const uint32_t tb = lane_addr + buf * kUnitN;
@@ -360,64 +360,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
         for (int c = 0; c < kUnitN; c += 32) {
           uint32_t v[32];
           tmem_ld32(tb + c, v);
+          float m0 = m_u, m1 = __uint_as_float(v[1]);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) m_u = fminf(m_u, fminf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fminf(m0, fminf(__uint_as_float(v[j]), __uint_as_float(v[j + 2])));
+            m1 = fminf(m1, fminf(__uint_as_float(v[j + 1]), __uint_as_float(v[j + 3])));
+          }
+          m_u = fminf(m0, m1);
         }
-        m_run = fminf(m_run, m_u);
+        // every earlier short-list entry scored >= the old minimum: if that is now out of range, drop them all
+        const float m_new = fminf(m_run, m_u);
+        if (m_run > m_new + slack) cnt = 0;
+        m_run = m_new;
         const float thr = m_run + slack;
-        // pass B: every score within the bound joins the short-list
-        if (!overflow) {
+        if (quarter == 0) VQ_TRACE(2, 4 * u + 2);
+        // pass B: every score within the bound joins the short-list (indices only).  tcgen05.ld is
+        // warp-collective (.sync.aligned): every lane runs the loop; the bit mask keeps the hot path
+        // branch-free, the append loop runs only for lanes that found something.
 #pragma unroll 1
-          for (int c = 0; c < kUnitN; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tb + c, v);
+        for (int c = 0; c < kUnitN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tb + c, v);
+          // bit (31 - j) of ~mk <=> v[j] <= thr: one FADD + one funnel shift per score (the sign of
+          // thr - v[j] is shifted in), two independent chains
+          uint32_t mka = 0u, mkb = 0u;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float sc = __uint_as_float(v[j]);
-              if (sc <= thr) {
-                if (cnt == kCandCap) {                    // compact: drop entries that a later, lower minimum excluded
-                  int w = 0;
-                  for (int e = 0; e < kCandCap; ++e) { float2 ce = cand[e]; if (ce.x <= thr) cand[w++] = ce; }
-                  cnt = w;
-                }
-                if (cnt < kCandCap) cand[cnt++] = make_float2(sc, __int_as_float(cc * kUnitN + c + j));
-                else overflow = true;
-              }
-            }
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t da = __float_as_uint(thr - __uint_as_float(v[j]));
+            const uint32_t db = __float_as_uint(thr - __uint_as_float(v[j + 16]));
+            mka = __funnelshift_l(da, mka, 1);
+            mkb = __funnelshift_l(db, mkb, 1);
+          }
+          uint32_t mk = ~((mka << 16) | (mkb & 0xffffu));
+          if (overflow) mk = 0u;
+          while (mk) {
+            const int j = __clz(mk);
+            mk &= ~(0x80000000u >> j);
+            if (cnt < kCandCap) cand[cnt++] = cc * kUnitN + c + j;
+            else { overflow = true; mk = 0u; }
           }
         }
+        if (quarter == 0) VQ_TRACE(2, 4 * u + 3);
         init_buf(buf, (u + 2) % a.n_cc);                  // hand the buffer back, pre-loaded for unit u+2
       }
       // ---- tile done: resolve rows ----
-      if (n < a.n_rows) {
-        const float thr = m_run + slack;
-        int w = 0, last = 0;
-        if (!overflow) {
-          for (int e = 0; e < cnt; ++e) {
-            float2 ce = cand[e];
-            if (ce.x <= thr) { last = __float_as_int(ce.y); cand[w++] = ce; }
-          }
-        }
-        const bool unique = !overflow && w == 1 && !a.force_rescore && last < a.K;
-        if (unique) {
-          a.idx_out[n] = (long long)last + a.code_base;
-          if (a.counts_out) atomicAdd(a.counts_out + last, 1ull);
-        } else {
+      const bool in_range = n < a.n_rows;
+      const int last = cnt > 0 ? cand[cnt - 1] : 0;
+      const bool unique = !overflow && cnt == 1 && !a.force_rescore && last < a.K;
+      if (in_range && unique) {
+        a.idx_out[n] = (long long)last + a.code_base;
+        if (a.counts_out) atomicAdd(a.counts_out + last, 1ull);
+      }
+      const bool flagged = in_range && !unique;
+      const uint32_t fm = __ballot_sync(0xffffffffu, flagged);
+      if (fm) {                                            // one atomic per warp on the work counter
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.work_count, __popc(fm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (flagged) {
           int nc = 0;
           if (!overflow)
-            for (int e = 0; e < w; ++e) {
-              int k = __float_as_int(cand[e].y);
+            for (int e = 0; e < cnt; ++e) {
+              int k = cand[e];
               if (k < a.K) a.cand_idx[n * kCandCap + nc++] = k;
             }
           a.cand_cnt[n] = (overflow || nc == 0) ? kCandCap + 1 : nc;     // > cap => exact pass scans all codes
-          int slot = atomicAdd(a.work_count, 1);
-          a.work_rows[slot] = (int)n;
+          a.work_rows[base + __popc(fm & ((1u << lane) - 1))] = (int)n;
         }
       }
     }
   }
 
   // ---- teardown ----
+  if ((warp & 3) == 0 || warp == 9 || warp == 8) VQ_TRACE(warp < 8 ? 0 : (warp == 9 ? 1 : (warp == 8 ? 3 : 2)), 255);
   tc_fence_before();
   __syncthreads();
   if (warp == 9) {
@@ -432,18 +447,26 @@ int launch_pack(const float* E, int K, int D, unsigned char* blob, cudaStream_t 
   return 0;
 }
 
-int launch_assign_tc(const TcArgs& a, cudaStream_t st) {
+template <int MODE>
+static int launch_mode(const TcArgs& a, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total);
+    cudaError_t e = cudaFuncSetAttribute(assign_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
-  if (grid <= 0) return 0;
-  assign_tc_kernel<<<grid, kTcThreads, TcSmem::total, st>>>(a);
+  assign_tc_kernel<MODE><<<grid, kTcThreads, TcSmem::total, st>>>(a);
   VQSEG_LAUNCH_CHECK();
   return 0;
+}
+
+int launch_assign_tc(const TcArgs& a, cudaStream_t st) {
+  int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
+  if (grid <= 0) return 0;
+  const bool al16 = (reinterpret_cast<uintptr_t>(a.x.ptr) & 15) == 0 && (a.x.sB & 3) == 0;
+  if (al16 && a.x.sP == 1 && (a.x.P & 3) == 0 && (a.x.sD & 3) == 0) return launch_mode<0>(a, grid, st);
+  if (al16 && a.x.sD == 1 && (a.x.D & 3) == 0 && (a.x.sP & 3) == 0) return launch_mode<1>(a, grid, st);
+  return launch_mode<2>(a, grid, st);
 }
 
 }  // namespace vqseg
