@@ -55,6 +55,9 @@ float       vqseg_get_kernel_timing_ms(int which);
 /* developer tool: per-CTA clock64 stamps of the tcgen05 kernel's pipeline roles into a device buffer
  * of n_ctas * 4 * 256 int64 (null disables).                                                      */
 void        vqseg_debug_set_trace(void* dev_buf);
+/* developer tool: 1 -> always use the streaming single-CTA tcgen05 kernel, even when the codebook-resident
+ * CTA-pair kernel applies (lets the tests cover both on the same shapes).                              */
+void        vqseg_debug_force_streaming_kernel(int on);
 const char* vqseg_error_string(int code);
 
 /* ---- codebook preparation --------------------------------------------------------------------

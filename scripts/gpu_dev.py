@@ -64,7 +64,8 @@ def stage_tc():
         mism = (idx.cpu() != gi).sum().item()
         mism_e = (idx != idx_e).sum().item()
         cm = (counts != counts_e).sum().item()
-        print(f"[tc] {name:16s} vs golden {mism}/{gi.numel()}  vs exact {mism_e}  counts mism {cm}  {'PASS' if mism_e == 0 and cm == 0 else 'FAIL'}", flush=True)
+        flagged = ops._last_assign_ws[:4].view(torch.int32).item()
+        print(f"[tc] {name:16s} vs golden {mism}/{gi.numel()}  vs exact {mism_e}  counts mism {cm}  rescored rows {flagged} ({100.0 * flagged / gi.numel():.1f}%)  {'PASS' if mism_e == 0 and cm == 0 else 'FAIL'}", flush=True)
 
 
 def stage_ops():

@@ -32,9 +32,9 @@ def test_error_strings_and_sizes(native):
     assert lib.vqseg_error_string(0) == b"ok"
     assert b"workspace" in lib.vqseg_error_string(-2)
     assert b"sm_100" in lib.vqseg_error_string(-4)
-    # blob = header + 2*K_pad fp32 norms + fp16 image of K_pad x D_pad
-    assert lib.vqseg_codebook_blob_bytes(512, 256) == 1024 + 4096 + 512 * 256 * 2
-    assert lib.vqseg_codebook_blob_bytes(300, 100) == 1024 + 4096 + 512 * 128 * 2
+    # blob = header + 2*K_pad fp32 norms + fp16 image of K_pad x D_pad + one 4 KiB |e|^2 limb tile per 128 codes
+    assert lib.vqseg_codebook_blob_bytes(512, 256) == 1024 + 4096 + 512 * 256 * 2 + 4 * 4096
+    assert lib.vqseg_codebook_blob_bytes(300, 100) == 1024 + 4096 + 512 * 128 * 2 + 4 * 4096
     assert lib.vqseg_assign_workspace_bytes(32768, 256, 512, 0) >= 32768 * (4 + 4 + 32)
     assert lib.vqseg_code_stats_workspace_bytes(1000, 64, 32, 0) == 256
 

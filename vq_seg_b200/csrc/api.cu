@@ -29,11 +29,28 @@ struct TcArgs {
   long long* trace;
 };
 int launch_pack(const float* E, int K, int D, unsigned char* blob, cudaStream_t st);
+// assign_tc2.cu
+struct Tc2Args {
+  Rows x;
+  const unsigned char* blob;
+  long long n_rows;
+  int n_ptiles, n_cc, n_dc;
+  int K, K_pad;
+  unsigned long long off_image, off_aug, off_enorm;
+  float tau;
+  long long* idx_out; unsigned long long* counts_out; long long code_base;
+  int force_rescore;
+  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
+  long long* trace;
+};
+bool tc2_supported(int n_cc, int n_dc);
+int launch_assign_tc2(const Tc2Args& a, cudaStream_t st);
 int launch_assign_tc(const TcArgs& a, cudaStream_t st);
 constexpr int kCandCapHost = 8;
 
 __global__ void blob_init_kernel(BlobHeader* h, int K, int D, int K_pad, int D_pad, unsigned long long off_enorm,
-                                 unsigned long long off_image) {
+                                 unsigned long long off_image, unsigned long long off_aug) {
+  h->off_aug = off_aug; h->aug_c = 1.f; h->flags = 0u;
   h->magic = kBlobMagic; h->K = K; h->D = D; h->K_pad = K_pad; h->D_pad = D_pad;
   h->scale = 1.f; h->max_enorm = 0.f; h->max_enorm_bits = 0u; h->max_abs_bits = 0u;
   h->off_enorm = off_enorm; h->off_image = off_image;
@@ -53,6 +70,7 @@ using namespace vqseg;
 
 static int g_timing = 0;
 static long long* g_trace = nullptr;
+static int g_force_tc1 = 0;
 static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 static int g_ev_valid[2] = {0, 0};
 static void ev_record(int i, cudaStream_t st) {
@@ -66,6 +84,7 @@ extern "C" {
 int vqseg_version(void) { return VQSEG_VERSION; }
 
 void vqseg_debug_set_trace(void* dev_buf) { g_trace = (long long*)dev_buf; }
+void vqseg_debug_force_streaming_kernel(int on) { g_force_tc1 = on; }
 
 void vqseg_set_kernel_timing(int enable) { g_timing = enable; g_ev_valid[0] = g_ev_valid[1] = 0; }
 
@@ -90,12 +109,14 @@ const char* vqseg_error_string(int code) {
 }
 
 static void blob_geometry(int64_t K, int64_t D, long long* K_pad, long long* D_pad, size_t* off_enorm, size_t* off_image,
-                          size_t* total) {
+                          size_t* total, size_t* off_aug = nullptr) {
   *K_pad = round_up(K, 256);
   *D_pad = round_up(D, kDChunk);
   *off_enorm = 1024;
   *off_image = *off_enorm + (size_t)round_up(2 * *K_pad * sizeof(float), 1024);
-  *total = *off_image + (size_t)(*K_pad / kCodeBlock) * (size_t)(*D_pad / kDChunk) * kTileBytes;
+  size_t aug = *off_image + (size_t)(*K_pad / kCodeBlock) * (size_t)(*D_pad / kDChunk) * kTileBytes;
+  if (off_aug) *off_aug = aug;
+  *total = aug + (size_t)(*K_pad / kCodeBlock) * 4096;
 }
 
 size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D) {
@@ -107,13 +128,13 @@ size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D) {
 
 int vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D, void* blob, size_t blob_bytes, void* stream) {
   if (!E || !blob || K <= 0 || D <= 0 || K >= (1ll << 30) || D >= (1ll << 20)) return VQSEG_EINVAL;
-  long long kp, dp; size_t oe, oi, tot;
-  blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot);
+  long long kp, dp; size_t oe, oi, tot, oa;
+  blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot, &oa);
   if (blob_bytes < tot) return VQSEG_EWORKSPACE;
   if ((reinterpret_cast<uintptr_t>(blob) & 1023) != 0) return VQSEG_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* b = (unsigned char*)blob;
-  blob_init_kernel<<<1, 1, 0, st>>>((BlobHeader*)b, (int)K, (int)D, (int)kp, (int)dp, oe, oi);
+  blob_init_kernel<<<1, 1, 0, st>>>((BlobHeader*)b, (int)K, (int)D, (int)kp, (int)dp, oe, oi, oa);
   VQSEG_LAUNCH_CHECK();
   int rc = launch_enorm(E, (int)K, (int)D, (int)kp, (float*)(b + oe), (BlobHeader*)b, st);
   if (rc) return rc;
@@ -155,9 +176,9 @@ int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
   const BlobHeader* hdr = (const BlobHeader*)blob;
   const float* enorm = nullptr;
   long long kp = 0, dp = 0;
+  size_t oe = 0, oi = 0, tot = 0, oa = 0;
   if (blob) {
-    size_t oe, oi, tot;
-    blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot);
+    blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot, &oa);
     enorm = (const float*)((const char*)blob + oe);
   } else {
     rc = launch_enorm(E, (int)K, (int)D, (int)K, enorm_ws, nullptr, st);
@@ -187,18 +208,35 @@ int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
 
   cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
-  TcArgs ta;
-  memset(&ta, 0, sizeof(ta));
-  ta.x = xr; ta.blob = (const unsigned char*)blob; ta.n_rows = n_rows;
-  ta.n_tiles = (int)((n_rows + 127) / 128); ta.n_cc = (int)(kp / 256); ta.n_dc = (int)(dp / kDChunk);
-  ta.K = (int)K;
-  ta.tau = 0.00390625f * 1.015625f;          // 2^-8 (two fp16 roundings per operand pair, both sides) + margin
-  ta.idx_out = (long long*)idx_out; ta.counts_out = (unsigned long long*)counts_out; ta.code_base = code_base;
-  ta.force_rescore = (best_key_out != nullptr || idx_out == nullptr) ? 1 : 0;
-  ta.cand_idx = cand_idx; ta.cand_cnt = cand_cnt; ta.work_rows = work_rows; ta.work_count = work_count;
-  ta.trace = g_trace;
+  const float tau = 0.00390625f * 1.015625f;   // 2^-8 (two fp16 roundings per operand pair, both sides) + margin
+  const int n_cc = (int)(kp / 256), n_dc = (int)(dp / kDChunk);
+  const bool force = (best_key_out != nullptr || idx_out == nullptr);
   ev_record(0, st);
-  rc = launch_assign_tc(ta, st);
+  if (tc2_supported(n_cc, n_dc) && g_force_tc1 == 0) {
+    Tc2Args t2;
+    memset(&t2, 0, sizeof(t2));
+    t2.x = xr; t2.blob = (const unsigned char*)blob; t2.n_rows = n_rows;
+    t2.n_ptiles = (int)((n_rows + 255) / 256); t2.n_cc = n_cc; t2.n_dc = n_dc;
+    t2.K = (int)K; t2.K_pad = (int)kp; t2.off_image = oi; t2.off_aug = oa; t2.off_enorm = oe;
+    t2.tau = tau;
+    t2.idx_out = (long long*)idx_out; t2.counts_out = (unsigned long long*)counts_out; t2.code_base = code_base;
+    t2.force_rescore = force ? 1 : 0;
+    t2.cand_idx = cand_idx; t2.cand_cnt = cand_cnt; t2.work_rows = work_rows; t2.work_count = work_count;
+    t2.trace = g_trace;
+    rc = launch_assign_tc2(t2, st);
+  } else {
+    TcArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.x = xr; ta.blob = (const unsigned char*)blob; ta.n_rows = n_rows;
+    ta.n_tiles = (int)((n_rows + 127) / 128); ta.n_cc = n_cc; ta.n_dc = n_dc;
+    ta.K = (int)K;
+    ta.tau = tau;
+    ta.idx_out = (long long*)idx_out; ta.counts_out = (unsigned long long*)counts_out; ta.code_base = code_base;
+    ta.force_rescore = force ? 1 : 0;
+    ta.cand_idx = cand_idx; ta.cand_cnt = cand_cnt; ta.work_rows = work_rows; ta.work_count = work_count;
+    ta.trace = g_trace;
+    rc = launch_assign_tc(ta, st);
+  }
   ev_record(1, st);
   if (rc) return rc;
   if (g_timing) g_ev_valid[0] = 1;

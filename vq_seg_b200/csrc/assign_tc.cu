@@ -94,11 +94,40 @@ __global__ void __launch_bounds__(256) pack_codebook_kernel(const float* __restr
     unsigned char* tile = reinterpret_cast<unsigned char*>(img) + ((long long)cb * n_dc + dc) * kTileBytes;
     *reinterpret_cast<uint4*>(tile + row * 128 + ((c8 ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h);
   }
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K_pad; k += gridDim.x * blockDim.x)
+  // |e|^2 limbs for the augmented K step: s|e_k|^2 = c * (h1 + h2 + h3), c a power of two putting the
+  // largest norm in [2^13, 2^14) so every limb is a normal/subnormal fp16 with residual <= 2^-24 c
+  const float men = __uint_as_float(hdr->max_enorm_bits) * s;
+  int ce = (int)((__float_as_uint(men) >> 23) & 0xff) - 127 - 13;
+  if (men == 0.f) ce = 0;
+  ce = ce < -14 ? -14 : (ce > 15 ? 15 : ce);
+  const float c = __uint_as_float((uint32_t)(127 + ce) << 23);
+  const float cinv = __uint_as_float((uint32_t)(127 - ce) << 23);
+  unsigned char* augbase = blob + hdr->off_aug;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K_pad; k += gridDim.x * blockDim.x) {
     enorm_s[k] = k < K ? enorm[k] * s : 3.0e38f;
+    float v = k < K ? enorm[k] * s * cinv : 60000.f;
+    __half h1, h2, h3;
+    if (k < K) {
+      if (!(v <= 60000.f)) { atomicOr(&hdr->flags, 1u); v = 60000.f; }
+      h1 = __float2half_rn(v);
+      const float r1 = v - __half2float(h1);
+      h2 = __float2half_rn(r1);
+      h3 = __float2half_rn(r1 - __half2float(h2));
+    } else {
+      h1 = h2 = h3 = __float2half_rn(60000.f);          // pad codes can never come near the row minimum
+    }
+    const int cb = k / kCodeBlock, row = k % kCodeBlock;
+    // SWIZZLE_NONE K-major core matrices: 8 rows x 16 B; byte = (row/8)*256 + khalf*128 + (row%8)*16
+    unsigned char* t = augbase + (long long)cb * 4096 + (row >> 3) * 256 + (row & 7) * 16;
+    __align__(16) __half lo[8] = {h1, h2, h3, __float2half_rn(0.f), __float2half_rn(0.f), __float2half_rn(0.f),
+                                  __float2half_rn(0.f), __float2half_rn(0.f)};
+    *reinterpret_cast<uint4*>(t) = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(t + 128) = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     hdr->scale = s;
     hdr->max_enorm = __uint_as_float(hdr->max_enorm_bits);
+    hdr->aug_c = c;
   }
 }
 

@@ -1,0 +1,400 @@
+// Codebook-resident, CTA-pair variant of the fused distance + argmin kernel (tcgen05.cta_group::2).
+//
+// Same contract as assign_tc.cu (it replaces torch.cdist + torch.argmin, vq_img.py:167-168) for
+// codebooks whose fp16 operand image fits the shared memory of TWO SMs:  (K_pad/256) * (D_pad/64) <= 8,
+// D_pad <= 256  -- e.g. the headline K=512, D=256.
+//
+//   * a cluster of 2 CTAs (one TPC) owns 256 rows per tile: each CTA converts and holds its own 128 rows
+//     (UMMA M = 256 = 2 x 128 TMEM lanes) and HALF of every 256-code chunk (UMMA N = 256 = 2 x 128 codes),
+//     so the whole codebook stays resident (128 KiB per CTA) and every x element is read from HBM once,
+//     converted once;
+//   * |e_k|^2 enters through one extra K=16 MMA step against a constant column (three fp16 limbs), so the
+//     accumulator IS the score and TMEM is never written by the SM;
+//   * the next tile's fp32 rows wait in REGISTERS (4 chunks x 32 regs per producer thread, register budget
+//     moved to the producers with setmaxnreg) while the current tile's fp16 operand sits in smem;
+//   * the epilogue reads each accumulator exactly once: per 32 columns block-min -> running threshold ->
+//     sign-bit mask (one FADD + one funnel shift per score) -> short-list of code indices.
+// Roles per CTA (16 warps): 0-7 producers, 8-11 epilogue, 12 MMA issuer (leader CTA) + TMEM alloc,
+// 13 codebook loader (cp.async.bulk), 14-15 idle (they only donate registers).
+#include "tc_common.cuh"
+
+namespace vqseg {
+
+constexpr int k2Threads = 512;
+constexpr int k2Rows = 128;                 // rows per CTA per tile (pair tile = 256)
+constexpr int k2ASlots = 4;                 // A ring = one tile (D_pad <= 256)
+constexpr int k2MaxBTiles = 8;              // resident 16 KiB codebook tiles per CTA
+constexpr int k2MaxCC = 4;
+constexpr int k2CandCap = 8;
+constexpr int k2XsqBufs = 4;
+constexpr int k2AugBytes = 128 * 16 * 2;    // 4 KiB: 128 rows x 16 fp16, SWIZZLE_NONE core matrices
+constexpr uint32_t k2Idesc = make_idesc_f16(256, 256);
+
+struct Tc2Smem {
+  static constexpr int off_b = 0;                                         // [k2MaxBTiles] 16 KiB
+  static constexpr int off_a = off_b + k2MaxBTiles * kTileBytes;           // [k2ASlots] 16 KiB
+  static constexpr int off_baug = off_a + k2ASlots * kTileBytes;           // [k2MaxCC] 4 KiB
+  static constexpr int off_aaug = off_baug + k2MaxCC * k2AugBytes;         // 4 KiB
+  static constexpr int off_cand = off_aaug + k2AugBytes;                   // [128][cap] int
+  static constexpr int off_xsq = off_cand + k2Rows * k2CandCap * 4;        // [bufs][128] float
+  static constexpr int off_bar = off_xsq + k2XsqBufs * k2Rows * 4;
+  static constexpr int n_bars = 2 * k2ASlots + 4 + 2;
+  static constexpr int off_tmem = off_bar + 8 * n_bars;
+  static constexpr int total = off_tmem + 16 + 1024;
+};
+static_assert(Tc2Smem::total <= 227 * 1024, "smem budget");
+
+struct Tc2Args {
+  Rows x;
+  const unsigned char* blob;
+  long long n_rows;
+  int n_ptiles, n_cc, n_dc;       // pair tiles of 256 rows, code chunks of 256, dim chunks of 64
+  int K, K_pad;
+  unsigned long long off_image, off_aug, off_enorm;
+  float tau;
+  long long* idx_out; unsigned long long* counts_out; long long code_base;
+  int force_rescore;
+  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
+  long long* trace;
+};
+
+#define VQ2_TRACE(role, slot) do { if (a.trace && lane == 0 && (slot) < 256) \
+    a.trace[((long long)blockIdx.x * 4 + (role)) * 256 + (slot)] = clock64(); } while (0)
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign_tc2_kernel(Tc2Args a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw2[];
+  unsigned char* smem = smem_raw2 + ((1024u - (smem_u32(smem_raw2) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(a.blob);
+
+  const uint32_t bar_full = sbase + Tc2Smem::off_bar;                  // [slots]  leader: 16 producer-warp arrivals
+  const uint32_t bar_empty = bar_full + 8 * k2ASlots;                  // [slots]  each CTA: 1 (multicast commit)
+  const uint32_t bar_tfull = bar_empty + 8 * k2ASlots;                 // [2]      each CTA: 1 (multicast commit)
+  const uint32_t bar_tempty = bar_tfull + 16;                          // [2]      leader: 8 epilogue-warp arrivals
+  const uint32_t bar_bload = bar_tempty + 16;                          // local bulk-copy completion
+  const uint32_t bar_bready = bar_bload + 8;                           // leader: 2 (codebook resident in both CTAs)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Tc2Smem::off_tmem);
+  float* xsq = reinterpret_cast<float*>(smem + Tc2Smem::off_xsq);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < k2ASlots; ++s) { mbar_init(bar_full + 8 * s, 16); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }
+    mbar_init(bar_bload, 1);
+    mbar_init(bar_bready, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_pairs = (int)gridDim.x >> 1;
+  const int pair = (int)blockIdx.x >> 1;
+  const int my_tiles = a.n_ptiles > pair ? (a.n_ptiles - 1 - pair) / n_pairs + 1 : 0;
+  const int my_units = my_tiles * a.n_cc;
+  const uint32_t lead_full = mapa_u32(bar_full, 0);
+  const uint32_t lead_tempty = mapa_u32(bar_tempty, 0);
+
+  if (warp < 8) {
+    // ================= A producers =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    const int g8 = lane & 7, quad = lane >> 3;
+    const int r0 = 16 * warp + 4 * quad;
+    const int D = (int)a.x.D;
+    const float* rp[4];
+    bool rv[4];
+    auto decode = [&](int tt) {
+      const long long n0 = ((long long)pair + (long long)tt * n_pairs) * 256 + rank * 128 + r0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rv[i] = n0 + i < a.n_rows;
+        rp[i] = a.x.row(rv[i] ? n0 + i : 0);
+      }
+    };
+    auto load_chunk = [&](float (&v)[4][8], int dc) {
+      const int d0 = dc * kDChunk + 8 * g8;
+      if (MODE == 0) {
+        const float* p0 = rp[0] + (long long)d0 * a.x.sD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rv[0] && d0 + j < D) f = __ldg(reinterpret_cast<const float4*>(p0 + (long long)j * a.x.sD));
+          v[0][j] = f.x; v[1][j] = f.y; v[2][j] = f.z; v[3][j] = f.w;
+        }
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+          if (rv[i] && d0 + 4 <= D) f0 = __ldg(reinterpret_cast<const float4*>(rp[i] + d0));
+          if (rv[i] && d0 + 8 <= D) f1 = __ldg(reinterpret_cast<const float4*>(rp[i] + d0 + 4));
+          v[i][0] = f0.x; v[i][1] = f0.y; v[i][2] = f0.z; v[i][3] = f0.w;
+          v[i][4] = f1.x; v[i][5] = f1.y; v[i][6] = f1.z; v[i][7] = f1.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[i][j] = (rv[i] && d0 + j < D) ? __ldg(rp[i] + (long long)(d0 + j) * a.x.sD) : 0.f;
+      }
+    };
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+    auto store_chunk = [&](float (&v)[4][8], int dc, int tt) {
+      if (warp == 0) VQ2_TRACE(0, 2 * (tt * a.n_dc + dc));
+      mbar_wait(bar_empty + 8 * dc, ((uint32_t)tt & 1) ^ 1);        // last tile's MMAs on this slot retired
+      if (warp == 0) VQ2_TRACE(0, 2 * (tt * a.n_dc + dc) + 1);
+      unsigned char* at = smem + Tc2Smem::off_a + dc * kTileBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + i;
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          ss[i] = fmaf(v[i][j], v[i][j], ss[i]); ss[i] = fmaf(v[i][j + 1], v[i][j + 1], ss[i]);
+          __half2 h = __floats2half2_rn(v[i][j], v[i][j + 1]);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(at + r * 128 + ((g8 ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      if (dc == a.n_dc - 1) {                                        // row norms complete: publish before the arrive
+        float* xs = xsq + (tt & (k2XsqBufs - 1)) * k2Rows;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v2 = ss[i];
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
+          if (g8 == 0) xs[r0 + i] = (v2 < 4.0e9f) ? v2 : __int_as_float(0x7f800000);
+          ss[i] = 0.f;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_full + 8 * dc);        // leader's barrier (remote for rank 1)
+    };
+
+    float v0[4][8], v1[4][8], v2r[4][8], v3[4][8];
+    if (my_tiles > 0) {
+      decode(0);
+      load_chunk(v0, 0);
+      if (a.n_dc > 1) load_chunk(v1, 1);
+      if (a.n_dc > 2) load_chunk(v2r, 2);
+      if (a.n_dc > 3) load_chunk(v3, 3);
+    }
+    for (int tt = 0; tt < my_tiles; ++tt) {
+      const bool more = tt + 1 < my_tiles;
+      if (more) decode(tt + 1);
+      store_chunk(v0, 0, tt);                   if (more) load_chunk(v0, 0);
+      if (a.n_dc > 1) { store_chunk(v1, 1, tt);  if (more) load_chunk(v1, 1); }
+      if (a.n_dc > 2) { store_chunk(v2r, 2, tt); if (more) load_chunk(v2r, 2); }
+      if (a.n_dc > 3) { store_chunk(v3, 3, tt);  if (more) load_chunk(v3, 3); }
+    }
+  } else if (warp < 12) {
+    // ================= epilogue =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int* cand = reinterpret_cast<int*>(smem + Tc2Smem::off_cand) + r * k2CandCap;
+    float scale = 0.f, emax = 0.f;
+    int u = 0;
+    for (int tt = 0; tt < my_tiles; ++tt) {
+      const long long n = ((long long)pair + (long long)tt * n_pairs) * 256 + rank * 128 + r;
+      float m_run = __int_as_float(0x7f800000);
+      float slack = 0.f;
+      int cnt = 0;
+      bool overflow = false;
+      for (int cc = 0; cc < a.n_cc; ++cc, ++u) {
+        const int buf = u & 1;
+        if (quarter == 0) VQ2_TRACE(2, 4 * u);
+        mbar_wait(bar_tfull + 8 * buf, (uint32_t)(u >> 1) & 1);
+        tc_fence_after();
+        if (quarter == 0) VQ2_TRACE(2, 4 * u + 1);
+        if (cc == 0) {
+          if (tt == 0) { scale = hdr->scale; emax = sqrtf(hdr->max_enorm) * 1.0001f; overflow = false; }
+          const float xn = sqrtf(xsq[(tt & (k2XsqBufs - 1)) * k2Rows + r]) * 1.0001f;
+          const float e_s = emax * scale;
+          const float sum = xn + emax;
+          // see assign_tc.cu: fp16 operand rounding + fp16 subnormal floor + limb residual of |e|^2 + fp32 chain
+          // error of the exact scorer, all in the scaled domain
+          slack = a.tau * xn * e_s + 2.4e-7f * sqrtf((float)(a.n_dc * kDChunk)) * (e_s + xn)
+                + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum + 1.0e-6f * e_s * emax;
+          if (!(slack < 3.0e38f) || (hdr->flags & 1u)) overflow = true;
+        }
+        const uint32_t tb = lane_addr + buf * 256;
+#pragma unroll 1
+        for (int c = 0; c < 256; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tb + c, v);
+          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fminf(m0, fminf(__uint_as_float(v[j]), __uint_as_float(v[j + 2])));
+            m1 = fminf(m1, fminf(__uint_as_float(v[j + 1]), __uint_as_float(v[j + 3])));
+          }
+          const float m_new = fminf(m_run, fminf(m0, m1));
+          if (m_run > m_new + slack) cnt = 0;          // every earlier entry scored >= the old minimum
+          m_run = m_new;
+          const float thr = m_run + slack;
+          uint32_t mka = 0u, mkb = 0u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t da = __float_as_uint(thr - __uint_as_float(v[j]));
+            const uint32_t db = __float_as_uint(thr - __uint_as_float(v[j + 16]));
+            mka = __funnelshift_l(da, mka, 1);
+            mkb = __funnelshift_l(db, mkb, 1);
+          }
+          uint32_t mk = ~((mka << 16) | (mkb & 0xffffu));
+          if (overflow) mk = 0u;
+          while (mk) {
+            const int j = __clz(mk);
+            mk &= ~(0x80000000u >> j);
+            if (cnt < k2CandCap) cand[cnt++] = cc * 256 + c + j;
+            else { overflow = true; mk = 0u; }
+          }
+        }
+        if (quarter == 0) VQ2_TRACE(2, 4 * u + 2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);     // accumulator drained
+      }
+      const bool in_range = n < a.n_rows;
+      const int last = cnt > 0 ? cand[cnt - 1] : 0;
+      const bool unique = !overflow && cnt == 1 && !a.force_rescore && last < a.K;
+      if (in_range && unique) {
+        a.idx_out[n] = (long long)last + a.code_base;
+        if (a.counts_out) atomicAdd(a.counts_out + last, 1ull);
+      }
+      const bool flagged = in_range && !unique;
+      const uint32_t fm = __ballot_sync(0xffffffffu, flagged);
+      if (fm) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.work_count, __popc(fm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (flagged) {
+          int nc = 0;
+          if (!overflow)
+            for (int e = 0; e < cnt; ++e) {
+              int k = cand[e];
+              if (k < a.K) a.cand_idx[n * k2CandCap + nc++] = k;
+            }
+          a.cand_cnt[n] = (overflow || nc == 0) ? k2CandCap + 1 : nc;
+          a.work_rows[base + __popc(fm & ((1u << lane) - 1))] = (int)n;
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 13) {
+      // ================= codebook loader: this CTA's half of every 256-code chunk stays resident =================
+      {   // A-side augmentation tile: column 0..2 = c (power of two), rest 0; SWIZZLE_NONE core matrices
+        const __half cval = __float2half_rn(hdr->aug_c);
+        const uint32_t c2 = (uint32_t)__half_as_ushort(cval);
+        uint4* aa = reinterpret_cast<uint4*>(smem + Tc2Smem::off_aaug);
+        for (int i = lane; i < k2AugBytes / 16; i += 32) {
+          // 16-byte unit i: group g = i / 16, k-half h = (i / 8) & 1, row-in-group = i & 7
+          const bool first_half = ((i >> 3) & 1) == 0;
+          aa[i] = first_half ? make_uint4(c2 | (c2 << 16), c2, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async();
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const unsigned char* img = a.blob + a.off_image;
+        const unsigned char* aug = a.blob + a.off_aug;
+        const uint32_t bytes = (uint32_t)(a.n_cc * a.n_dc) * kTileBytes + (uint32_t)a.n_cc * k2AugBytes;
+        mbar_arrive_expect_tx(bar_bload, bytes);
+        for (int cc = 0; cc < a.n_cc; ++cc) {
+          const int cb = 2 * cc + (int)rank;                       // this CTA's 128 codes of chunk cc
+          for (int dc = 0; dc < a.n_dc; ++dc)
+            bulk_g2s(sbase + Tc2Smem::off_b + (cc * a.n_dc + dc) * kTileBytes,
+                     img + ((long long)cb * a.n_dc + dc) * kTileBytes, kTileBytes, bar_bload);
+          bulk_g2s(sbase + Tc2Smem::off_baug + cc * k2AugBytes, aug + (long long)cb * k2AugBytes, k2AugBytes, bar_bload);
+        }
+        mbar_wait(bar_bload, 0);
+        mbar_arrive_cluster(mapa_u32(bar_bready, 0));
+      }
+    } else if (warp == 12 && rank == 0) {
+      // ================= MMA issuer (leader CTA) =================
+      mbar_wait_cluster(bar_bready, 0);
+      tc_fence_after();
+      const uint64_t aaug = make_desc_noswz(sbase + Tc2Smem::off_aaug, 128, 256);
+      for (int u = 0; u < my_units; ++u) {
+        const int tt = u / a.n_cc, cc = u - tt * a.n_cc;
+        const int buf = u & 1;
+        VQ2_TRACE(1, 128 + 2 * u);
+        mbar_wait_cluster(bar_tempty + 8 * buf, (((uint32_t)u >> 1) & 1) ^ 1);   // both epilogues drained it
+        VQ2_TRACE(1, 128 + 2 * u + 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        for (int dc = 0; dc < a.n_dc; ++dc) {
+          if (cc == 0) {
+            VQ2_TRACE(1, 2 * (tt * a.n_dc + dc));
+            mbar_wait_cluster(bar_full + 8 * dc, (uint32_t)tt & 1);    // both CTAs' halves of the A chunk landed
+            VQ2_TRACE(1, 2 * (tt * a.n_dc + dc) + 1);
+            tc_fence_after();
+          }
+          if (lane == 0) {
+            const uint64_t ad = make_desc(sbase + Tc2Smem::off_a + dc * kTileBytes);
+            const uint64_t bd = make_desc(sbase + Tc2Smem::off_b + (cc * a.n_dc + dc) * kTileBytes);
+#pragma unroll
+            for (int k = 0; k < kDChunk / 16; ++k)
+              tc_mma_f16_2cta(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), k2Idesc, (dc | k) ? 1u : 0u);
+            if (cc == a.n_cc - 1) tc_commit_2cta(bar_empty + 8 * dc);   // A slot free in both CTAs
+          }
+          __syncwarp();
+        }
+        if (lane == 0) {
+          const uint64_t baug = make_desc_noswz(sbase + Tc2Smem::off_baug + cc * k2AugBytes, 128, 256);
+          tc_mma_f16_2cta(d_tmem, aaug, baug, k2Idesc, 1u);             // + s |e_k|^2
+          tc_commit_2cta(bar_tfull + 8 * buf);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 12) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+template <int MODE>
+static int launch_mode2(const Tc2Args& a, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(assign_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Smem::total);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  assign_tc2_kernel<MODE><<<grid, k2Threads, Tc2Smem::total, st>>>(a);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+bool tc2_supported(int n_cc, int n_dc) { return n_dc <= k2ASlots && n_cc <= k2MaxCC && n_cc * n_dc <= k2MaxBTiles; }
+
+int launch_assign_tc2(const Tc2Args& a, cudaStream_t st) {
+  int pairs = num_sms() / 2;
+  if (a.n_ptiles < pairs) pairs = a.n_ptiles;
+  if (pairs <= 0) return 0;
+  const int grid = 2 * pairs;
+  const bool al16 = (reinterpret_cast<uintptr_t>(a.x.ptr) & 15) == 0 && (a.x.sB & 3) == 0;
+  if (al16 && a.x.sP == 1 && (a.x.P & 3) == 0 && (a.x.sD & 3) == 0) return launch_mode2<0>(a, grid, st);
+  if (al16 && a.x.sD == 1 && (a.x.D & 3) == 0 && (a.x.sP & 3) == 0) return launch_mode2<1>(a, grid, st);
+  return launch_mode2<2>(a, grid, st);
+}
+
+}  // namespace vqseg

@@ -35,6 +35,7 @@ struct RowsOut {
 // [1024] enorm  : K_pad fp32, |e_k|^2 in torch's CPU pow(2).sum(-1) order (pads = +inf marker 3e38)
 // [..]   image  : fp16 (-2*s*E) as SWIZZLE_128B K-major tiles of 128 codes x 64 dims (16 KiB each),
 //                 ordered [code_block][d_chunk]
+// [..]   aug    : per code block a 4 KiB SWIZZLE_NONE tile (128 codes x 16 fp16): cols 0..2 = limbs of s|e|^2/aug_c
 struct BlobHeader {
   uint32_t magic;        // 'VQSB'
   int32_t  K, D, K_pad, D_pad;      // K_pad multiple of 256, D_pad multiple of 64
@@ -42,7 +43,9 @@ struct BlobHeader {
   float    max_enorm;    // max_k |e_k|^2  (fp32, >= true value)
   uint32_t max_enorm_bits;          // written with atomicMax on the float bits
   uint32_t max_abs_bits;            // max |e_kd| bits
-  uint64_t off_enorm, off_image;
+  uint64_t off_enorm, off_image, off_aug;
+  float    aug_c;        // power of two: s|e_k|^2 = aug_c * (h1 + h2 + h3), three fp16 limbs per code
+  uint32_t flags;        // bit 0: limbs not representable -> tensor-core filter must defer every row
 };
 constexpr uint32_t kBlobMagic = 0x42535156u;
 constexpr int kCodeBlock = 128;     // codes per packed tile

@@ -12,6 +12,7 @@ from . import _native
 
 ALGO_AUTO, ALGO_EXACT, ALGO_TC = 0, 1, 2
 MODE_EVAL, MODE_TRAIN, MODE_TRAIN_AMP, MODE_EVAL_AMP = 0, 1, 2, 3
+_last_assign_ws = None
 
 
 def _stream():
@@ -55,7 +56,8 @@ def prepare_codebook(codebook: torch.Tensor) -> torch.Tensor:
 def _(codebook):
     k, d = codebook.shape
     kp, dp = (k + 255) // 256 * 256, (d + 63) // 64 * 64
-    return codebook.new_empty(1024 + ((2 * kp * 4 + 1023) // 1024) * 1024 + kp * dp * 2, dtype=torch.uint8)
+    return codebook.new_empty(1024 + ((2 * kp * 4 + 1023) // 1024) * 1024 + kp * dp * 2 + (kp // 128) * 4096,
+                              dtype=torch.uint8)
 
 
 @torch.library.custom_op("vqseg::assign", mutates_args=())
@@ -80,6 +82,8 @@ def assign(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor]
                                          blob.data_ptr() if blob is not None else None,
                                          idx.data_ptr(), counts.data_ptr(), None, 0, kblock, algo,
                                          ws.data_ptr(), nws, _stream()), "assign")
+    global _last_assign_ws
+    _last_assign_ws = ws            # dev diagnostics: ws[0:4] = number of rows sent to the exact pass
     return idx, counts
 
 
