@@ -64,7 +64,14 @@ def stage_tc():
         mism = (idx.cpu() != gi).sum().item()
         mism_e = (idx != idx_e).sum().item()
         cm = (counts != counts_e).sum().item()
-        flagged = ops._last_assign_ws[:4].view(torch.int32).item()
+        ws = ops._last_assign_ws
+        flagged = ws[:4].view(torch.int32).item()
+        nrows = gi.numel()
+        r256 = lambda v: (v + 255) // 256 * 256
+        wr = ws[256:256 + 4 * nrows].view(torch.int32)[:flagged].long()
+        cc = ws[256 + r256(4 * nrows):256 + r256(4 * nrows) + 4 * nrows].view(torch.int32)
+        hist = torch.bincount(cc[wr].clamp(0, 9), minlength=10).tolist() if flagged else []
+        print("      candidate-count histogram of rescored rows (9 = all codes):", hist)
         print(f"[tc] {name:16s} vs golden {mism}/{gi.numel()}  vs exact {mism_e}  counts mism {cm}  rescored rows {flagged} ({100.0 * flagged / gi.numel():.1f}%)  {'PASS' if mism_e == 0 and cm == 0 else 'FAIL'}", flush=True)
 
 
@@ -109,11 +116,28 @@ def stage_time():
     xd, ed = x.to(dev), e.to(dev)
     xv = view(xd)
     blob = ops.prepare_codebook(ed)
+    from vq_seg_b200 import _native
+    L = _native.lib()
     for algo, nm in [(ops.ALGO_EXACT, "exact"), (ops.ALGO_TC, "tc+rescore")]:
-        if algo == ops.ALGO_TC and "notc" in sys.argv:
+        if algo == ops.ALGO_EXACT and "noexact" in sys.argv:
             continue
         med, best = timeit(lambda: ops.assign(xv, ed, blob, algo), n=10 if algo == ops.ALGO_EXACT else 50)
-        print(f"[time] assign {nm:10s} C2: median {med:9.1f} us best {best:9.1f} us -> {32768 / med:.3f} Gvec/s... {2*32768*512*256/med/1e6:.1f} TFLOP/s", flush=True)
+        print(f"[time] assign {nm:10s} C2 (x L2-resident): median {med:9.1f} us best {best:9.1f} us -> {2*32768*512*256/med/1e6:.1f} TFLOP/s", flush=True)
+    L.vqseg_set_kernel_timing(1)
+    kt, rt = [], []
+    for _ in range(20):
+        ops.assign(xv, ed, blob, ops.ALGO_TC); torch.cuda.synchronize()
+        kt.append(L.vqseg_get_kernel_timing_ms(0) * 1e3); rt.append(L.vqseg_get_kernel_timing_ms(1) * 1e3)
+    # cold-L2 variant: thrash L2 between calls
+    junk = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    kc, rc = [], []
+    for _ in range(20):
+        junk.fill_(1); ops.assign(xv, ed, blob, ops.ALGO_TC); torch.cuda.synchronize()
+        kc.append(L.vqseg_get_kernel_timing_ms(0) * 1e3); rc.append(L.vqseg_get_kernel_timing_ms(1) * 1e3)
+    L.vqseg_set_kernel_timing(0)
+    kt.sort(); rt.sort(); kc.sort(); rc.sort()
+    print(f"[time] filter kernel  : warm-L2 median {kt[10]:.1f} us (best {kt[0]:.1f}); cold-L2 median {kc[10]:.1f} us (best {kc[0]:.1f})")
+    print(f"[time] rescore kernel : warm-L2 median {rt[10]:.1f} us (best {rt[0]:.1f}); cold-L2 median {rc[10]:.1f} us (best {rc[0]:.1f})", flush=True)
     idx, _ = ops.assign(xv, ed, blob, ops.ALGO_EXACT)
     med, best = timeit(lambda: ops.prepare_codebook(ed), n=50)
     print(f"[time] prepare_codebook: median {med:.1f} us best {best:.1f}")
@@ -162,8 +186,20 @@ def stage_trace():
     L.vqseg_debug_set_trace(None)
     t = buf.cpu().reshape(148, 4, 256)
     torch.save(t, os.path.join(ROOT, "gpurun_out", "trace.pt"))
+    g = t[:, 3, :8]
+    g0 = g[:, 0].min().item()
+    print("globaltimer (ns since first CTA entry): entry min/max", (g[:, 0] - g0).min().item(), (g[:, 0] - g0).max().item(),
+          "| setup done min/max", (g[:, 1] - g0).min().item(), (g[:, 1] - g0).max().item(),
+          "| roles done (thread 0) min/max", (g[:, 2] - g0).min().item(), (g[:, 2] - g0).max().item(),
+          "| exit min/max", (g[:, 3] - g0).min().item(), (g[:, 3] - g0).max().item())
+    print("cta0 clocks: entry->setup", (g[0, 5] - g[0, 4]).item(), "setup->rolesdone(t0)", (g[0, 6] - g[0, 5]).item(), "teardown", (g[0, 7] - g[0, 6]).item())
+    L.vqseg_set_kernel_timing(1)
+    ops.assign(xv, ed, blob, ops.ALGO_TC); torch.cuda.synchronize()
+    print("event-timed filter kernel us:", L.vqseg_get_kernel_timing_ms(0) * 1e3)
+    L.vqseg_set_kernel_timing(0)
     for cta in (0, 100):
-        tt = t[cta]
+        tt = t[cta].clone()
+        tt[3, :8] = 0
         t0 = tt[tt > 0].min().item()
         names = ["producer(w0)", "mma", "epilogue(q0)", "bloader"]
         for role in range(4):

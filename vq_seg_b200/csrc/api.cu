@@ -12,6 +12,7 @@ struct ExactArgs {
   const int* work_rows; const int* work_count;
   const int* cand_idx; const int* cand_cnt; int cand_cap;
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
+  int stage_e;
 };
 int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st);
 int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st);

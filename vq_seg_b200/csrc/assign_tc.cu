@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (lane == 0) mbar_arrive_relaxed(bar_full + 8 * s);
       pit += 1;
       if (++p_in_tile == per_tile) { p_in_tile = 0; p_tile += 1; }
     };

@@ -10,17 +10,18 @@
 //     converted once;
 //   * |e_k|^2 enters through one extra K=16 MMA step against a constant column (three fp16 limbs), so the
 //     accumulator IS the score and TMEM is never written by the SM;
-//   * the next tile's fp32 rows wait in REGISTERS (4 chunks x 32 regs per producer thread, register budget
-//     moved to the producers with setmaxnreg) while the current tile's fp16 operand sits in smem;
+//   * the next three 64-dim chunks of fp32 rows wait in REGISTERS (3 x 32 regs per producer thread, register
+//     budget moved to the producers with setmaxnreg) while the current tile's fp16 operand sits in smem;
 //   * the epilogue reads each accumulator exactly once: per 32 columns block-min -> running threshold ->
 //     sign-bit mask (one FADD + one funnel shift per score) -> short-list of code indices.
-// Roles per CTA (16 warps): 0-7 producers, 8-11 epilogue, 12 MMA issuer (leader CTA) + TMEM alloc,
-// 13 codebook loader (cp.async.bulk), 14-15 idle (they only donate registers).
+// Roles per CTA (20 warps): 0-7 producers, 8-15 epilogue (two warps per TMEM lane quarter, 128 columns
+// each), 16 MMA issuer (leader CTA) + TMEM alloc, 17 codebook loader (cp.async.bulk), 18-19 idle (they
+// only donate registers).
 #include "tc_common.cuh"
 
 namespace vqseg {
 
-constexpr int k2Threads = 512;
+constexpr int k2Threads = 640;                // 20 warps: 8 producers, 8 epilogue, MMA, loader, 2 idle
 constexpr int k2Rows = 128;                 // rows per CTA per tile (pair tile = 256)
 constexpr int k2ASlots = 4;                 // A ring = one tile (D_pad <= 256)
 constexpr int k2MaxBTiles = 8;              // resident 16 KiB codebook tiles per CTA
@@ -35,14 +36,15 @@ struct Tc2Smem {
   static constexpr int off_a = off_b + k2MaxBTiles * kTileBytes;           // [k2ASlots] 16 KiB
   static constexpr int off_baug = off_a + k2ASlots * kTileBytes;           // [k2MaxCC] 4 KiB
   static constexpr int off_aaug = off_baug + k2MaxCC * k2AugBytes;         // 4 KiB
-  static constexpr int off_cand = off_aaug + k2AugBytes;                   // [128][cap] int
-  static constexpr int off_xsq = off_cand + k2Rows * k2CandCap * 4;        // [bufs][128] float
+  static constexpr int off_cand = off_aaug + k2AugBytes;                   // [2 halves][128][cap] int
+  static constexpr int off_xchg = off_cand + 2 * k2Rows * k2CandCap * 4;    // [128] {m_run, cnt|overflow} of the upper-half warp
+  static constexpr int off_xsq = off_xchg + k2Rows * 8;                     // [bufs][128] float
   static constexpr int off_bar = off_xsq + k2XsqBufs * k2Rows * 4;
   static constexpr int n_bars = 2 * k2ASlots + 4 + 2;
   static constexpr int off_tmem = off_bar + 8 * n_bars;
   static constexpr int total = off_tmem + 16 + 1024;
 };
-static_assert(Tc2Smem::total <= 227 * 1024, "smem budget");
+static_assert(Tc2Smem::total <= 232448, "smem budget");
 
 struct Tc2Args {
   Rows x;
@@ -69,6 +71,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(a.blob);
+  auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+  if (a.trace && threadIdx.x == 0) { a.trace[((long long)blockIdx.x * 4 + 3) * 256 + 0] = gtime(); a.trace[((long long)blockIdx.x * 4 + 3) * 256 + 4] = clock64(); }
 
   const uint32_t bar_full = sbase + Tc2Smem::off_bar;                  // [slots]  leader: 16 producer-warp arrivals
   const uint32_t bar_empty = bar_full + 8 * k2ASlots;                  // [slots]  each CTA: 1 (multicast commit)
@@ -81,12 +85,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < k2ASlots; ++s) { mbar_init(bar_full + 8 * s, 16); mbar_init(bar_empty + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 16); }
     mbar_init(bar_bload, 1);
     mbar_init(bar_bready, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
@@ -95,6 +99,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (a.trace && threadIdx.x == 0) { a.trace[((long long)blockIdx.x * 4 + 3) * 256 + 1] = gtime(); a.trace[((long long)blockIdx.x * 4 + 3) * 256 + 5] = clock64(); }
 
   const int n_pairs = (int)gridDim.x >> 1;
   const int pair = (int)blockIdx.x >> 1;
@@ -105,7 +110,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
 
   if (warp < 8) {
     // ================= A producers =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
     const int g8 = lane & 7, quad = lane >> 3;
     const int r0 = 16 * warp + 4 * quad;
     const int D = (int)a.x.D;
@@ -178,32 +183,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_full + 8 * dc);        // leader's barrier (remote for rank 1)
+      if (lane == 0) mbar_arrive_cluster_relaxed(lead_full + 8 * dc);        // leader's barrier (remote for rank 1)
     };
 
-    float v0[4][8], v1[4][8], v2r[4][8], v3[4][8];
-    if (my_tiles > 0) {
-      decode(0);
-      load_chunk(v0, 0);
-      if (a.n_dc > 1) load_chunk(v1, 1);
-      if (a.n_dc > 2) load_chunk(v2r, 2);
-      if (a.n_dc > 3) load_chunk(v3, 3);
+    // flat chunk stream q = tt * n_dc + dc; three register buffers rotate, loads run 3 chunks ahead
+    const int total = my_tiles * a.n_dc;
+    int lq = 0, l_dc = 0, l_tt = 0;               // next chunk to load
+    auto load_next = [&](float (&v)[4][8]) {
+      if (lq >= total) return;
+      if (l_dc == 0) decode(l_tt);
+      load_chunk(v, l_dc);
+      ++lq;
+      if (++l_dc == a.n_dc) { l_dc = 0; ++l_tt; }
+    };
+    int sq = 0, s_dc = 0, s_tt = 0;               // next chunk to convert + store
+    auto store_next = [&](float (&v)[4][8]) {
+      if (sq >= total) return;
+      store_chunk(v, s_dc, s_tt);
+      ++sq;
+      if (++s_dc == a.n_dc) { s_dc = 0; ++s_tt; }
+    };
+    float va[4][8], vb[4][8], vc[4][8];
+    load_next(va); load_next(vb); load_next(vc);
+    while (sq < total) {
+      store_next(va); load_next(va);
+      store_next(vb); load_next(vb);
+      store_next(vc); load_next(vc);
     }
-    for (int tt = 0; tt < my_tiles; ++tt) {
-      const bool more = tt + 1 < my_tiles;
-      if (more) decode(tt + 1);
-      store_chunk(v0, 0, tt);                   if (more) load_chunk(v0, 0);
-      if (a.n_dc > 1) { store_chunk(v1, 1, tt);  if (more) load_chunk(v1, 1); }
-      if (a.n_dc > 2) { store_chunk(v2r, 2, tt); if (more) load_chunk(v2r, 2); }
-      if (a.n_dc > 3) { store_chunk(v3, 3, tt);  if (more) load_chunk(v3, 3); }
-    }
-  } else if (warp < 12) {
+  } else if (warp < 16) {
     // ================= epilogue =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    const int quarter = warp & 3;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
+    const int half = (warp - 8) >> 2;                     // which 128 of the unit's 256 columns
     const int r = quarter * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    int* cand = reinterpret_cast<int*>(smem + Tc2Smem::off_cand) + r * k2CandCap;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 128;
+    int* cand = reinterpret_cast<int*>(smem + Tc2Smem::off_cand) + (half * k2Rows + r) * k2CandCap;
+    const int* cand_hi = reinterpret_cast<const int*>(smem + Tc2Smem::off_cand) + (k2Rows + r) * k2CandCap;
+    float2* xchg = reinterpret_cast<float2*>(smem + Tc2Smem::off_xchg) + r;
     float scale = 0.f, emax = 0.f;
     int u = 0;
     for (int tt = 0; tt < my_tiles; ++tt) {
@@ -214,12 +230,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
       bool overflow = false;
       for (int cc = 0; cc < a.n_cc; ++cc, ++u) {
         const int buf = u & 1;
-        if (quarter == 0) VQ2_TRACE(2, 4 * u);
+        if (warp == 8) VQ2_TRACE(2, 4 * u);
         mbar_wait(bar_tfull + 8 * buf, (uint32_t)(u >> 1) & 1);
         tc_fence_after();
-        if (quarter == 0) VQ2_TRACE(2, 4 * u + 1);
+        if (warp == 8) VQ2_TRACE(2, 4 * u + 1);
         if (cc == 0) {
-          if (tt == 0) { scale = hdr->scale; emax = sqrtf(hdr->max_enorm) * 1.0001f; overflow = false; }
+          if (tt == 0) { scale = hdr->scale; emax = sqrtf(hdr->max_enorm) * 1.0001f; }
           const float xn = sqrtf(xsq[(tt & (k2XsqBufs - 1)) * k2Rows + r]) * 1.0001f;
           const float e_s = emax * scale;
           const float sum = xn + emax;
@@ -231,7 +247,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
         }
         const uint32_t tb = lane_addr + buf * 256;
 #pragma unroll 1
-        for (int c = 0; c < 256; c += 32) {
+        for (int c = 0; c < 128; c += 32) {
           uint32_t v[32];
           tmem_ld32(tb + c, v);
           float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
@@ -244,56 +260,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
           if (m_run > m_new + slack) cnt = 0;          // every earlier entry scored >= the old minimum
           m_run = m_new;
           const float thr = m_run + slack;
-          uint32_t mka = 0u, mkb = 0u;
+          uint32_t mka = 0u, mkb = 0u, mkc = 0u, mkd = 0u;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t da = __float_as_uint(thr - __uint_as_float(v[j]));
-            const uint32_t db = __float_as_uint(thr - __uint_as_float(v[j + 16]));
-            mka = __funnelshift_l(da, mka, 1);
-            mkb = __funnelshift_l(db, mkb, 1);
+          for (int j = 0; j < 8; ++j) {
+            mka = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v[j])), mka, 1);
+            mkb = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v[j + 8])), mkb, 1);
+            mkc = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v[j + 16])), mkc, 1);
+            mkd = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v[j + 24])), mkd, 1);
           }
-          uint32_t mk = ~((mka << 16) | (mkb & 0xffffu));
+          uint32_t mk = ~((mka << 24) | ((mkb & 0xffu) << 16) | ((mkc & 0xffu) << 8) | (mkd & 0xffu));
           if (overflow) mk = 0u;
           while (mk) {
             const int j = __clz(mk);
             mk &= ~(0x80000000u >> j);
-            if (cnt < k2CandCap) cand[cnt++] = cc * 256 + c + j;
+            if (cnt < k2CandCap) cand[cnt++] = cc * 256 + half * 128 + c + j;
             else { overflow = true; mk = 0u; }
           }
         }
-        if (quarter == 0) VQ2_TRACE(2, 4 * u + 2);
+        if (warp == 8) VQ2_TRACE(2, 4 * u + 2);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);     // accumulator drained
+        if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);     // this warp's columns are drained
       }
-      const bool in_range = n < a.n_rows;
-      const int last = cnt > 0 ? cand[cnt - 1] : 0;
-      const bool unique = !overflow && cnt == 1 && !a.force_rescore && last < a.K;
-      if (in_range && unique) {
-        a.idx_out[n] = (long long)last + a.code_base;
-        if (a.counts_out) atomicAdd(a.counts_out + last, 1ull);
-      }
-      const bool flagged = in_range && !unique;
-      const uint32_t fm = __ballot_sync(0xffffffffu, flagged);
-      if (fm) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(a.work_count, __popc(fm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (flagged) {
-          int nc = 0;
-          if (!overflow)
-            for (int e = 0; e < cnt; ++e) {
-              int k = cand[e];
-              if (k < a.K) a.cand_idx[n * k2CandCap + nc++] = k;
+      // ---- tile done: the two column halves of each row meet (named barrier per lane quarter) ----
+      if (half == 1) *xchg = make_float2(m_run, __int_as_float(overflow ? -1 : cnt));
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      if (half == 0) {
+        const float2 o = *xchg;
+        int cnt1 = __float_as_int(o.y);
+        const float m = fminf(m_run, o.x);
+        if (cnt1 < 0) overflow = true;
+        // a half whose own minimum is out of range contributes nothing (all its entries scored >= that minimum)
+        if (m_run > m + slack) cnt = 0;
+        if (o.x > m + slack) cnt1 = 0;
+        const bool in_range = n < a.n_rows;
+        const int tot = overflow ? 0 : cnt + cnt1;
+        const int last = (!overflow && tot == 1) ? (cnt == 1 ? cand[0] : cand_hi[0]) : 0;
+        const bool unique = !overflow && tot == 1 && !a.force_rescore && last < a.K;
+        if (in_range && unique) {
+          a.idx_out[n] = (long long)last + a.code_base;
+          if (a.counts_out) atomicAdd(a.counts_out + last, 1ull);
+        }
+        const bool flagged = in_range && !unique;
+        const uint32_t fm = __ballot_sync(0xffffffffu, flagged);
+        if (fm) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(a.work_count, __popc(fm));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (flagged) {
+            int nc = 0;
+            if (!overflow) {
+              for (int e = 0; e < cnt; ++e) { int k = cand[e]; if (k < a.K && nc < k2CandCap) a.cand_idx[n * k2CandCap + nc++] = k; else if (k < a.K) overflow = true; }
+              for (int e = 0; e < cnt1; ++e) { int k = cand_hi[e]; if (k < a.K && nc < k2CandCap) a.cand_idx[n * k2CandCap + nc++] = k; else if (k < a.K) overflow = true; }
             }
-          a.cand_cnt[n] = (overflow || nc == 0) ? k2CandCap + 1 : nc;
-          a.work_rows[base + __popc(fm & ((1u << lane) - 1))] = (int)n;
+            a.cand_cnt[n] = (overflow || nc == 0) ? k2CandCap + 1 : nc;
+            a.work_rows[base + __popc(fm & ((1u << lane) - 1))] = (int)n;
+          }
         }
       }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // lists / xchg free for the next tile
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 13) {
+    if (warp == 17) {
       // ================= codebook loader: this CTA's half of every 256-code chunk stays resident =================
       {   // A-side augmentation tile: column 0..2 = c (power of two), rest 0; SWIZZLE_NONE core matrices
         const __half cval = __float2half_rn(hdr->aug_c);
@@ -322,23 +351,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
         mbar_wait(bar_bload, 0);
         mbar_arrive_cluster(mapa_u32(bar_bready, 0));
       }
-    } else if (warp == 12 && rank == 0) {
+    } else if (warp == 16 && rank == 0) {
       // ================= MMA issuer (leader CTA) =================
-      mbar_wait_cluster(bar_bready, 0);
+      mbar_wait(bar_bready, 0);
       tc_fence_after();
       const uint64_t aaug = make_desc_noswz(sbase + Tc2Smem::off_aaug, 128, 256);
       for (int u = 0; u < my_units; ++u) {
         const int tt = u / a.n_cc, cc = u - tt * a.n_cc;
         const int buf = u & 1;
         VQ2_TRACE(1, 128 + 2 * u);
-        mbar_wait_cluster(bar_tempty + 8 * buf, (((uint32_t)u >> 1) & 1) ^ 1);   // both epilogues drained it
+        mbar_wait(bar_tempty + 8 * buf, (((uint32_t)u >> 1) & 1) ^ 1);   // both epilogues drained it
         VQ2_TRACE(1, 128 + 2 * u + 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256;
         for (int dc = 0; dc < a.n_dc; ++dc) {
           if (cc == 0) {
             VQ2_TRACE(1, 2 * (tt * a.n_dc + dc));
-            mbar_wait_cluster(bar_full + 8 * dc, (uint32_t)tt & 1);    // both CTAs' halves of the A chunk landed
+            mbar_wait(bar_full + 8 * dc, (uint32_t)tt & 1);    // both CTAs' halves of the A chunk landed
             VQ2_TRACE(1, 2 * (tt * a.n_dc + dc) + 1);
             tc_fence_after();
           }
@@ -363,10 +392,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
   }
 
   // ---- teardown ----
+  if (a.trace && threadIdx.x == 0) { a.trace[((long long)blockIdx.x * 4 + 3) * 256 + 2] = gtime(); a.trace[((long long)blockIdx.x * 4 + 3) * 256 + 6] = clock64(); }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 12) {
+  if (a.trace && threadIdx.x == 0) { a.trace[((long long)blockIdx.x * 4 + 3) * 256 + 3] = gtime(); a.trace[((long long)blockIdx.x * 4 + 3) * 256 + 7] = clock64(); }
+  if (warp == 16) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }

@@ -40,8 +40,10 @@ __global__ void enorm_kernel(const float* __restrict__ E, int K, int D, int K_pa
 }
 
 // one augmented chain, generic block size. xs: shared x row, e: global code row
+template <bool LDG>
 __device__ __forceinline__ float chain_dist2(const float* __restrict__ xs, const float* __restrict__ e,
                                              int D, float xnorm, float enorm, int kb, bool vec4) {
+  auto ld = [](const float* p) { return LDG ? __ldg(p) : *p; };
   const int L = D + 2;
   if (kb <= 0 || kb > L) kb = L;
   float c = 0.f;
@@ -52,7 +54,7 @@ __device__ __forceinline__ float chain_dist2(const float* __restrict__ xs, const
     float t = 0.f;
     int j = blk;
     if (vec4) {
-      for (; j < dend && (j & 3); ++j) t = __fmaf_rn(xs[j], __ldg(e + j), t);
+      for (; j < dend && (j & 3); ++j) t = __fmaf_rn(xs[j], ld(e + j), t);
       for (; j + 4 <= dend; j += 4) {
         float4 ev = __ldg(reinterpret_cast<const float4*>(e + j));
         float4 xv = *reinterpret_cast<const float4*>(xs + j);
@@ -60,11 +62,42 @@ __device__ __forceinline__ float chain_dist2(const float* __restrict__ xs, const
         t = __fmaf_rn(xv.z, ev.z, t); t = __fmaf_rn(xv.w, ev.w, t);
       }
     }
-    for (; j < dend; ++j) t = __fmaf_rn(xs[j], __ldg(e + j), t);
+    for (; j < dend; ++j) t = __fmaf_rn(xs[j], ld(e + j), t);
     float s = -2.f * t;                                   // exact
     if (end > D) {
       if (blk <= D) s = __fadd_rn(s, xnorm);              // term D   : |x|^2 * 1
       if (end > D + 1) s = __fadd_rn(s, enorm);           // term D+1 : 1 * |e|^2
+    }
+    c = first ? s : __fadd_rn(c, s);
+    first = false;
+  }
+  return c;
+}
+
+// chain over smem-staged operands (both 16-byte aligned): loads are hoisted 8 terms ahead of the FMA chain
+__device__ __forceinline__ float chain_dist2_smem(const float* __restrict__ xs, const float* __restrict__ es,
+                                                  int D, float xnorm, float enorm, int kb) {
+  const int L = D + 2;
+  if (kb <= 0 || kb > L) kb = L;
+  float c = 0.f;
+  bool first = true;
+  for (int blk = 0; blk < L; blk += kb) {
+    const int end = min(blk + kb, L);
+    const int dend = min(end, D);
+    float t = 0.f;
+    int j = blk;
+    for (; j < dend && (j & 7); ++j) t = __fmaf_rn(xs[j], es[j], t);
+    for (; j + 8 <= dend; j += 8) {
+      const float4 x0 = *reinterpret_cast<const float4*>(xs + j), x1 = *reinterpret_cast<const float4*>(xs + j + 4);
+      const float4 e0 = *reinterpret_cast<const float4*>(es + j), e1 = *reinterpret_cast<const float4*>(es + j + 4);
+      t = __fmaf_rn(x0.x, e0.x, t); t = __fmaf_rn(x0.y, e0.y, t); t = __fmaf_rn(x0.z, e0.z, t); t = __fmaf_rn(x0.w, e0.w, t);
+      t = __fmaf_rn(x1.x, e1.x, t); t = __fmaf_rn(x1.y, e1.y, t); t = __fmaf_rn(x1.z, e1.z, t); t = __fmaf_rn(x1.w, e1.w, t);
+    }
+    for (; j < dend; ++j) t = __fmaf_rn(xs[j], es[j], t);
+    float s = -2.f * t;
+    if (end > D) {
+      if (blk <= D) s = __fadd_rn(s, xnorm);
+      if (end > D + 1) s = __fadd_rn(s, enorm);
     }
     c = first ? s : __fadd_rn(c, s);
     first = false;
@@ -138,6 +171,7 @@ struct ExactArgs {
   const int* work_rows; const int* work_count;        // flagged row ids, device counter
   const int* cand_idx; const int* cand_cnt; int cand_cap;   // per row: up to cand_cap codes; cnt > cap => all codes
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
+  int stage_e;
 };
 
 constexpr int kExactWarps = 8;
@@ -146,7 +180,9 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
   extern __shared__ __align__(16) float smem_x[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int D = (int)a.x.D;
-  float* xs = smem_x + (size_t)wib * ((D + 3) & ~3);
+  const int xs_stride = (D + 3) & ~3;
+  const bool stage_e = a.stage_e != 0;                   // smem also holds cand_cap code rows per warp
+  float* xs = smem_x + (size_t)wib * (xs_stride + (stage_e ? a.cand_cap * (xs_stride + 4) : 0));
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.E) & 15) == 0);
   const long long n_rows = a.x.n_rows();
   long long n_work = a.work_rows ? (long long)*a.work_count : n_rows;
@@ -163,13 +199,31 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
     int cnt = a.cand_cnt ? a.cand_cnt[n] : -1;
     if (cnt >= 0 && cnt <= a.cand_cap) {
       const int* cl = a.cand_idx + n * a.cand_cap;
-      for (int c0 = 0; c0 < cnt; c0 += 32) {
-        int c = c0 + lane;
-        if (c < cnt) {
-          int k = cl[c];
-          float c2 = chain_dist2(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, vec4);
-          float d = __fsqrt_rn(fmaxf(c2, 0.f));
-          lexmin(best, best_k, d, k);
+      if (stage_e) {
+        // short-list rows: stage the candidate code rows in smem with coalesced loads (row stride es_stride
+        // = D rounded to 4, + 4: 16-byte aligned rows, and the <= 8 lanes chaining different rows read
+        // disjoint bank quads), then lane c runs the chain of candidate c
+        float* es = xs + xs_stride;
+        const int es_stride = xs_stride + 4;
+        for (int c = 0; c < cnt; ++c) {
+          const float* er = a.E + (long long)cl[c] * D;
+          for (int j = lane; j < D; j += 32) es[c * es_stride + j] = __ldg(er + j);
+        }
+        __syncwarp();
+        if (lane < cnt) {
+          const int k = cl[lane];
+          float c2 = chain_dist2_smem(xs, es + lane * es_stride, D, xnorm, a.enorm[k], a.kblock);
+          lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), k);
+        }
+      } else {
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+          int c = c0 + lane;
+          if (c < cnt) {
+            int k = cl[c];
+            float c2 = chain_dist2<true>(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, vec4);
+            float d = __fsqrt_rn(fmaxf(c2, 0.f));
+            lexmin(best, best_k, d, k);
+          }
         }
       }
     } else {
@@ -181,7 +235,7 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             int k = k0 + 32 * q;
-            c4[q] = k < a.K ? chain_dist2(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, false) : 0.f;
+            c4[q] = k < a.K ? chain_dist2<true>(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, false) : 0.f;
           }
         }
 #pragma unroll
@@ -216,10 +270,14 @@ int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHead
   return 0;
 }
 
-int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st) {
+int launch_exact(const ExactArgs& a_in, long long max_work, cudaStream_t st) {
   if (max_work <= 0) return 0;
+  ExactArgs a = a_in;
   const int D = (int)a.x.D;
-  size_t smem = (size_t)kExactWarps * ((D + 3) & ~3) * sizeof(float);
+  const size_t xs_bytes = (size_t)((D + 3) & ~3) * sizeof(float);
+  const size_t es_bytes = (size_t)a.cand_cap * (((D + 3) & ~3) + 4) * sizeof(float);
+  a.stage_e = (a.cand_idx != nullptr && kExactWarps * (xs_bytes + es_bytes) <= 100 * 1024) ? 1 : 0;
+  size_t smem = (size_t)kExactWarps * (xs_bytes + (a.stage_e ? es_bytes : 0));
   if (smem > 200 * 1024) return VQSEG_EUNSUPPORTED;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -228,7 +286,7 @@ int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st) {
     configured = smem;
   }
   long long blocks = (max_work + kExactWarps - 1) / kExactWarps;
-  long long cap = (long long)num_sms() * 8;
+  long long cap = (long long)num_sms() * (a.stage_e ? 3 : 8);
   if (blocks > cap) blocks = cap;
   exact_score_kernel<<<(unsigned)blocks, kExactWarps * 32, smem, st>>>(a);
   VQSEG_LAUNCH_CHECK();

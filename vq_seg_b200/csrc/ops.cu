@@ -11,61 +11,89 @@ namespace vqseg {
 // Pixel-contiguous layout (NCHW: sP == 1).  A block owns a 64-pixel x 64-dim tile: codebook rows
 // are read along d (coalesced 128 B per code row segment) into a padded smem tile, then x / q are
 // streamed along pixels (coalesced).  algorithmic bytes: 4ND (x) + 4ND (q) + 8N (idx) + 4KD (E).
-constexpr int kGTile = 64;
+constexpr int kGTile = 64;       // dims per tile
+constexpr int kGPix = 128;       // pixels per tile
 
 __device__ __forceinline__ float round_fp16(float v) { return __half2float(__float2half_rn(v)); }
 
-template <int MODE>
+// VEC: pixel quads are 16-byte aligned and never straddle an image (P % 4 == 0, aligned bases)
+template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float* __restrict__ E, int K,
                                                              const long long* __restrict__ idx, RowsOut q,
                                                              float* __restrict__ partial) {
-  __shared__ float tile[kGTile][kGTile + 1];
-  __shared__ int s_idx[kGTile];
+  __shared__ float tile[kGTile][kGPix + 1];
+  __shared__ int s_idx[kGPix];
   __shared__ float s_red[8];
   const int D = (int)x.D;
   const long long n_rows = x.n_rows();
-  const long long n0 = (long long)blockIdx.x * kGTile;
+  const long long n0 = (long long)blockIdx.x * kGPix;
   const int d0 = blockIdx.y * kGTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x < kGTile) {
+  constexpr bool kTrain = (MODE == VQSEG_MODE_TRAIN || MODE == VQSEG_MODE_TRAIN_AMP);
+  constexpr bool kAmp = (MODE == VQSEG_MODE_TRAIN_AMP || MODE == VQSEG_MODE_EVAL_AMP);
+  if (threadIdx.x < kGPix) {
     long long n = n0 + threadIdx.x;
     long long k = n < n_rows ? idx[n] : 0;
     s_idx[threadIdx.x] = (int)(k < 0 ? 0 : (k >= K ? K - 1 : k));
   }
   __syncthreads();
-  // phase 1: gather code row segments, lanes along d
-  for (int p = warp; p < kGTile; p += 8) {
+  // phase 1: gather code row segments (256 B each), lanes along d
+  for (int p = warp; p < kGPix; p += 8) {
     const float* er = E + (long long)s_idx[p] * D + d0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       int d = lane + 32 * h;
       float v = (d0 + d < D) ? __ldg(er + d) : 0.f;
-      if (MODE == VQSEG_MODE_TRAIN_AMP || MODE == VQSEG_MODE_EVAL_AMP) v = round_fp16(v);
+      if (kAmp) v = round_fp16(v);
       tile[d][p] = v;
     }
   }
   __syncthreads();
-  // phase 2: stream pixels, lanes along p
+  // phase 2: stream pixels; lane owns 4 consecutive pixels, warps take the dims round-robin
   float acc = 0.f;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int p = lane + 32 * h;
-    const long long n = n0 + p;
+  const int p4 = lane * 4;
+  const long long n = n0 + p4;
+  if (VEC) {
     if (n < n_rows) {
       const long long b = n / x.P, pp = n - b * x.P;
-      const float* xb = x.ptr + b * x.sB + pp * x.sP;
-      float* qb = q.ptr + b * q.sB + pp * q.sP;
+      const float* xb = kTrain ? x.ptr + b * x.sB + pp : nullptr;
+      float* qb = q.ptr + b * q.sB + pp;
+#pragma unroll 4
       for (int d = warp; d < kGTile; d += 8) {
         if (d0 + d < D) {
-          float e = tile[d][p];
-          if (MODE == VQSEG_MODE_EVAL || MODE == VQSEG_MODE_EVAL_AMP) {
-            qb[(long long)(d0 + d) * q.sD] = e;
-          } else {
-            float xv = __ldg(xb + (long long)(d0 + d) * x.sD);
-            float qs = __fadd_rn(xv, __fsub_rn(e, xv));          // x + (q - x): two roundings (:236)
-            qb[(long long)(d0 + d) * q.sD] = qs;
-            float df = __fsub_rn(qs, xv);
-            acc = __fmaf_rn(df, df, acc);
+          float4 e = make_float4(tile[d][p4], tile[d][p4 + 1], tile[d][p4 + 2], tile[d][p4 + 3]);
+          float4 o = e;
+          if (kTrain) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + (long long)(d0 + d) * x.sD));
+            o.x = __fadd_rn(xv.x, __fsub_rn(e.x, xv.x)); o.y = __fadd_rn(xv.y, __fsub_rn(e.y, xv.y));   // x + (q - x)
+            o.z = __fadd_rn(xv.z, __fsub_rn(e.z, xv.z)); o.w = __fadd_rn(xv.w, __fsub_rn(e.w, xv.w));
+            float f;
+            f = __fsub_rn(o.x, xv.x); acc = __fmaf_rn(f, f, acc); f = __fsub_rn(o.y, xv.y); acc = __fmaf_rn(f, f, acc);
+            f = __fsub_rn(o.z, xv.z); acc = __fmaf_rn(f, f, acc); f = __fsub_rn(o.w, xv.w); acc = __fmaf_rn(f, f, acc);
+          }
+          *reinterpret_cast<float4*>(qb + (long long)(d0 + d) * q.sD) = o;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long ni = n + i;
+      if (ni < n_rows) {
+        const long long b = ni / x.P, pp = ni - b * x.P;
+        const float* xb = kTrain ? x.ptr + b * x.sB + pp * x.sP : nullptr;
+        float* qb = q.ptr + b * q.sB + pp * q.sP;
+        for (int d = warp; d < kGTile; d += 8) {
+          if (d0 + d < D) {
+            float e = tile[d][p4 + i];
+            float o = e;
+            if (kTrain) {
+              float xv = __ldg(xb + (long long)(d0 + d) * x.sD);
+              o = __fadd_rn(xv, __fsub_rn(e, xv));
+              float f = __fsub_rn(o, xv);
+              acc = __fmaf_rn(f, f, acc);
+            }
+            qb[(long long)(d0 + d) * q.sD] = o;
           }
         }
       }
@@ -152,10 +180,14 @@ static int launch_gather(const Rows& x, const float* E, int K, const long long* 
   const bool want_loss = train && loss_out != nullptr;
   int n_partial = 0;
   if (x.sP == 1 && q.sP == 1) {
-    dim3 grid((unsigned)((n_rows + kGTile - 1) / kGTile), (unsigned)((x.D + kGTile - 1) / kGTile));
+    dim3 grid((unsigned)((n_rows + kGPix - 1) / kGPix), (unsigned)((x.D + kGTile - 1) / kGTile));
     n_partial = (int)(grid.x * grid.y);
     if (want_loss && (size_t)n_partial > partial_cap) return VQSEG_EWORKSPACE;
-    gather_ste_pxc_kernel<MODE><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr);
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = (x.P % 4 == 0) && al(q.ptr) && (q.sD % 4 == 0) && (q.sB % 4 == 0) &&
+                     (!train || (al(x.ptr) && (x.sD % 4 == 0) && (x.sB % 4 == 0)));
+    if (vec) gather_ste_pxc_kernel<MODE, true><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr);
+    else     gather_ste_pxc_kernel<MODE, false><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr);
   } else {
     long long blocks = (n_rows + 7) / 8;
     long long cap = (long long)num_sms() * 16;
@@ -193,6 +225,22 @@ __global__ void __launch_bounds__(256) ste_bwd_kernel(View g, View x, View q, co
       r = __fmaf_rn(coef, __fsub_rn(xv, qv), gv);
     }
     o.ptr[b * o.sB + p * o.sP + d * o.sD] = r;
+  }
+}
+
+// same dense layout for all four tensors: flat, vectorised, memory order
+__global__ void __launch_bounds__(256) ste_bwd_flat_kernel(const float4* __restrict__ g, const float4* __restrict__ x,
+                                                           const float4* __restrict__ q, const float* __restrict__ coef_dev,
+                                                           float coef_scale, float4* __restrict__ o, long long n4) {
+  const float coef = coef_dev ? coef_scale * __ldg(coef_dev) : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 r = g ? __ldg(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (coef_dev) {
+      const float4 xv = __ldg(x + i), qv = __ldg(q + i);
+      r.x = __fmaf_rn(coef, __fsub_rn(xv.x, qv.x), r.x); r.y = __fmaf_rn(coef, __fsub_rn(xv.y, qv.y), r.y);
+      r.z = __fmaf_rn(coef, __fsub_rn(xv.z, qv.z), r.z); r.w = __fmaf_rn(coef, __fsub_rn(xv.w, qv.w), r.w);
+    }
+    o[i] = r;
   }
 }
 
@@ -453,7 +501,7 @@ using namespace vqseg;
 extern "C" {
 
 size_t vqseg_gather_workspace_bytes(int64_t n_rows, int64_t D) {
-  long long tiles = ((n_rows + kGTile - 1) / kGTile) * ((D + kGTile - 1) / kGTile);
+  long long tiles = ((n_rows + kGPix - 1) / kGPix) * ((D + kGTile - 1) / kGTile);
   long long generic = (long long)num_sms() * 16;
   long long n = tiles > generic ? tiles : generic;
   return (size_t)round_up(n * sizeof(float), 256);
@@ -492,6 +540,21 @@ int vqseg_ste_bwd_f32(const float* g_q, int64_t gB, int64_t gP, int64_t gD,
   if (!gx || B < 0 || P < 0 || D <= 0) return VQSEG_EINVAL;
   if (coef_dev && (!x || !q_ste)) return VQSEG_EINVAL;
   if (B * P == 0) return 0;
+  {
+    auto dense = [&](int64_t b, int64_t p, int64_t d) {
+      return (p == 1 && d == P && b == D * P) || (d == 1 && p == D && b == P * D);
+    };
+    auto same = [&](int64_t b, int64_t p, int64_t d) { return b == oB && p == oP && d == oD; };
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const long long total = B * P * D;
+    if (dense(oB, oP, oD) && (!g_q || same(gB, gP, gD)) && (!coef_dev || (same(sB, sP, sD) && same(qB, qP, qD))) &&
+        total % 4 == 0 && al(gx) && al(g_q) && al(x) && al(q_ste)) {
+      ste_bwd_flat_kernel<<<grid_for(total / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+          (const float4*)g_q, (const float4*)x, (const float4*)q_ste, coef_dev, coef_scale, (float4*)gx, total / 4);
+      VQSEG_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   View g{g_q, gB, gP, gD}, xv{x, sB, sP, sD}, qv{q_ste, qB, qP, qD};
   RowsOut o{gx, B, P, D, oB, oP, oD};
   bool px_fast = (oP == 1);

@@ -104,8 +104,20 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
   return r;
 }
+// Arrive on a (possibly remote) CTA's mbarrier.  Default semantics (.release.cta), like
+// cutlass::arch::ClusterBarrier::arrive(cta_id): a cluster-scope release would compile to a MEMBAR that
+// also waits for the producer's in-flight prefetch loads and serialises the pipeline.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Relaxed arrives for producers that still have prefetch loads in flight: a .release arrive compiles to
+// MEMBAR.ALL.CTA + SYNCS.ARRIVE and the MEMBAR waits for those loads.  Ordering of the operand stores is
+// provided by the fence.proxy.async every writing thread executes before the warp-level sync.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
