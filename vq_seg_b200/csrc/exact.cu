@@ -191,7 +191,13 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
     const long long n = a.work_rows ? a.work_rows[w] : w;
     const float* xr = a.x.row(n);
     __syncwarp();
-    for (int j = lane; j < D; j += 32) xs[j] = xr[(long long)j * a.x.sD];
+    for (int j0 = 0; j0 < D; j0 += 256) {               // 8 strided loads in flight per lane before the stores
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int j = j0 + lane + 32 * u; t[u] = j < D ? __ldg(xr + (long long)j * a.x.sD) : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int j = j0 + lane + 32 * u; if (j < D) xs[j] = t[u]; }
+    }
     __syncwarp();
     const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
     float best = __int_as_float(0x7f800000);   // +inf
@@ -205,9 +211,20 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
         // disjoint bank quads), then lane c runs the chain of candidate c
         float* es = xs + xs_stride;
         const int es_stride = xs_stride + 4;
-        for (int c = 0; c < cnt; ++c) {
-          const float* er = a.E + (long long)cl[c] * D;
-          for (int j = lane; j < D; j += 32) es[c * es_stride + j] = __ldg(er + j);
+        int kc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) kc[c] = c < cnt ? cl[c] : 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < cnt) {
+            const float* er = a.E + (long long)kc[c] * D;
+            if (vec4) {
+              for (int j = 4 * lane; j < D; j += 128)
+                *reinterpret_cast<float4*>(es + c * es_stride + j) = __ldg(reinterpret_cast<const float4*>(er + j));
+            } else {
+              for (int j = lane; j < D; j += 32) es[c * es_stride + j] = __ldg(er + j);
+            }
+          }
         }
         __syncwarp();
         if (lane < cnt) {

@@ -38,15 +38,22 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
   }
   __syncthreads();
   // phase 1: gather code row segments (256 B each), lanes along d
-  for (int p = warp; p < kGPix; p += 8) {
-    const float* er = E + (long long)s_idx[p] * D + d0;
+#pragma unroll 2
+  for (int p0 = warp; p0 < kGPix; p0 += 64) {           // 16 loads in flight per lane before the smem stores
+    float v[8][2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      int d = lane + 32 * h;
-      float v = (d0 + d < D) ? __ldg(er + d) : 0.f;
-      if (kAmp) v = round_fp16(v);
-      tile[d][p] = v;
+    for (int u = 0; u < 8; ++u) {
+      const float* er = E + (long long)s_idx[p0 + 8 * u] * D + d0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int d = lane + 32 * h;
+        v[u][h] = (d0 + d < D) ? __ldg(er + d) : 0.f;
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) tile[lane + 32 * h][p0 + 8 * u] = kAmp ? round_fp16(v[u][h]) : v[u][h];
   }
   __syncthreads();
   // phase 2: stream pixels; lane owns 4 consecutive pixels, warps take the dims round-robin
@@ -58,13 +65,23 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
       const long long b = n / x.P, pp = n - b * x.P;
       const float* xb = kTrain ? x.ptr + b * x.sB + pp : nullptr;
       float* qb = q.ptr + b * q.sB + pp;
-#pragma unroll 4
-      for (int d = warp; d < kGTile; d += 8) {
+      float4 xr[kGTile / 8];
+      if (kTrain) {                                        // all 8 row loads in flight before the first use
+#pragma unroll
+        for (int u = 0; u < kGTile / 8; ++u) {
+          const int d = warp + 8 * u;
+          xr[u] = (d0 + d < D) ? __ldg(reinterpret_cast<const float4*>(xb + (long long)(d0 + d) * x.sD))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGTile / 8; ++u) {
+        const int d = warp + 8 * u;
         if (d0 + d < D) {
           float4 e = make_float4(tile[d][p4], tile[d][p4 + 1], tile[d][p4 + 2], tile[d][p4 + 3]);
           float4 o = e;
           if (kTrain) {
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + (long long)(d0 + d) * x.sD));
+            const float4 xv = xr[u];
             o.x = __fadd_rn(xv.x, __fsub_rn(e.x, xv.x)); o.y = __fadd_rn(xv.y, __fsub_rn(e.y, xv.y));   // x + (q - x)
             o.z = __fadd_rn(xv.z, __fsub_rn(e.z, xv.z)); o.w = __fadd_rn(xv.w, __fsub_rn(e.w, xv.w));
             float f;
