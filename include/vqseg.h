@@ -58,6 +58,9 @@ void        vqseg_debug_set_trace(void* dev_buf);
 /* developer tool: 1 -> always use the streaming single-CTA tcgen05 kernel, even when the codebook-resident
  * CTA-pair kernel applies (lets the tests cover both on the same shapes).                              */
 void        vqseg_debug_force_streaming_kernel(int on);
+/* developer micro-benchmark: global->register bandwidth of the producer access patterns (csrc/debug_bw.cu) */
+int         vqseg_debug_load_bandwidth(const float* x, int64_t n_floats, int64_t row_stride, int pattern, int depth,
+                                       float* sink, void* stream);
 const char* vqseg_error_string(int code);
 
 /* ---- codebook preparation --------------------------------------------------------------------

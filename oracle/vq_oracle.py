@@ -225,6 +225,7 @@ class OracleVectorQuantizer(torch.nn.Module):
             cb.initted = True
         self.codebook = cb
         self.kmeans_init_indices = None   # test hook: injected init rows
+        self.faithful_ops = False         # True: run the reference's literal op sequence (one_hot + matmul, :169-170)
 
     def forward(self, x):
         x = x.to(torch.float32)
@@ -242,12 +243,19 @@ class OracleVectorQuantizer(torch.nn.Module):
         if self.distance == "cosine":
             weight.data.copy_(l2norm(weight.data))
         with torch.no_grad():
-            idx = (assign_euclidean(x_bnc, weight) if self.distance == "euclidean"
-                   else assign_cosine(x_bnc, weight))
-        quantized = weight[idx]
+            if self.faithful_ops and self.distance == "euclidean":
+                idx = torch.argmin(torch.cdist(x_bnc, weight, p=2), dim=-1)
+            else:
+                idx = (assign_euclidean(x_bnc, weight) if self.distance == "euclidean"
+                       else assign_cosine(x_bnc, weight))
+        if self.faithful_ops:
+            onehot = torch.nn.functional.one_hot(idx, num_classes=cb.num_embeddings)
+            quantized = torch.matmul(onehot.float(), weight)
+        else:
+            quantized = weight[idx]
         counts = torch.bincount(idx.reshape(-1), minlength=cb.num_embeddings)
         usage = code_usage_from_counts(counts, cb.num_embeddings)
-        loss = torch.tensor([0.0], requires_grad=self.training, dtype=torch.float32)
+        loss = torch.tensor([0.0], device=x.device, requires_grad=self.training, dtype=torch.float32)
         if self.training:
             quantized = x_bnc + (quantized - x_bnc).detach()
             if self.commitment_weight > 0:

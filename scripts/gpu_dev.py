@@ -170,6 +170,28 @@ def stage_prof():
     print("prof done", idx.sum().item(), mse.item(), u.item())
 
 
+def stage_bw():
+    from vq_seg_b200 import _native
+    L = _native.lib()
+    x = torch.randn(8 * 256 * 4096, device=dev)          # 33.5 MB, rows of 4096 floats (one image's d-row)
+    sink = torch.zeros(4, device=dev)
+    junk = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for (pat, depth, nm) in [(0, 8, "LDG.128 8x64B/instr"), (1, 4, "LDG.256 8x128B/instr"), (2, 8, "LDG.128 512B contiguous")]:
+        for cold in (False, True):
+            ts = []
+            for _ in range(10):
+                if cold:
+                    junk.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                rc = L.vqseg_debug_load_bandwidth(x.data_ptr(), x.numel(), 4096, pat, depth, sink.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                b.record(); torch.cuda.synchronize()
+                assert rc == 0
+                ts.append(a.elapsed_time(b) * 1e3)
+            ts.sort()
+            print(f"[bw] {nm:26s} {'cold' if cold else 'L2-warm':8s}: median {ts[5]:7.1f} us -> {x.numel() * 4 / ts[5] / 1e6:6.2f} TB/s (best {ts[0]:.1f} us)")
+
+
 def stage_trace():
     from vq_seg_b200 import _native
     L = _native.lib()
@@ -179,12 +201,15 @@ def stage_trace():
     blob = ops.prepare_codebook(ed)
     for _ in range(3):
         ops.assign(xv, ed, blob, ops.ALGO_TC)
-    buf = torch.zeros(148 * 4 * 256, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148 * 4 * 256 + 8, dtype=torch.int64, device=dev)
+    buf[-8] = 2 ** 62
     L.vqseg_debug_set_trace(buf.data_ptr())
     ops.assign(xv, ed, blob, ops.ALGO_TC)
     torch.cuda.synchronize()
     L.vqseg_debug_set_trace(None)
-    t = buf.cpu().reshape(148, 4, 256)
+    ex = buf[-8:].cpu()
+    print('rescoring kernel: globaltimer span us', (ex[1] - ex[0]).item() / 1e3, 'rows', ex[7].item(), 'mean cycles per row: rowid', ex[2].item() // max(ex[7].item(), 1), 'wave2', ex[3].item() // max(ex[7].item(), 1), 'wave3', ex[4].item() // max(ex[7].item(), 1), 'xnorm', ex[5].item() // max(ex[7].item(), 1), 'chain', ex[6].item() // max(ex[7].item(), 1))
+    t = buf[:-8].cpu().reshape(148, 4, 256)
     torch.save(t, os.path.join(ROOT, "gpurun_out", "trace.pt"))
     g = t[:, 3, :8]
     g0 = g[:, 0].min().item()
@@ -210,5 +235,5 @@ def stage_trace():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

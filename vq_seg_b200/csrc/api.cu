@@ -13,6 +13,7 @@ struct ExactArgs {
   const int* cand_idx; const int* cand_cnt; int cand_cap;
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
   int stage_e;
+  long long* trace;
 };
 int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st);
 int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st);
@@ -51,7 +52,7 @@ constexpr int kCandCapHost = 8;
 
 __global__ void blob_init_kernel(BlobHeader* h, int K, int D, int K_pad, int D_pad, unsigned long long off_enorm,
                                  unsigned long long off_image, unsigned long long off_aug) {
-  h->off_aug = off_aug; h->aug_c = 1.f; h->flags = 0u;
+  h->off_aug = off_aug; h->aug_c = 1.f; h->flags = 0u; h->max_de2_bits = 0u;
   h->magic = kBlobMagic; h->K = K; h->D = D; h->K_pad = K_pad; h->D_pad = D_pad;
   h->scale = 1.f; h->max_enorm = 0.f; h->max_enorm_bits = 0u; h->max_abs_bits = 0u;
   h->off_enorm = off_enorm; h->off_image = off_image;
@@ -243,6 +244,7 @@ int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
   if (g_timing) g_ev_valid[0] = 1;
   ea.work_rows = work_rows; ea.work_count = work_count;
   ea.cand_idx = cand_idx; ea.cand_cnt = cand_cnt; ea.cand_cap = kCandCapHost;
+  ea.trace = g_trace ? g_trace + 148 * 4 * 256 : nullptr;      // dev tool: 8 int64 after the filter's trace area
   ev_record(2, st);
   rc = launch_exact(ea, n_rows, st);
   ev_record(3, st);

@@ -39,8 +39,8 @@ struct TcSmem {
   static constexpr int off_a = 0;
   static constexpr int off_b = off_a + kStages * kAStageBytes;
   static constexpr int off_cand = off_b + kStages * kBStageBytes;            // [128][kCandCap] code indices
-  static constexpr int off_xsq = off_cand + kTileM * kCandCap * 4;           // [kXsqBufs][128] float
-  static constexpr int off_enorm = off_xsq + kXsqBufs * kTileM * 4;          // [kEnormSmem] float: s*|e|^2
+  static constexpr int off_xsq = off_cand + kTileM * kCandCap * 4;           // [kXsqBufs][128] float2 {|x|^2, |fp16(x)-x|^2}
+  static constexpr int off_enorm = off_xsq + kXsqBufs * kTileM * 8;          // [kEnormSmem] float: s*|e|^2
   static constexpr int off_bar = off_enorm + kEnormSmem * 4;                 // mbarriers
   static constexpr int off_tmem = off_bar + 8 * (2 * kStages + 4);
   static constexpr int total = off_tmem + 16 + 1024;   // + slack for the runtime 1024-B alignment
@@ -131,6 +131,24 @@ __global__ void __launch_bounds__(256) pack_codebook_kernel(const float* __restr
   }
 }
 
+// rounding error of the fp16 codebook operand, per code, exact: one warp per code -> header max
+__global__ void __launch_bounds__(256) codebook_rounding_error_kernel(const float* __restrict__ E, int K, int D,
+                                                                      unsigned char* __restrict__ blob) {
+  BlobHeader* hdr = reinterpret_cast<BlobHeader*>(blob);
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const float s = hdr->scale;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = -2.f * s * E[(long long)k * D + d];
+    const float df = __half2float(__float2half_rn(v)) - v;
+    acc = fmaf(df, df, acc);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) atomicMax(&hdr->max_de2_bits, __float_as_uint(acc * 1.0001f));
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------
 // MODE 0: pixel-contiguous float4 loads (NCHW), 1: dim-contiguous float4 (packed rows), 2: scalar, any strides
 template <int MODE>
@@ -199,15 +217,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ls.rv[0] && d0 + j < D) f = __ldg(reinterpret_cast<const float4*>(p0 + (long long)j * a.x.sD));
+          if (ls.rv[0] && d0 + j < D) f = ldg_stream_f4(p0 + (long long)j * a.x.sD);
           v[0][j] = f.x; v[1][j] = f.y; v[2][j] = f.z; v[3][j] = f.w;
         }
       } else if (mode == 1) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-          if (ls.rv[i] && d0 + 4 <= D) f0 = __ldg(reinterpret_cast<const float4*>(ls.rp[i] + d0));
-          if (ls.rv[i] && d0 + 8 <= D) f1 = __ldg(reinterpret_cast<const float4*>(ls.rp[i] + d0 + 4));
+          if (ls.rv[i] && d0 + 4 <= D) f0 = ldg_stream_f4(ls.rp[i] + d0);
+          if (ls.rv[i] && d0 + 8 <= D) f1 = ldg_stream_f4(ls.rp[i] + d0 + 4);
           v[i][0] = f0.x; v[i][1] = f0.y; v[i][2] = f0.z; v[i][3] = f0.w;
           v[i][4] = f1.x; v[i][5] = f1.y; v[i][6] = f1.z; v[i][7] = f1.w;
         }
@@ -216,14 +234,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            v[i][j] = (ls.rv[i] && d0 + j < D) ? __ldg(ls.rp[i] + (long long)(d0 + j) * a.x.sD) : 0.f;
+            v[i][j] = (ls.rv[i] && d0 + j < D) ? ldg_stream_f1(ls.rp[i] + (long long)(d0 + j) * a.x.sD) : 0.f;
       }
       ls.it += 1; ls.rem -= 1;
       ls.dc = (ls.dc + 1 == a.n_dc) ? 0 : ls.dc + 1;
     };
 
     int pit = 0, p_in_tile = 0, p_tile = 0;       // chunk being converted, its position in the tile
-    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+    float ss[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f};
     auto store_chunk = [&](float (&v)[4][8]) {
       if (pit >= total) return;
       const int s = pit & (kStages - 1);
@@ -239,23 +257,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-          if (first_pass) { ss[i] = fmaf(v[i][j], v[i][j], ss[i]); ss[i] = fmaf(v[i][j + 1], v[i][j + 1], ss[i]); }
           __half2 h = __floats2half2_rn(v[i][j], v[i][j + 1]);
+          if (first_pass) {
+            const float2 hb = __half22float2(h);
+            const float d0 = hb.x - v[i][j], d1 = hb.y - v[i][j + 1];
+            ss[i] = fmaf(v[i][j], v[i][j], ss[i]); ss[i] = fmaf(v[i][j + 1], v[i][j + 1], ss[i]);
+            sd[i] = fmaf(d0, d0, sd[i]); sd[i] = fmaf(d1, d1, sd[i]);
+          }
           pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(at + r * 128 + ((g8 ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       if (p_in_tile == a.n_dc - 1) {                         // row norms complete: publish before the arrive
-        float* xs = xsq + (p_tile & (kXsqBufs - 1)) * kTileM;
+        float2* xs = reinterpret_cast<float2*>(xsq) + (p_tile & (kXsqBufs - 1)) * kTileM;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float v2 = ss[i];
-          v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
-          v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
-          v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
-          // any |x_d| >= 65504 overflows the fp16 operand; it also makes the sum >= 4.29e9
-          if (g8 == 0) xs[r0 + i] = (v2 < 4.0e9f) ? v2 : __int_as_float(0x7f800000);
-          ss[i] = 0.f;
+          float v2 = ss[i], e2 = sd[i];
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 1); e2 += __shfl_xor_sync(0xffffffffu, e2, 1);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 2); e2 += __shfl_xor_sync(0xffffffffu, e2, 2);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 4); e2 += __shfl_xor_sync(0xffffffffu, e2, 4);
+          // |x|^2 and |fp16(x) - x|^2 (inf when an element overflows fp16: the row then goes to the exact pass)
+          if (g8 == 0) xs[r0 + i] = make_float2(v2, e2);
+          ss[i] = 0.f; sd[i] = 0.f;
         }
       }
       fence_proxy_async();
@@ -331,7 +354,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
     int* cand = reinterpret_cast<int*>(smem + TcSmem::off_cand) + r * kCandCap;
     const float emax = sqrtf(hdr->max_enorm) * 1.0001f;
     const float e_s = emax * scale;
-    const float sqrt_dpad = sqrtf((float)(a.n_dc * kDChunk));
+    const float de_max = sqrtf(__uint_as_float(hdr->max_de2_bits)) * 1.0001f;
 
     if (en_smem) {                                        // s*|e_k|^2 for every code, staged once per CTA
       float* dst = reinterpret_cast<float*>(smem + TcSmem::off_enorm);
@@ -375,11 +398,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
         if (quarter == 0) VQ_TRACE(2, 4 * u + 1);
         if (cc == 0) {
           // all A chunks of this tile's first unit are in: the row's sum of x^2 has been published
-          const float xn = sqrtf(xsq[(t & (kXsqBufs - 1)) * kTileM + r]) * 1.0001f;
+          const float2 nr = reinterpret_cast<const float2*>(xsq)[(t & (kXsqBufs - 1)) * kTileM + r];
+          const float xn = sqrtf(nr.x) * 1.0001f, dn = sqrtf(nr.y) * 1.0001f;
           const float sum = xn + emax;
-          // |approx - exact| bound, scaled domain (scores are s * (|e|^2 - 2 x.e)):
-          //   fp16 operand rounding (both sides) + fp16 subnormal floor + fp32 chain error of the exact scorer
-          slack = a.tau * xn * e_s + 2.4e-7f * sqrt_dpad * (e_s + xn) + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum;
+          // |approx - exact| <= |dx| |e^| + |x| |de|  (Cauchy-Schwarz on the ACTUAL operand rounding errors,
+          // both measured exactly: dx by the producers, de by codebook_rounding_error_kernel), two-sided, plus
+          // the fp32 accumulation error of the tensor core and of the exact scorer's chain (scaled domain)
+          slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum;
           if (!(slack < 3.0e38f)) overflow = true;                                   // fp16 overflow in this row
         }
         const uint32_t tb = lane_addr + buf * kUnitN;
@@ -472,6 +497,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
 int launch_pack(const float* E, int K, int D, unsigned char* blob, cudaStream_t st) {
   int blocks = num_sms() * 2;
   pack_codebook_kernel<<<blocks, 256, 0, st>>>(E, K, D, blob);
+  VQSEG_LAUNCH_CHECK();
+  codebook_rounding_error_kernel<<<(K * 32 + 255) / 256, 256, 0, st>>>(E, K, D, blob);
   VQSEG_LAUNCH_CHECK();
   return 0;
 }

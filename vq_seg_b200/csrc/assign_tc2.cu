@@ -38,9 +38,9 @@ struct Tc2Smem {
   static constexpr int off_aaug = off_baug + k2MaxCC * k2AugBytes;         // 4 KiB
   static constexpr int off_cand = off_aaug + k2AugBytes;                   // [2 halves][128][cap] int
   static constexpr int off_xchg = off_cand + 2 * k2Rows * k2CandCap * 4;    // [128] {m_run, cnt|overflow} of the upper-half warp
-  static constexpr int off_xsq = off_xchg + k2Rows * 8;                     // [bufs][128] float
-  static constexpr int off_bar = off_xsq + k2XsqBufs * k2Rows * 4;
-  static constexpr int n_bars = 2 * k2ASlots + 4 + 2;
+  static constexpr int off_xsq = off_xchg + k2Rows * 8;                     // [bufs][128] float2 {|x|^2, |fp16(x)-x|^2}
+  static constexpr int off_bar = off_xsq + k2XsqBufs * k2Rows * 8;
+  static constexpr int n_bars = 2 * k2ASlots + 4 + 2 * k2MaxCC;
   static constexpr int off_tmem = off_bar + 8 * n_bars;
   static constexpr int total = off_tmem + 16 + 1024;
 };
@@ -78,16 +78,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
   const uint32_t bar_empty = bar_full + 8 * k2ASlots;                  // [slots]  each CTA: 1 (multicast commit)
   const uint32_t bar_tfull = bar_empty + 8 * k2ASlots;                 // [2]      each CTA: 1 (multicast commit)
   const uint32_t bar_tempty = bar_tfull + 16;                          // [2]      leader: 8 epilogue-warp arrivals
-  const uint32_t bar_bload = bar_tempty + 16;                          // local bulk-copy completion
-  const uint32_t bar_bready = bar_bload + 8;                           // leader: 2 (codebook resident in both CTAs)
+  const uint32_t bar_bload = bar_tempty + 16;                          // [k2MaxCC] local bulk-copy completion per code chunk
+  const uint32_t bar_bready = bar_bload + 8 * k2MaxCC;                 // [k2MaxCC] leader: 2 (chunk resident in both CTAs)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Tc2Smem::off_tmem);
   float* xsq = reinterpret_cast<float*>(smem + Tc2Smem::off_xsq);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < k2ASlots; ++s) { mbar_init(bar_full + 8 * s, 16); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 16); }
-    mbar_init(bar_bload, 1);
-    mbar_init(bar_bready, 2);
+    for (int c = 0; c < k2MaxCC; ++c) { mbar_init(bar_bload + 8 * c, 1); mbar_init(bar_bready + 8 * c, 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 16) {
@@ -131,15 +130,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rv[0] && d0 + j < D) f = __ldg(reinterpret_cast<const float4*>(p0 + (long long)j * a.x.sD));
+          if (rv[0] && d0 + j < D) f = ldg_stream_f4(p0 + (long long)j * a.x.sD);
           v[0][j] = f.x; v[1][j] = f.y; v[2][j] = f.z; v[3][j] = f.w;
         }
       } else if (MODE == 1) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-          if (rv[i] && d0 + 4 <= D) f0 = __ldg(reinterpret_cast<const float4*>(rp[i] + d0));
-          if (rv[i] && d0 + 8 <= D) f1 = __ldg(reinterpret_cast<const float4*>(rp[i] + d0 + 4));
+          if (rv[i] && d0 + 4 <= D) f0 = ldg_stream_f4(rp[i] + d0);
+          if (rv[i] && d0 + 8 <= D) f1 = ldg_stream_f4(rp[i] + d0 + 4);
           v[i][0] = f0.x; v[i][1] = f0.y; v[i][2] = f0.z; v[i][3] = f0.w;
           v[i][4] = f1.x; v[i][5] = f1.y; v[i][6] = f1.z; v[i][7] = f1.w;
         }
@@ -148,10 +147,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            v[i][j] = (rv[i] && d0 + j < D) ? __ldg(rp[i] + (long long)(d0 + j) * a.x.sD) : 0.f;
+            v[i][j] = (rv[i] && d0 + j < D) ? ldg_stream_f1(rp[i] + (long long)(d0 + j) * a.x.sD) : 0.f;
       }
     };
-    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+    float ss[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f};
     auto store_chunk = [&](float (&v)[4][8], int dc, int tt) {
       if (warp == 0) VQ2_TRACE(0, 2 * (tt * a.n_dc + dc));
       mbar_wait(bar_empty + 8 * dc, ((uint32_t)tt & 1) ^ 1);        // last tile's MMAs on this slot retired
@@ -163,22 +162,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-          ss[i] = fmaf(v[i][j], v[i][j], ss[i]); ss[i] = fmaf(v[i][j + 1], v[i][j + 1], ss[i]);
           __half2 h = __floats2half2_rn(v[i][j], v[i][j + 1]);
+          const float2 hb = __half22float2(h);
+          const float e0 = hb.x - v[i][j], e1 = hb.y - v[i][j + 1];
+          ss[i] = fmaf(v[i][j], v[i][j], ss[i]); ss[i] = fmaf(v[i][j + 1], v[i][j + 1], ss[i]);
+          sd[i] = fmaf(e0, e0, sd[i]); sd[i] = fmaf(e1, e1, sd[i]);
           pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(at + r * 128 + ((g8 ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       if (dc == a.n_dc - 1) {                                        // row norms complete: publish before the arrive
-        float* xs = xsq + (tt & (k2XsqBufs - 1)) * k2Rows;
+        float2* xs = reinterpret_cast<float2*>(xsq) + (tt & (k2XsqBufs - 1)) * k2Rows;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float v2 = ss[i];
-          v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
-          v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
-          v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
-          if (g8 == 0) xs[r0 + i] = (v2 < 4.0e9f) ? v2 : __int_as_float(0x7f800000);
-          ss[i] = 0.f;
+          float v2 = ss[i], e2 = sd[i];
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 1); e2 += __shfl_xor_sync(0xffffffffu, e2, 1);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 2); e2 += __shfl_xor_sync(0xffffffffu, e2, 2);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 4); e2 += __shfl_xor_sync(0xffffffffu, e2, 4);
+          // |x|^2 and |fp16(x) - x|^2 (inf when an element overflows fp16: the row then goes to the exact pass)
+          if (g8 == 0) xs[r0 + i] = make_float2(v2, e2);
+          ss[i] = 0.f; sd[i] = 0.f;
         }
       }
       fence_proxy_async();
@@ -220,7 +223,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
     int* cand = reinterpret_cast<int*>(smem + Tc2Smem::off_cand) + (half * k2Rows + r) * k2CandCap;
     const int* cand_hi = reinterpret_cast<const int*>(smem + Tc2Smem::off_cand) + (k2Rows + r) * k2CandCap;
     float2* xchg = reinterpret_cast<float2*>(smem + Tc2Smem::off_xchg) + r;
-    float scale = 0.f, emax = 0.f;
+    float scale = 0.f, emax = 0.f, de_max = 0.f;
     int u = 0;
     for (int tt = 0; tt < my_tiles; ++tt) {
       const long long n = ((long long)pair + (long long)tt * n_pairs) * 256 + rank * 128 + r;
@@ -235,14 +238,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
         tc_fence_after();
         if (warp == 8) VQ2_TRACE(2, 4 * u + 1);
         if (cc == 0) {
-          if (tt == 0) { scale = hdr->scale; emax = sqrtf(hdr->max_enorm) * 1.0001f; }
-          const float xn = sqrtf(xsq[(tt & (k2XsqBufs - 1)) * k2Rows + r]) * 1.0001f;
+          if (tt == 0) {
+            scale = hdr->scale; emax = sqrtf(hdr->max_enorm) * 1.0001f;
+            de_max = sqrtf(__uint_as_float(hdr->max_de2_bits)) * 1.0001f;
+          }
+          const float2 nr = reinterpret_cast<const float2*>(xsq)[(tt & (k2XsqBufs - 1)) * k2Rows + r];
+          const float xn = sqrtf(nr.x) * 1.0001f, dn = sqrtf(nr.y) * 1.0001f;
           const float e_s = emax * scale;
           const float sum = xn + emax;
-          // see assign_tc.cu: fp16 operand rounding + fp16 subnormal floor + limb residual of |e|^2 + fp32 chain
-          // error of the exact scorer, all in the scaled domain
-          slack = a.tau * xn * e_s + 2.4e-7f * sqrtf((float)(a.n_dc * kDChunk)) * (e_s + xn)
-                + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum + 1.0e-6f * e_s * emax;
+          // |approx - exact| <= |dx| |e^| + |x| |de| (Cauchy-Schwarz on the ACTUAL operand rounding errors, see
+          // assign_tc.cu), two-sided, + fp32 accumulation / exact-chain error + limb residual of |e|^2
+          slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum
+                + 1.0e-6f * e_s * emax;
           if (!(slack < 3.0e38f) || (hdr->flags & 1u)) overflow = true;
         }
         const uint32_t tb = lane_addr + buf * 256;
@@ -339,22 +346,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
       if (lane == 0) {
         const unsigned char* img = a.blob + a.off_image;
         const unsigned char* aug = a.blob + a.off_aug;
-        const uint32_t bytes = (uint32_t)(a.n_cc * a.n_dc) * kTileBytes + (uint32_t)a.n_cc * k2AugBytes;
-        mbar_arrive_expect_tx(bar_bload, bytes);
+        const uint32_t bytes = (uint32_t)a.n_dc * kTileBytes + k2AugBytes;
+        // code chunk by code chunk: chunk 0 is needed at once, the others only after the first unit, and at
+        // kernel start every CTA's codebook load competes with the first x tile for L2 bandwidth
         for (int cc = 0; cc < a.n_cc; ++cc) {
           const int cb = 2 * cc + (int)rank;                       // this CTA's 128 codes of chunk cc
+          mbar_arrive_expect_tx(bar_bload + 8 * cc, bytes);
           for (int dc = 0; dc < a.n_dc; ++dc)
             bulk_g2s(sbase + Tc2Smem::off_b + (cc * a.n_dc + dc) * kTileBytes,
-                     img + ((long long)cb * a.n_dc + dc) * kTileBytes, kTileBytes, bar_bload);
-          bulk_g2s(sbase + Tc2Smem::off_baug + cc * k2AugBytes, aug + (long long)cb * k2AugBytes, k2AugBytes, bar_bload);
+                     img + ((long long)cb * a.n_dc + dc) * kTileBytes, kTileBytes, bar_bload + 8 * cc);
+          bulk_g2s(sbase + Tc2Smem::off_baug + cc * k2AugBytes, aug + (long long)cb * k2AugBytes, k2AugBytes,
+                   bar_bload + 8 * cc);
+          mbar_wait(bar_bload + 8 * cc, 0);
+          mbar_arrive_cluster(mapa_u32(bar_bready + 8 * cc, 0));
         }
-        mbar_wait(bar_bload, 0);
-        mbar_arrive_cluster(mapa_u32(bar_bready, 0));
       }
     } else if (warp == 16 && rank == 0) {
       // ================= MMA issuer (leader CTA) =================
-      mbar_wait(bar_bready, 0);
-      tc_fence_after();
       const uint64_t aaug = make_desc_noswz(sbase + Tc2Smem::off_aaug, 128, 256);
       for (int u = 0; u < my_units; ++u) {
         const int tt = u / a.n_cc, cc = u - tt * a.n_cc;
@@ -362,6 +370,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
         VQ2_TRACE(1, 128 + 2 * u);
         mbar_wait(bar_tempty + 8 * buf, (((uint32_t)u >> 1) & 1) ^ 1);   // both epilogues drained it
         VQ2_TRACE(1, 128 + 2 * u + 1);
+        if (tt == 0) mbar_wait(bar_bready + 8 * cc, 0);                 // this code chunk is resident in both CTAs
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256;
         for (int dc = 0; dc < a.n_dc; ++dc) {

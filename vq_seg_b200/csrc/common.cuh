@@ -46,6 +46,7 @@ struct BlobHeader {
   uint64_t off_enorm, off_image, off_aug;
   float    aug_c;        // power of two: s|e_k|^2 = aug_c * (h1 + h2 + h3), three fp16 limbs per code
   uint32_t flags;        // bit 0: limbs not representable -> tensor-core filter must defer every row
+  uint32_t max_de2_bits; // max_k |fp16(-2 s e_k) - (-2 s e_k)|^2 : the codebook operand's rounding error, exact
 };
 constexpr uint32_t kBlobMagic = 0x42535156u;
 constexpr int kCodeBlock = 128;     // codes per packed tile

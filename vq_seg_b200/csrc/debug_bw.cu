@@ -1,0 +1,78 @@
+// Developer micro-benchmark (not part of the product path): achievable global->register bandwidth of the
+// producer-style access patterns under the same conditions as the tcgen05 kernels (8 loading warps per SM,
+// large shared-memory carve-out, data resident in L2 or not).  Exposed as vqseg_debug_load_bandwidth.
+#include "common.cuh"
+
+namespace vqseg {
+
+template <int PATTERN, int DEPTH>
+__global__ void __launch_bounds__(256, 1) load_bw_kernel(const float* __restrict__ x, long long n_floats,
+                                                         long long row_stride, float* __restrict__ sink) {
+  extern __shared__ unsigned char pad_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // each CTA walks "tiles" of 128 px x 64 rows like the producers do: tile t -> rows r0.., px p0..
+  const long long px_per_row = row_stride;                 // floats per row
+  const long long tiles_per_row = px_per_row / 128;
+  const long long n_rows = n_floats / row_stride;
+  const long long n_tiles = tiles_per_row * (n_rows / 64);
+  float acc = 0.f;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long rt = t / tiles_per_row, pt = t % tiles_per_row;
+    const float* base = x + rt * 64 * row_stride + pt * 128;
+    if (PATTERN == 0) {            // LDG.128: warp -> 16 px, lane = quad*8+g8, 8 rows per thread: 8 x 64 B per instr
+      const int g8 = lane & 7, quad = lane >> 3;
+      const float* p = base + (long long)(8 * g8) * row_stride + 16 * warp + 4 * quad;
+      float4 v[DEPTH];
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                     : "l"(p + (long long)(j & 7) * row_stride + (j >> 3) * 0));
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j) acc += v[j].x + v[j].y + v[j].z + v[j].w;
+    } else if (PATTERN == 1) {     // LDG.256: warps 0-3 rows 0..31? -> warp pair covers 32 px: 8 x 128 B per instr
+      const int g8 = lane & 7, o4 = lane >> 3;
+      const int pw = warp & 3, half = warp >> 2;        // half selects rows 0-31 / 32-63 via j offset
+      const float* p = base + (long long)(8 * g8 % 32 + 32 * half) * row_stride + 32 * pw + 8 * o4;
+      float v[DEPTH][8];
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j)
+        asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[j][0]), "=f"(v[j][1]), "=f"(v[j][2]), "=f"(v[j][3]), "=f"(v[j][4]), "=f"(v[j][5]), "=f"(v[j][6]), "=f"(v[j][7])
+                     : "l"(p + (long long)(j & 3) * row_stride));
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc += v[j][e];
+    } else {                       // LDG.128 fully contiguous 512 B per warp instruction
+      const float* p = base + (long long)(8 * warp) * row_stride + 4 * lane;
+      float4 v[DEPTH];
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                     : "l"(p + (long long)(j & 7) * row_stride));
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j) acc += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+  }
+  if (acc == 12345.678f) sink[0] = acc;
+}
+
+template <int P, int D>
+static int launch_bw(const float* x, long long n, long long rs, float* sink, cudaStream_t st) {
+  cudaFuncSetAttribute(load_bw_kernel<P, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  load_bw_kernel<P, D><<<num_sms(), 256, 200 * 1024, st>>>(x, n, rs, sink);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vqseg
+
+extern "C" int vqseg_debug_load_bandwidth(const float* x, int64_t n_floats, int64_t row_stride, int pattern, int depth,
+                                          float* sink, void* stream) {
+  using namespace vqseg;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pattern == 0 && depth == 8) return launch_bw<0, 8>(x, n_floats, row_stride, sink, st);
+  if (pattern == 1 && depth == 4) return launch_bw<1, 4>(x, n_floats, row_stride, sink, st);
+  if (pattern == 2 && depth == 8) return launch_bw<2, 8>(x, n_floats, row_stride, sink, st);
+  return VQSEG_EINVAL;
+}

@@ -87,11 +87,20 @@ __device__ __forceinline__ float chain_dist2_smem(const float* __restrict__ xs, 
     float t = 0.f;
     int j = blk;
     for (; j < dend && (j & 7); ++j) t = __fmaf_rn(xs[j], es[j], t);
-    for (; j + 8 <= dend; j += 8) {
-      const float4 x0 = *reinterpret_cast<const float4*>(xs + j), x1 = *reinterpret_cast<const float4*>(xs + j + 4);
-      const float4 e0 = *reinterpret_cast<const float4*>(es + j), e1 = *reinterpret_cast<const float4*>(es + j + 4);
+    if (j + 8 <= dend) {
+      // the next 8 terms are fetched from smem while the current 8 dependent FMAs retire
+      float4 x0 = *reinterpret_cast<const float4*>(xs + j), x1 = *reinterpret_cast<const float4*>(xs + j + 4);
+      float4 e0 = *reinterpret_cast<const float4*>(es + j), e1 = *reinterpret_cast<const float4*>(es + j + 4);
+      for (; j + 16 <= dend; j += 8) {
+        const float4 nx0 = *reinterpret_cast<const float4*>(xs + j + 8), nx1 = *reinterpret_cast<const float4*>(xs + j + 12);
+        const float4 ne0 = *reinterpret_cast<const float4*>(es + j + 8), ne1 = *reinterpret_cast<const float4*>(es + j + 12);
+        t = __fmaf_rn(x0.x, e0.x, t); t = __fmaf_rn(x0.y, e0.y, t); t = __fmaf_rn(x0.z, e0.z, t); t = __fmaf_rn(x0.w, e0.w, t);
+        t = __fmaf_rn(x1.x, e1.x, t); t = __fmaf_rn(x1.y, e1.y, t); t = __fmaf_rn(x1.z, e1.z, t); t = __fmaf_rn(x1.w, e1.w, t);
+        x0 = nx0; x1 = nx1; e0 = ne0; e1 = ne1;
+      }
       t = __fmaf_rn(x0.x, e0.x, t); t = __fmaf_rn(x0.y, e0.y, t); t = __fmaf_rn(x0.z, e0.z, t); t = __fmaf_rn(x0.w, e0.w, t);
       t = __fmaf_rn(x1.x, e1.x, t); t = __fmaf_rn(x1.y, e1.y, t); t = __fmaf_rn(x1.z, e1.z, t); t = __fmaf_rn(x1.w, e1.w, t);
+      j += 8;
     }
     for (; j < dend; ++j) t = __fmaf_rn(xs[j], es[j], t);
     float s = -2.f * t;
@@ -172,6 +181,7 @@ struct ExactArgs {
   const int* cand_idx; const int* cand_cnt; int cand_cap;   // per row: up to cand_cap codes; cnt > cap => all codes
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
   int stage_e;
+  long long* trace;     // dev tool: [0] min start ns, [1] max end ns, [2..] per-phase clock sums
 };
 
 constexpr int kExactWarps = 8;
@@ -184,40 +194,74 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
   const bool stage_e = a.stage_e != 0;                   // smem also holds cand_cap code rows per warp
   float* xs = smem_x + (size_t)wib * (xs_stride + (stage_e ? a.cand_cap * (xs_stride + 4) : 0));
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.E) & 15) == 0);
+  auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+  if (a.trace && threadIdx.x == 0) atomicMin((unsigned long long*)a.trace, (unsigned long long)gtime());
+  long long c0 = clock64(), c1 = c0, c2 = c0, c3 = c0, c4 = c0;
   const long long n_rows = a.x.n_rows();
-  long long n_work = a.work_rows ? (long long)*a.work_count : n_rows;
+  const long long w_first = (long long)blockIdx.x * kExactWarps + wib;
+  // the work counter and this warp's first row id are independent loads (the list has n_rows slots)
+  int n_spec = (a.work_rows && w_first < n_rows) ? __ldg(a.work_rows + w_first) : 0;
+  long long n_work = a.work_rows ? (long long)__ldg(a.work_count) : n_rows;
   if (a.work_rows && n_work > n_rows) n_work = n_rows;
-  for (long long w = (long long)blockIdx.x * kExactWarps + wib; w < n_work; w += (long long)gridDim.x * kExactWarps) {
-    const long long n = a.work_rows ? a.work_rows[w] : w;
+  for (long long w = w_first; w < n_work; w += (long long)gridDim.x * kExactWarps) {
+    const long long n = a.work_rows ? (w == w_first ? n_spec : a.work_rows[w]) : w;
     const float* xr = a.x.row(n);
+    // wave 2 of dependent loads, all issued before the first use: candidate count, candidate ids (lane c
+    // holds candidate c) and the row itself (8 strided loads per lane)
+    c1 = clock64();
+    int cnt = a.cand_cnt ? __ldg(a.cand_cnt + n) : -1;
+    int my_k = 0;
+    if (a.cand_idx && lane < a.cand_cap) my_k = __ldg(a.cand_idx + n * a.cand_cap + lane);
     __syncwarp();
-    for (int j0 = 0; j0 < D; j0 += 256) {               // 8 strided loads in flight per lane before the stores
+    for (int j0 = 0; j0 < D; j0 += 256) {
       float t[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) { const int j = j0 + lane + 32 * u; t[u] = j < D ? __ldg(xr + (long long)j * a.x.sD) : 0.f; }
 #pragma unroll
       for (int u = 0; u < 8; ++u) { const int j = j0 + lane + 32 * u; if (j < D) xs[j] = t[u]; }
     }
-    __syncwarp();
-    const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
     float best = __int_as_float(0x7f800000);   // +inf
     int best_k = 0x7fffffff;
-    int cnt = a.cand_cnt ? a.cand_cnt[n] : -1;
-    if (cnt >= 0 && cnt <= a.cand_cap) {
-      const int* cl = a.cand_idx + n * a.cand_cap;
-      if (stage_e) {
-        // short-list rows: stage the candidate code rows in smem with coalesced loads (row stride es_stride
-        // = D rounded to 4, + 4: 16-byte aligned rows, and the <= 8 lanes chaining different rows read
-        // disjoint bank quads), then lane c runs the chain of candidate c
-        float* es = xs + xs_stride;
-        const int es_stride = xs_stride + 4;
-        int kc[8];
+    const bool listed = cnt >= 0 && cnt <= a.cand_cap;
+    __syncwarp(); c2 = clock64();
+    my_k = (listed && lane < cnt && my_k >= 0 && my_k < a.K) ? my_k : 0;
+    if (listed && stage_e) {
+      // wave 3: candidate code rows (coalesced, into smem; row stride es_stride = D rounded to 4, + 4:
+      // 16-byte aligned rows, and the <= 8 lanes chaining different rows read disjoint bank quads) and
+      // each candidate's |e|^2
+      float* es = xs + xs_stride;
+      const int es_stride = xs_stride + 4;
+      const float my_en = lane < cnt ? __ldg(a.enorm + my_k) : 0.f;
+      float xnorm;
+      if (vec4 && D <= 256 && cnt <= 4) {
+        // common case: <= 4 candidates of <= 256 dims: their rows travel in registers while |x|^2 is reduced
+        float4 ev[4][2];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) kc[c] = c < cnt ? cl[c] : 0;
+        for (int c = 0; c < 4; ++c) {
+          const float* er = a.E + (long long)__shfl_sync(0xffffffffu, my_k, c) * D;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = 4 * lane + 128 * h;
+            ev[c][h] = (c < cnt && j < D) ? __ldg(reinterpret_cast<const float4*>(er + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        __syncwarp();
+        c3 = clock64();
+        xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = 4 * lane + 128 * h;
+            if (c < cnt && j < D) *reinterpret_cast<float4*>(es + c * es_stride + j) = ev[c][h];
+          }
+        __syncwarp();
+        c4 = clock64();
+      } else {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           if (c < cnt) {
-            const float* er = a.E + (long long)kc[c] * D;
+            const float* er = a.E + (long long)__shfl_sync(0xffffffffu, my_k, c) * D;
             if (vec4) {
               for (int j = 4 * lane; j < D; j += 128)
                 *reinterpret_cast<float4*>(es + c * es_stride + j) = __ldg(reinterpret_cast<const float4*>(er + j));
@@ -227,23 +271,24 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
           }
         }
         __syncwarp();
-        if (lane < cnt) {
-          const int k = cl[lane];
-          float c2 = chain_dist2_smem(xs, es + lane * es_stride, D, xnorm, a.enorm[k], a.kblock);
-          lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), k);
-        }
-      } else {
-        for (int c0 = 0; c0 < cnt; c0 += 32) {
-          int c = c0 + lane;
-          if (c < cnt) {
-            int k = cl[c];
-            float c2 = chain_dist2<true>(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, vec4);
-            float d = __fsqrt_rn(fmaxf(c2, 0.f));
-            lexmin(best, best_k, d, k);
-          }
-        }
+        c3 = clock64();
+        xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
+        c4 = clock64();
+      }
+      if (lane < cnt) {
+        float c2 = chain_dist2_smem(xs, es + lane * es_stride, D, xnorm, my_en, a.kblock);
+        lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), my_k);
+      }
+    } else if (listed) {
+      __syncwarp();
+      const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
+      if (lane < cnt) {
+        float c2 = chain_dist2<true>(xs, a.E + (long long)my_k * D, D, xnorm, a.enorm[my_k], a.kblock, vec4);
+        lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), my_k);
       }
     } else {
+      __syncwarp();
+      const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
       for (int k0 = lane; k0 < a.K; k0 += 128) {
         float c4[4];
         if (vec4) {
@@ -269,6 +314,15 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
       int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
       lexmin(best, best_k, d2, k2);
     }
+    if (a.trace && lane == 0) {
+      long long c5 = clock64();
+      atomicAdd((unsigned long long*)a.trace + 2, (unsigned long long)(c1 - c0));   // until row id known
+      atomicAdd((unsigned long long*)a.trace + 3, (unsigned long long)(c2 - c1));   // wave 2 (cnt, ids, x row)
+      atomicAdd((unsigned long long*)a.trace + 4, (unsigned long long)(c3 - c2));   // wave 3 (code rows)
+      atomicAdd((unsigned long long*)a.trace + 5, (unsigned long long)(c4 - c3));   // |x|^2
+      atomicAdd((unsigned long long*)a.trace + 6, (unsigned long long)(c5 - c4));   // chains + argmin
+      atomicAdd((unsigned long long*)a.trace + 7, 1ull);
+    }
     if (lane == 0) {
       if (best_k == 0x7fffffff) best_k = 0;
       if (a.idx_out) a.idx_out[n] = (long long)best_k + a.code_base;
@@ -277,6 +331,7 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
         a.key_out[n] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(uint32_t)(best_k + a.code_base);
     }
   }
+  if (a.trace && threadIdx.x == 0) atomicMax((unsigned long long*)a.trace + 1, (unsigned long long)gtime());
 }
 
 int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st) {

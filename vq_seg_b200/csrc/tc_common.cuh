@@ -93,6 +93,20 @@ __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo
   return ((uint64_t)hi << 32) | lo;
 }
 
+// Streaming 16-byte load that does not allocate in L1: with a 228 KB shared-memory carve-out the L1 has room
+// for only ~160 lines, and every in-flight allocating miss pins one -- that capped the producers at ~11 B/clk/SM.
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // ---- cluster (CTA pair) helpers ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {

@@ -38,8 +38,7 @@ def _aligned_bytes(nbytes: int, device) -> torch.Tensor:
 
 
 # -------------------------------------------------------------------------------------------------
-@torch.library.custom_op("vqseg::prepare_codebook", mutates_args=())
-def prepare_codebook(codebook: torch.Tensor) -> torch.Tensor:
+def _prepare_codebook_impl(codebook: torch.Tensor) -> torch.Tensor:
     """fp32 |e|^2 (torch CPU summation order) + fp16 tcgen05 operand image; see vqseg.h."""
     _require_cuda(codebook)
     L = _native.lib()
@@ -52,6 +51,9 @@ def prepare_codebook(codebook: torch.Tensor) -> torch.Tensor:
     return blob
 
 
+prepare_codebook = torch.library.custom_op("vqseg::prepare_codebook", mutates_args=())(_prepare_codebook_impl)
+
+
 @prepare_codebook.register_fake
 def _(codebook):
     k, d = codebook.shape
@@ -60,8 +62,7 @@ def _(codebook):
                               dtype=torch.uint8)
 
 
-@torch.library.custom_op("vqseg::assign", mutates_args=())
-def assign(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], algo: int = 0,
+def _assign_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], algo: int = 0,
            kblock: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """(idx (B,P) int64, counts (K,) int64): first-index argmin of the reference's fp32 cdist."""
     _require_cuda(x, codebook, blob)
@@ -87,14 +88,16 @@ def assign(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor]
     return idx, counts
 
 
+assign = torch.library.custom_op("vqseg::assign", mutates_args=())(_assign_impl)
+
+
 @assign.register_fake
 def _(x, codebook, blob, algo=0, kblock=0):
     return (x.new_empty((x.shape[0], x.shape[1]), dtype=torch.int64),
             x.new_empty((codebook.shape[0],), dtype=torch.int64))
 
 
-@torch.library.custom_op("vqseg::assign_keys", mutates_args=())
-def assign_keys(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], code_base: int,
+def _assign_keys_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], code_base: int,
                 algo: int = 0, kblock: int = 0) -> torch.Tensor:
     """Sharded mode: per row the packed key (float_bits(dist) << 32 | code_base + local idx) as int64."""
     _require_cuda(x, codebook, blob)
@@ -115,13 +118,15 @@ def assign_keys(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Te
     return keys
 
 
+assign_keys = torch.library.custom_op("vqseg::assign_keys", mutates_args=())(_assign_keys_impl)
+
+
 @assign_keys.register_fake
 def _(x, codebook, blob, code_base, algo=0, kblock=0):
     return x.new_empty((x.shape[0], x.shape[1]), dtype=torch.int64)
 
 
-@torch.library.custom_op("vqseg::unpack_keys", mutates_args=())
-def unpack_keys(keys: torch.Tensor, num_codes: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def _unpack_keys_impl(keys: torch.Tensor, num_codes: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     _require_cuda(keys)
     L = _native.lib()
     keys = keys.contiguous()
@@ -135,14 +140,16 @@ def unpack_keys(keys: torch.Tensor, num_codes: int) -> Tuple[torch.Tensor, torch
     return idx, dist, counts
 
 
+unpack_keys = torch.library.custom_op("vqseg::unpack_keys", mutates_args=())(_unpack_keys_impl)
+
+
 @unpack_keys.register_fake
 def _(keys, num_codes):
     return (keys.new_empty(keys.shape), keys.new_empty(keys.shape, dtype=torch.float32),
             keys.new_empty((num_codes,)))
 
 
-@torch.library.custom_op("vqseg::gather_ste", mutates_args=())
-def gather_ste(x: torch.Tensor, codebook: torch.Tensor, idx: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.Tensor]:
+def _gather_ste_impl(x: torch.Tensor, codebook: torch.Tensor, idx: torch.Tensor, mode: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """(q (B,P,D) laid out like an NCHW map, mse (1,)): E[idx] (eval) or x + (E[idx] - x) (train)
     and mean((q - x)^2) in one pass."""
     _require_cuda(x, codebook, idx)
@@ -163,6 +170,9 @@ def gather_ste(x: torch.Tensor, codebook: torch.Tensor, idx: torch.Tensor, mode:
     return q, loss
 
 
+gather_ste = torch.library.custom_op("vqseg::gather_ste", mutates_args=())(_gather_ste_impl)
+
+
 @gather_ste.register_fake
 def _(x, codebook, idx, mode):
     b, p, d = x.shape
@@ -170,8 +180,7 @@ def _(x, codebook, idx, mode):
             x.new_empty((1,), dtype=torch.float32))
 
 
-@torch.library.custom_op("vqseg::ste_bwd", mutates_args=())
-def ste_bwd(grad_q: Optional[torch.Tensor], x: torch.Tensor, q_ste: torch.Tensor,
+def _ste_bwd_impl(grad_q: Optional[torch.Tensor], x: torch.Tensor, q_ste: torch.Tensor,
             grad_mse: Optional[torch.Tensor], coef_scale: float) -> torch.Tensor:
     """gx = grad_q + coef_scale * grad_mse * (x - q_ste)   (coef_scale = 2 / numel)."""
     _require_cuda(x, q_ste, grad_q, grad_mse)
@@ -192,13 +201,15 @@ def ste_bwd(grad_q: Optional[torch.Tensor], x: torch.Tensor, q_ste: torch.Tensor
     return gx
 
 
+ste_bwd = torch.library.custom_op("vqseg::ste_bwd", mutates_args=())(_ste_bwd_impl)
+
+
 @ste_bwd.register_fake
 def _(grad_q, x, q_ste, grad_mse, coef_scale):
     return torch.empty_like(x, dtype=torch.float32)
 
 
-@torch.library.custom_op("vqseg::gather_bwd_codebook", mutates_args=())
-def gather_bwd_codebook(grad_q: torch.Tensor, idx: torch.Tensor, num_codes: int) -> torch.Tensor:
+def _gather_bwd_codebook_impl(grad_q: torch.Tensor, idx: torch.Tensor, num_codes: int) -> torch.Tensor:
     _require_cuda(grad_q, idx)
     L = _native.lib()
     gq = grad_q.float()
@@ -211,13 +222,15 @@ def gather_bwd_codebook(grad_q: torch.Tensor, idx: torch.Tensor, num_codes: int)
     return ge
 
 
+gather_bwd_codebook = torch.library.custom_op("vqseg::gather_bwd_codebook", mutates_args=())(_gather_bwd_codebook_impl)
+
+
 @gather_bwd_codebook.register_fake
 def _(grad_q, idx, num_codes):
     return grad_q.new_empty((num_codes, grad_q.shape[2]), dtype=torch.float32)
 
 
-@torch.library.custom_op("vqseg::code_stats", mutates_args=())
-def code_stats(x: torch.Tensor, idx: torch.Tensor, num_codes: int, deterministic: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+def _code_stats_impl(x: torch.Tensor, idx: torch.Tensor, num_codes: int, deterministic: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """(counts (K,) int64, sums (K, D) fp32) of the rows assigned to each code."""
     _require_cuda(x, idx)
     L = _native.lib()
@@ -236,13 +249,15 @@ def code_stats(x: torch.Tensor, idx: torch.Tensor, num_codes: int, deterministic
     return counts, sums
 
 
+code_stats = torch.library.custom_op("vqseg::code_stats", mutates_args=())(_code_stats_impl)
+
+
 @code_stats.register_fake
 def _(x, idx, num_codes, deterministic=True):
     return x.new_empty((num_codes,), dtype=torch.int64), x.new_empty((num_codes, x.shape[2]), dtype=torch.float32)
 
 
-@torch.library.custom_op("vqseg::kmeans_finalize", mutates_args=("means",))
-def kmeans_finalize(sums: torch.Tensor, counts: torch.Tensor, means: torch.Tensor, cosine: bool = False) -> None:
+def _kmeans_finalize_impl(sums: torch.Tensor, counts: torch.Tensor, means: torch.Tensor, cosine: bool = False) -> None:
     _require_cuda(sums, counts, means)
     L = _native.lib()
     assert means.is_contiguous() and sums.is_contiguous() and counts.is_contiguous()
@@ -252,8 +267,10 @@ def kmeans_finalize(sums: torch.Tensor, counts: torch.Tensor, means: torch.Tenso
                                                   int(cosine), _stream()), "kmeans_finalize")
 
 
-@torch.library.custom_op("vqseg::code_usage", mutates_args=())
-def code_usage(counts: torch.Tensor) -> torch.Tensor:
+kmeans_finalize = torch.library.custom_op("vqseg::kmeans_finalize", mutates_args=("means",))(_kmeans_finalize_impl)
+
+
+def _code_usage_impl(counts: torch.Tensor) -> torch.Tensor:
     """0-dim fp32: percent of UNUSED codes (vq_img.py:173-175)."""
     _require_cuda(counts)
     L = _native.lib()
@@ -264,13 +281,15 @@ def code_usage(counts: torch.Tensor) -> torch.Tensor:
     return out
 
 
+code_usage = torch.library.custom_op("vqseg::code_usage", mutates_args=())(_code_usage_impl)
+
+
 @code_usage.register_fake
 def _(counts):
     return counts.new_empty((), dtype=torch.float32)
 
 
-@torch.library.custom_op("vqseg::gather_rows", mutates_args=())
-def gather_rows(x: torch.Tensor, row_ids: torch.Tensor) -> torch.Tensor:
+def _gather_rows_impl(x: torch.Tensor, row_ids: torch.Tensor) -> torch.Tensor:
     _require_cuda(x, row_ids)
     L = _native.lib()
     if x.dtype != torch.float32:
@@ -284,13 +303,15 @@ def gather_rows(x: torch.Tensor, row_ids: torch.Tensor) -> torch.Tensor:
     return out
 
 
+gather_rows = torch.library.custom_op("vqseg::gather_rows", mutates_args=())(_gather_rows_impl)
+
+
 @gather_rows.register_fake
 def _(x, row_ids):
     return x.new_empty((row_ids.numel(), x.shape[2]), dtype=torch.float32)
 
 
-@torch.library.custom_op("vqseg::l2norm_rows", mutates_args=())
-def l2norm_rows(x: torch.Tensor) -> torch.Tensor:
+def _l2norm_rows_impl(x: torch.Tensor) -> torch.Tensor:
     """F.normalize(x, dim=-1) packed as (B, P, D) contiguous."""
     _require_cuda(x)
     L = _native.lib()
@@ -303,13 +324,15 @@ def l2norm_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+l2norm_rows = torch.library.custom_op("vqseg::l2norm_rows", mutates_args=())(_l2norm_rows_impl)
+
+
 @l2norm_rows.register_fake
 def _(x):
     return x.new_empty(x.shape, dtype=torch.float32)
 
 
-@torch.library.custom_op("vqseg::assign_cosine", mutates_args=())
-def assign_cosine(xn: torch.Tensor, codebook: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def _assign_cosine_impl(xn: torch.Tensor, codebook: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     _require_cuda(xn, codebook)
     L = _native.lib()
     xn = xn.contiguous().float()
@@ -324,12 +347,22 @@ def assign_cosine(xn: torch.Tensor, codebook: torch.Tensor) -> Tuple[torch.Tenso
     return idx, counts
 
 
+assign_cosine = torch.library.custom_op("vqseg::assign_cosine", mutates_args=())(_assign_cosine_impl)
+
+
 @assign_cosine.register_fake
 def _(xn, codebook):
     return xn.new_empty(xn.shape[:2], dtype=torch.int64), xn.new_empty((codebook.shape[0],), dtype=torch.int64)
 
 
 # -------------------------------------------------------------------------------------------------
+def _fast():
+    """Eager fast path: call the Python implementations directly instead of going through the
+    torch.library dispatcher (saves ~20 us of host time per op); the registered custom ops are used
+    whenever a graph is being traced / compiled."""
+    return not torch.compiler.is_compiling()
+
+
 class _StraightThrough(torch.autograd.Function):
     """Training forward of vq_img.py:235-240: q_ste = x + (E[idx] - x), mse = mean((q_ste - x)^2).
     Gradients: d q_ste / dx = I (straight-through), d mse / dx = 2 (x - q_ste) / numel; the codebook
@@ -337,7 +370,7 @@ class _StraightThrough(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, codebook, idx, mode):
-        q, mse = gather_ste(x, codebook, idx, mode)
+        q, mse = (_gather_ste_impl if _fast() else gather_ste)(x, codebook, idx, mode)
         ctx.save_for_backward(x, q)
         ctx.mark_non_differentiable(idx)
         return q, mse
@@ -347,7 +380,7 @@ class _StraightThrough(torch.autograd.Function):
         x, q = ctx.saved_tensors
         if not ctx.needs_input_grad[0]:
             return None, None, None, None
-        gx = ste_bwd(grad_q, x, q, grad_mse, 2.0 / x.numel())
+        gx = (_ste_bwd_impl if _fast() else ste_bwd)(grad_q, x, q, grad_mse, 2.0 / x.numel())
         return gx, None, None, None
 
 
@@ -357,7 +390,7 @@ class _EvalGather(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, codebook, x_like, idx, mode):
-        q, _ = gather_ste(x_like, codebook, idx, mode)
+        q, _ = (_gather_ste_impl if _fast() else gather_ste)(x_like, codebook, idx, mode)
         ctx.save_for_backward(idx)
         ctx.num_codes = codebook.shape[0]
         return q
@@ -365,7 +398,8 @@ class _EvalGather(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_q):
         (idx,) = ctx.saved_tensors
-        ge = gather_bwd_codebook(grad_q, idx, ctx.num_codes) if ctx.needs_input_grad[0] else None
+        ge = ((_gather_bwd_codebook_impl if _fast() else gather_bwd_codebook)(grad_q, idx, ctx.num_codes)
+              if ctx.needs_input_grad[0] else None)
         return ge, None, None, None
 
 
@@ -375,3 +409,15 @@ def straight_through(x, codebook, idx, amp_fp16=False):
 
 def eval_gather(codebook, x_like, idx, amp_fp16=False):
     return _EvalGather.apply(codebook, x_like, idx, MODE_EVAL_AMP if amp_fp16 else MODE_EVAL)
+
+
+def fast_assign(x, codebook, blob, algo=ALGO_AUTO, kblock=0):
+    return (_assign_impl if _fast() else assign)(x, codebook, blob, algo, kblock)
+
+
+def fast_code_usage(counts):
+    return (_code_usage_impl if _fast() else code_usage)(counts)
+
+
+def fast_prepare_codebook(codebook):
+    return (_prepare_codebook_impl if _fast() else prepare_codebook)(codebook)

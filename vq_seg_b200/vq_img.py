@@ -111,7 +111,7 @@ class _CodebookBase(nn.Module):
         w = self.embedding.weight
         key = (w.data_ptr(), w._version, w.device)
         if self._blob is None or self._blob_key != key:
-            self._blob = ops.prepare_codebook(w.detach())
+            self._blob = ops.fast_prepare_codebook(w.detach())
             self._blob_key = key
         return self._blob
 
@@ -134,7 +134,7 @@ class EuclideanCodebook(_CodebookBase):
         if x.shape[-1] != self.embedding_dim:
             raise RuntimeError(f"X1 and X2 must have the same number of columns. X1: {x.shape[-1]} X2: {self.embedding_dim}")
         blob = self._prepared() if self.algo != ops.ALGO_EXACT else None
-        return ops.assign(x, self.embedding.weight.detach(), blob, self.algo)
+        return ops.fast_assign(x, self.embedding.weight.detach(), blob, self.algo)
 
     def forward(self, x):
         """x: (B, HxW, C) -> (quantized (B,HW,C), embed_idx (B,HW), code_usage)   [vq_img.py:160-177]"""
@@ -205,8 +205,8 @@ class VectorQuantizer(nn.Module):
         if cb.kmeans_init and self.training and not cb.initted:
             cb._kmeans_init(ops.l2norm_rows(xv) if cosine else xv, cosine=cosine)
         idx, counts = cb.lookup(xv)
-        code_usage = ops.code_usage(counts)
-        loss = torch.tensor([0.], device=device, requires_grad=self.training, dtype=torch.float32)
+        code_usage = ops.fast_code_usage(counts)
+        loss = torch.zeros(1, device=device, dtype=torch.float32, requires_grad=self.training)   # no H2D copy
         if self.training:
             quantize, mse = ops.straight_through(xv, cb.embedding.weight.detach(), idx, amp16)
             if self.commitment_weight > 0:
