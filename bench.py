@@ -186,18 +186,38 @@ def main():
             graphs.append(g)
             outs.append(o)
 
+    # N > 1: the 4 KiB all-reduce of the code counts + the usage kernel of step i run on a side stream and
+    # overlap step i+1's kernels (the lookup itself needs no exchange); a ring slot is not replayed before its
+    # previous reduction has finished.
+    side_stream = torch.cuda.Stream() if world > 1 else None
+    ev_main = [torch.cuda.Event() for _ in range(args.ring)]
+    ev_side = [torch.cuda.Event() for _ in range(args.ring)]
+    usages = [None] * args.ring
+
     def step(i):
+        s = i % args.ring
+        main_s = torch.cuda.current_stream()
+        if world > 1 and usages[s] is not None:
+            main_s.wait_event(ev_side[s])
         if graphs:
-            graphs[i % args.ring].replay()
-            q, idx, counts = outs[i % args.ring]
+            graphs[s].replay()
+            q, idx, counts = outs[s]
         else:
             q, idx, counts = step_eager(i)
         if world > 1:
-            dist.all_reduce(counts)                # global code usage (4 KiB): the only exchange of the lookup path
-        usage = ops.code_usage(counts)
+            ev_main[s].record(main_s)
+            with torch.cuda.stream(side_stream):
+                side_stream.wait_event(ev_main[s])
+                dist.all_reduce(counts)            # global code usage (4 KiB): the only exchange of the lookup path
+                usages[s] = ops.code_usage(counts)
+                ev_side[s].record(side_stream)
+            usage = usages[s]
+        else:
+            usage = ops.code_usage(counts)
         return q, idx, usage
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

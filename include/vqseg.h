@@ -107,6 +107,18 @@ int    vqseg_gather_ste_f32(const float* x, int64_t B, int64_t P, int64_t D,
                             float* q_out, int64_t qB, int64_t qP, int64_t qD,
                             float* loss_out, int mode, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- the whole VectorQuantizer.forward in one call -------------------------------------------------
+ * vqseg_assign_f32 + vqseg_code_usage + vqseg_gather_ste_f32 enqueued back to back (vq_img.py:228-244 minus the
+ * k-means hook): one host call instead of three, for latency-bound feature-map sizes.  counts_out is zeroed
+ * here.  ws must hold vqseg_forward_workspace_bytes.  Outputs as in the individual calls.               */
+size_t vqseg_forward_workspace_bytes(int64_t n_rows, int64_t D, int64_t K);
+int    vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                            int64_t sB, int64_t sP, int64_t sD,
+                            const float* E, int64_t K, const void* blob,
+                            int64_t* idx_out, int64_t* counts_out, float* usage_out,
+                            float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out,
+                            int mode, int algo, int kblock, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- backward of the training forward w.r.t. x -----------------------------------------------
  * Replaces autograd through vq_img.py:236-240:  gx = g_q + coef * (x - q_ste), with
  * coef = g_loss * commitment_weight * 2 / numel read from device memory (coef_dev, 1 float) so no

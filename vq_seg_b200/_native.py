@@ -28,6 +28,9 @@ SIGNATURES = {
     "vqseg_unpack_keys": (ci, [vp, i64, vp, vp, vp, i64, vp]),
     "vqseg_gather_workspace_bytes": (sz, [i64, i64]),
     "vqseg_gather_ste_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, i64, i64, i64, vp, ci, vp, sz, vp]),
+    "vqseg_forward_workspace_bytes": (sz, [i64, i64, i64]),
+    "vqseg_vq_forward_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64, vp,
+                                  ci, ci, ci, vp, sz, vp]),
     "vqseg_ste_bwd_f32": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, f32,
                                vp, i64, i64, i64, i64, i64, i64, vp]),
     "vqseg_gather_bwd_codebook_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, vp]),

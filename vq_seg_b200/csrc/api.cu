@@ -252,4 +252,27 @@ int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
   return rc;
 }
 
+size_t vqseg_forward_workspace_bytes(int64_t n_rows, int64_t D, int64_t K) {
+  return (size_t)round_up(vqseg_assign_workspace_bytes(n_rows, D, K, 0), 256) + vqseg_gather_workspace_bytes(n_rows, D);
+}
+
+int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                         const float* E, int64_t K, const void* blob,
+                         int64_t* idx_out, int64_t* counts_out, float* usage_out,
+                         float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out,
+                         int mode, int algo, int kblock, void* ws, size_t ws_bytes, void* stream) {
+  if (!idx_out || !counts_out || !q_out || K <= 0) return VQSEG_EINVAL;
+  const size_t wa = (size_t)round_up(vqseg_assign_workspace_bytes(B * P, D, K, algo), 256);
+  if (!ws || ws_bytes < wa + vqseg_gather_workspace_bytes(B * P, D)) return VQSEG_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(counts_out, 0, (size_t)K * sizeof(int64_t), st);
+  if (e != cudaSuccess) return (int)e;
+  if (loss_out) { e = cudaMemsetAsync(loss_out, 0, sizeof(float), st); if (e != cudaSuccess) return (int)e; }
+  int rc = vqseg_assign_f32(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, kblock, algo, ws, wa, stream);
+  if (rc) return rc;
+  if (usage_out) { rc = vqseg_code_usage(counts_out, K, usage_out, stream); if (rc) return rc; }
+  return vqseg_gather_ste_f32(x, B, P, D, sB, sP, sD, E, K, idx_out, q_out, qB, qP, qD, loss_out, mode,
+                              (char*)ws + wa, ws_bytes - wa, stream);
+}
+
 }  // extern "C"

@@ -356,6 +356,49 @@ def _(xn, codebook):
 
 
 # -------------------------------------------------------------------------------------------------
+def _vq_forward_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], mode: int,
+                     algo: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(q (B,P,D) in NCHW memory order, idx (B,P) int64, mse (1,), code_usage ()): the whole forward of
+    vq_img.py:228-244 (minus the k-means hook) enqueued by ONE host call."""
+    _require_cuda(x, codebook, blob)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    cb = codebook.detach()
+    if cb.dtype != torch.float32 or not cb.is_contiguous():
+        cb = cb.contiguous().float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    k = cb.shape[0]
+    if cb.shape[1] != d:
+        raise RuntimeError(f"X1 and X2 must have the same number of columns. X1: {d} X2: {cb.shape[1]}")
+    dev = x.device
+    idx = torch.empty((b, p), dtype=torch.int64, device=dev)
+    counts = torch.empty(k, dtype=torch.int64, device=dev)
+    usage = torch.empty((), dtype=torch.float32, device=dev)
+    q = torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    nws = L.vqseg_forward_workspace_bytes(b * p, d, k)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(L.vqseg_vq_forward_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
+                                             blob.data_ptr() if blob is not None else None,
+                                             idx.data_ptr(), counts.data_ptr(), usage.data_ptr(),
+                                             q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), loss.data_ptr(),
+                                             mode, algo, 0, ws.data_ptr(), nws, _stream()), "vq_forward")
+    return q, idx, loss, usage
+
+
+vq_forward = torch.library.custom_op("vqseg::vq_forward", mutates_args=())(_vq_forward_impl)
+
+
+@vq_forward.register_fake
+def _(x, codebook, blob, mode, algo=0):
+    b, p, d = x.shape
+    return (torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=x.device),
+            x.new_empty((b, p), dtype=torch.int64), x.new_empty((1,), dtype=torch.float32),
+            x.new_empty((), dtype=torch.float32))
+
+
 def _fast():
     """Eager fast path: call the Python implementations directly instead of going through the
     torch.library dispatcher (saves ~20 us of host time per op); the registered custom ops are used
@@ -401,6 +444,58 @@ class _EvalGather(torch.autograd.Function):
         ge = ((_gather_bwd_codebook_impl if _fast() else gather_bwd_codebook)(grad_q, idx, ctx.num_codes)
               if ctx.needs_input_grad[0] else None)
         return ge, None, None, None
+
+
+class _FusedTrainForward(torch.autograd.Function):
+    """Training forward in one host call: lookup + STE + commitment mse + usage.  Same gradients as
+    _StraightThrough (identity to x, 2 (x - q) / numel from the mse; nothing to the codebook)."""
+
+    @staticmethod
+    def forward(ctx, x, codebook, blob, mode, algo):
+        q, idx, mse, usage = (_vq_forward_impl if _fast() else vq_forward)(x, codebook, blob, mode, algo)
+        ctx.save_for_backward(x, q)
+        ctx.mark_non_differentiable(idx, usage)
+        return q, idx, mse, usage
+
+    @staticmethod
+    def backward(ctx, grad_q, _gi, grad_mse, _gu):
+        x, q = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        gx = (_ste_bwd_impl if _fast() else ste_bwd)(grad_q, x, q, grad_mse, 2.0 / x.numel())
+        return gx, None, None, None, None
+
+
+class _FusedEvalForward(torch.autograd.Function):
+    """Eval forward in one host call; like the reference's one-hot matmul the gradient goes to the codebook."""
+
+    @staticmethod
+    def forward(ctx, codebook, x, blob, mode, algo):
+        q, idx, mse, usage = (_vq_forward_impl if _fast() else vq_forward)(x, codebook, blob, mode, algo)
+        ctx.save_for_backward(idx)
+        ctx.num_codes = codebook.shape[0]
+        ctx.mark_non_differentiable(idx, usage, mse)
+        return q, idx, mse, usage
+
+    @staticmethod
+    def backward(ctx, grad_q, _gi, _gm, _gu):
+        (idx,) = ctx.saved_tensors
+        ge = ((_gather_bwd_codebook_impl if _fast() else gather_bwd_codebook)(grad_q, idx, ctx.num_codes)
+              if ctx.needs_input_grad[0] else None)
+        return ge, None, None, None, None
+
+
+def fused_forward(x, weight, blob, training, amp_fp16=False, algo=ALGO_AUTO):
+    """(q, idx, mse, usage) with autograd attached when needed."""
+    if training:
+        mode = MODE_TRAIN_AMP if amp_fp16 else MODE_TRAIN
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _FusedTrainForward.apply(x, weight.detach(), blob, mode, algo)
+        return (_vq_forward_impl if _fast() else vq_forward)(x, weight, blob, mode, algo)
+    mode = MODE_EVAL_AMP if amp_fp16 else MODE_EVAL
+    if torch.is_grad_enabled() and weight.requires_grad:
+        return _FusedEvalForward.apply(weight, x, blob, mode, algo)
+    return (_vq_forward_impl if _fast() else vq_forward)(x, weight, blob, mode, algo)
 
 
 def straight_through(x, codebook, idx, amp_fp16=False):

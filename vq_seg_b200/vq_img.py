@@ -204,15 +204,22 @@ class VectorQuantizer(nn.Module):
         cosine = isinstance(cb, CosinesimCodebook)
         if cb.kmeans_init and self.training and not cb.initted:
             cb._kmeans_init(ops.l2norm_rows(xv) if cosine else xv, cosine=cosine)
-        idx, counts = cb.lookup(xv)
-        code_usage = ops.fast_code_usage(counts)
         loss = torch.zeros(1, device=device, dtype=torch.float32, requires_grad=self.training)   # no H2D copy
-        if self.training:
-            quantize, mse = ops.straight_through(xv, cb.embedding.weight.detach(), idx, amp16)
-            if self.commitment_weight > 0:
-                loss = loss + mse * self.commitment_weight
+        if cosine:
+            idx, counts = cb.lookup(xv)
+            code_usage = ops.fast_code_usage(counts)
+            if self.training:
+                quantize, mse = ops.straight_through(xv, cb.embedding.weight.detach(), idx, amp16)
+            else:
+                quantize, mse = ops.eval_gather(cb.embedding.weight, xv, idx, amp16), None
         else:
-            quantize = ops.eval_gather(cb.embedding.weight, xv, idx, amp16)
+            # Euclidean: lookup + gather + STE + mse + usage are enqueued by one host call
+            if xv.shape[-1] != cb.embedding_dim:
+                raise RuntimeError(f"X1 and X2 must have the same number of columns. X1: {xv.shape[-1]} X2: {cb.embedding_dim}")
+            blob = cb._prepared() if cb.algo != ops.ALGO_EXACT else None
+            quantize, idx, mse, code_usage = ops.fused_forward(xv, cb.embedding.weight, blob, self.training, amp16, cb.algo)
+        if self.training and self.commitment_weight > 0:
+            loss = loss + mse * self.commitment_weight
         quantize = quantize.permute(0, 2, 1).reshape(b, c, h, w)     # memory is already (B, C, H*W): a view
         embed_index = idx.reshape(b, h, w)
         return quantize, embed_index, loss, code_usage
