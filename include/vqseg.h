@@ -59,6 +59,8 @@ void        vqseg_debug_set_trace(void* dev_buf);
  * CTA-pair kernel applies (lets the tests cover both on the same shapes).                              */
 void        vqseg_debug_force_streaming_kernel(int on);
 /* developer micro-benchmark: global->register bandwidth of the producer access patterns (csrc/debug_bw.cu) */
+/* developer micro-benchmark: fixed cost of an empty launch with the tcgen05 kernels' launch geometry */
+int         vqseg_debug_null_launch(int kind, void* stream);
 int         vqseg_debug_load_bandwidth(const float* x, int64_t n_floats, int64_t row_stride, int pattern, int depth,
                                        float* sink, void* stream);
 const char* vqseg_error_string(int code);

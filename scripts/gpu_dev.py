@@ -176,7 +176,8 @@ def stage_bw():
     x = torch.randn(8 * 256 * 4096, device=dev)          # 33.5 MB, rows of 4096 floats (one image's d-row)
     sink = torch.zeros(4, device=dev)
     junk = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for (pat, depth, nm) in [(0, 8, "LDG.128 8x64B/instr"), (1, 4, "LDG.256 8x128B/instr"), (2, 8, "LDG.128 512B contiguous")]:
+    for (pat, depth, nm) in [(0, 8, "LDG.128 8x64B/instr"), (1, 4, "LDG.256 8x128B/instr"), (2, 8, "LDG.128 512B contiguous"),
+                             (22, 8, "contiguous, 2 CTA/SM"), (42, 8, "contiguous, 4 CTA/SM"), (82, 8, "contiguous, 8 CTA/SM")]:
         for cold in (False, True):
             ts = []
             for _ in range(10):
@@ -190,6 +191,84 @@ def stage_bw():
                 ts.append(a.elapsed_time(b) * 1e3)
             ts.sort()
             print(f"[bw] {nm:26s} {'cold' if cold else 'L2-warm':8s}: median {ts[5]:7.1f} us -> {x.numel() * 4 / ts[5] / 1e6:6.2f} TB/s (best {ts[0]:.1f} us)")
+    big = torch.randn(1 << 28, device=dev)     # 1 GiB
+    for (pat, nm) in [(2, "1 GiB contiguous 1 CTA/SM"), (82, "1 GiB contiguous 8 CTA/SM")]:
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            L.vqseg_debug_load_bandwidth(big.data_ptr(), big.numel(), 4096, pat, 8, sink.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        ts.sort()
+        print(f"[bw] {nm:26s}: median {ts[2]:7.1f} us -> {big.numel() * 4 / ts[2] / 1e6:6.2f} TB/s")
+
+
+def stage_shapes():
+    """filter / rescoring kernel times (CUDA events inside the C ABI) over the BASELINE shapes"""
+    from vq_seg_b200 import _native
+    L = _native.lib()
+    shapes = {"C2": (8, 256, 64, 64, 512), "C1 l3": (2, 512, 64, 64, 512), "C1 l4": (2, 1024, 32, 32, 512),
+              "C1 l5": (2, 2048, 16, 16, 512), "C3 l3": (4, 512, 64, 64, 512), "C3 l4": (4, 1024, 32, 32, 512),
+              "C3 l5": (4, 2048, 16, 16, 512), "r448 l3": (4, 512, 56, 56, 512), "K4096": (8, 256, 64, 64, 4096),
+              "C5-like K=16384": (4, 256, 64, 64, 16384), "C4-like rows": (1, 512, 1, 262144, 1024)}
+    for nm, (b, c, h, w, k) in shapes.items():
+        g = torch.Generator(device="cuda").manual_seed(3)
+        if nm.startswith("C4"):
+            x = torch.randn(1, h * w, c, generator=g, device=dev)           # packed (N, D) rows
+            xv = x
+        else:
+            x = torch.relu(torch.randn(b, c, h * w, generator=g, device=dev))
+            xv = x.permute(0, 2, 1)
+        e = torch.randn(k, c, generator=g, device=dev)
+        blob = ops.prepare_codebook(e)
+        for _ in range(3):
+            ops.assign(xv, e, blob, ops.ALGO_TC)
+        L.vqseg_set_kernel_timing(1)
+        kt, rt = [], []
+        for _ in range(10):
+            ops.assign(xv, e, blob, ops.ALGO_TC); torch.cuda.synchronize()
+            kt.append(L.vqseg_get_kernel_timing_ms(0) * 1e3); rt.append(L.vqseg_get_kernel_timing_ms(1) * 1e3)
+        L.vqseg_set_kernel_timing(0)
+        kt.sort(); rt.sort()
+        n = xv.shape[0] * xv.shape[1]
+        flagged = ops._last_assign_ws[:4].view(torch.int32).item()
+        fl = 2.0 * n * k * c
+        print(f"[shapes] {nm:16s} N={n:7d} D={c:5d} K={k:6d}: filter {kt[5]:8.1f} us ({fl / kt[5] / 1e6:7.1f} TFLOP/s)  rescoring {rt[5]:7.1f} us  rescored {100.0 * flagged / n:5.1f}%", flush=True)
+
+
+def stage_null():
+    from vq_seg_b200 import _native
+    L = _native.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    small = torch.zeros(1024, device=dev)
+    for kind, nm in [(0, "148x640 threads"), (1, "+ 229 KB dynamic smem"), (2, "+ cluster of 2"), (3, "+ TMEM alloc/dealloc + cluster sync")]:
+        ts = []
+        for _ in range(5):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(200):
+                rc = L.vqseg_debug_null_launch(kind, st)
+            b.record(); torch.cuda.synchronize()
+            assert rc == 0, rc
+            ts.append(a.elapsed_time(b) * 1e3 / 200)
+        ts.sort()
+        print(f"[null] {nm:38s}: {ts[2]:6.2f} us per launch (200 back-to-back launches, GPU queue full)")
+
+
+def stage_stats():
+    """one k-means iteration's kernels at a config-4-like size (packed rows), for ncu's launch list"""
+    n, d, k = 1_000_000, 512, 1024
+    x = torch.randn(1, n, d, device=dev)
+    means = x[0, :k].contiguous()
+    blob = ops.prepare_codebook(means)
+    for rep in range(2):
+        idx, counts = ops.assign(x, means, blob, ops.ALGO_AUTO)
+        c1, s1 = ops.code_stats(x, idx, k, True)
+        c2, s2 = ops.code_stats(x, idx, k, False)
+        torch.cuda.synchronize()
+    print("stats done", c1.max().item(), c1.min().item(), (s1 - s2).abs().max().item())
 
 
 def stage_trace():
@@ -235,5 +314,5 @@ def stage_trace():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "shapes": stage_shapes, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

@@ -240,6 +240,30 @@ def test_code_stats_paths(dev):
     assert torch.equal(s.cpu(), ref_sums)
 
 
+def test_code_stats_chunked_large(dev):
+    """> 64 MB of rows: the ordered sums run range by range (TLB reach) and must still equal the sequential
+    CPU scatter_add_ bit for bit; skewed clusters on purpose."""
+    from vq_seg_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    n, d, k = 90_000, 512, 64
+    x = torch.randn(n, d, generator=g)
+    idx = (torch.rand(n, generator=g) ** 3 * k).long().clamp_(0, k - 1)          # heavy skew towards code 0
+    ref_sums = torch.zeros(k, d).scatter_add_(0, idx.reshape(-1, 1).expand(-1, d).contiguous(), x)
+    ref_counts = torch.bincount(idx, minlength=k)
+    c, s = ops.code_stats(x.unsqueeze(0).to(dev), idx.unsqueeze(0).to(dev), k, True)
+    assert torch.equal(c.cpu(), ref_counts) and torch.equal(s.cpu(), ref_sums)
+    c, s = ops.code_stats(x.unsqueeze(0).to(dev), idx.unsqueeze(0).to(dev), k, False)
+    assert torch.equal(c.cpu(), ref_counts)
+    torch.testing.assert_close(s.cpu(), ref_sums, rtol=2e-5, atol=2e-3)
+    # many images (NCHW): whole-image groups per pass
+    xi = torch.randn(40, 256, 4096, generator=g)                                  # 40 images x 4 MiB
+    ii = torch.randint(0, k, (40, 4096), generator=g)
+    flat = xi.permute(0, 2, 1).reshape(-1, 256)
+    ref = torch.zeros(k, 256).scatter_add_(0, ii.reshape(-1, 1).expand(-1, 256).contiguous(), flat.contiguous())
+    c, s = ops.code_stats(xi.permute(0, 2, 1).to(dev), ii.to(dev), k, True)
+    assert torch.equal(s.cpu(), ref)
+
+
 def test_amp_compat_rounds_code_through_fp16(dev):
     import vq_seg_b200 as V
     g = torch.Generator().manual_seed(19)

@@ -20,6 +20,7 @@ SIGNATURES = {
     "vqseg_get_kernel_timing_ms": (f32, [ci]),
     "vqseg_debug_set_trace": (None, [vp]),
     "vqseg_debug_force_streaming_kernel": (None, [ci]),
+    "vqseg_debug_null_launch": (ci, [ci, vp]),
     "vqseg_debug_load_bandwidth": (ci, [vp, i64, i64, ci, ci, vp, vp]),
     "vqseg_codebook_blob_bytes": (sz, [i64, i64]),
     "vqseg_codebook_prepare_f32": (ci, [vp, i64, i64, vp, sz, vp]),

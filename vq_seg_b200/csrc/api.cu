@@ -76,9 +76,8 @@ static int g_force_tc1 = 0;
 static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 static int g_ev_valid[2] = {0, 0};
 static void ev_record(int i, cudaStream_t st) {
-  if (!g_timing) return;
-  if (!g_ev[i]) cudaEventCreate(&g_ev[i]);
-  cudaEventRecord(g_ev[i], st);
+  if (!g_timing || !g_ev[i]) return;
+  if (cudaEventRecord(g_ev[i], st) != cudaSuccess) (void)cudaGetLastError();   // never poison the launch checks
 }
 
 extern "C" {
@@ -88,13 +87,19 @@ int vqseg_version(void) { return VQSEG_VERSION; }
 void vqseg_debug_set_trace(void* dev_buf) { g_trace = (long long*)dev_buf; }
 void vqseg_debug_force_streaming_kernel(int on) { g_force_tc1 = on; }
 
-void vqseg_set_kernel_timing(int enable) { g_timing = enable; g_ev_valid[0] = g_ev_valid[1] = 0; }
+void vqseg_set_kernel_timing(int enable) {
+  g_timing = enable; g_ev_valid[0] = g_ev_valid[1] = 0;
+  if (enable)                               // created here, outside any stream capture
+    for (int i = 0; i < 4; ++i)
+      if (!g_ev[i] && cudaEventCreate(&g_ev[i]) != cudaSuccess) { (void)cudaGetLastError(); g_ev[i] = nullptr; }
+}
 
 float vqseg_get_kernel_timing_ms(int which) {
   if (which < 0 || which > 1 || !g_ev_valid[which]) return -1.f;
   float ms = -1.f;
-  if (cudaEventSynchronize(g_ev[2 * which + 1]) != cudaSuccess) return -1.f;
-  if (cudaEventElapsedTime(&ms, g_ev[2 * which], g_ev[2 * which + 1]) != cudaSuccess) return -1.f;
+  if (!g_ev[2 * which] || !g_ev[2 * which + 1]) return -1.f;
+  if (cudaEventSynchronize(g_ev[2 * which + 1]) != cudaSuccess) { (void)cudaGetLastError(); return -1.f; }
+  if (cudaEventElapsedTime(&ms, g_ev[2 * which], g_ev[2 * which + 1]) != cudaSuccess) { (void)cudaGetLastError(); return -1.f; }
   return ms;
 }
 

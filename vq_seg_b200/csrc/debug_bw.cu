@@ -6,7 +6,7 @@
 namespace vqseg {
 
 template <int PATTERN, int DEPTH>
-__global__ void __launch_bounds__(256, 1) load_bw_kernel(const float* __restrict__ x, long long n_floats,
+__global__ void __launch_bounds__(256) load_bw_kernel(const float* __restrict__ x, long long n_floats,
                                                          long long row_stride, float* __restrict__ sink) {
   extern __shared__ unsigned char pad_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -57,20 +57,54 @@ __global__ void __launch_bounds__(256, 1) load_bw_kernel(const float* __restrict
   if (acc == 12345.678f) sink[0] = acc;
 }
 
+static int g_bw_blocks_per_sm = 1;
 template <int P, int D>
 static int launch_bw(const float* x, long long n, long long rs, float* sink, cudaStream_t st) {
+  const int smem = g_bw_blocks_per_sm == 1 ? 200 * 1024 : 0;
   cudaFuncSetAttribute(load_bw_kernel<P, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  load_bw_kernel<P, D><<<num_sms(), 256, 200 * 1024, st>>>(x, n, rs, sink);
+  load_bw_kernel<P, D><<<num_sms() * g_bw_blocks_per_sm, 256, smem, st>>>(x, n, rs, sink);
   VQSEG_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace vqseg
 
+namespace vqseg {
+__global__ void __launch_bounds__(640, 1) null_kernel(int* p) { if (p && threadIdx.x == 9999) p[0] = 1; }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) null_cluster_kernel(int* p) { if (p && threadIdx.x == 9999) p[0] = 1; }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) null_cluster_tmem_kernel(int* p) {
+  __shared__ uint32_t slot;
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512u));
+  if (p && threadIdx.x == 9999) p[0] = 1;
+}
+}  // namespace vqseg
+
+// kind 0: 148 x 640 threads, no smem; 1: + 228 KB dynamic smem; 2: + cluster of 2; 3: + TMEM alloc/dealloc + cluster sync
+extern "C" int vqseg_debug_null_launch(int kind, void* stream) {
+  using namespace vqseg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = 226 * 1024;
+  if (kind == 0) null_kernel<<<num_sms(), 640, 0, st>>>(nullptr);
+  else if (kind == 1) { cudaFuncSetAttribute(null_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); null_kernel<<<num_sms(), 640, smem, st>>>(nullptr); }
+  else if (kind == 2) { cudaFuncSetAttribute(null_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); null_cluster_kernel<<<num_sms(), 640, smem, st>>>(nullptr); }
+  else { cudaFuncSetAttribute(null_cluster_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem - 1024); null_cluster_tmem_kernel<<<num_sms(), 640, smem - 1024, st>>>(nullptr); }
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int vqseg_debug_load_bandwidth(const float* x, int64_t n_floats, int64_t row_stride, int pattern, int depth,
                                           float* sink, void* stream) {
   using namespace vqseg;
   cudaStream_t st = (cudaStream_t)stream;
+  g_bw_blocks_per_sm = pattern >= 10 ? pattern / 10 : 1;     // pattern 42 -> 4 blocks per SM, pattern 2
+  pattern %= 10;
   if (pattern == 0 && depth == 8) return launch_bw<0, 8>(x, n_floats, row_stride, sink, st);
   if (pattern == 1 && depth == 4) return launch_bw<1, 4>(x, n_floats, row_stride, sink, st);
   if (pattern == 2 && depth == 8) return launch_bw<2, 8>(x, n_floats, row_stride, sink, st);

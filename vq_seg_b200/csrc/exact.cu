@@ -216,7 +216,10 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
     for (int j0 = 0; j0 < D; j0 += 256) {
       float t[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { const int j = j0 + lane + 32 * u; t[u] = j < D ? __ldg(xr + (long long)j * a.x.sD) : 0.f; }
+      for (int u = 0; u < 8; ++u) {      // unconditional (clamped) loads: a predicated load gets fused with its predicated store and serialises
+        const int j = min(j0 + lane + 32 * u, D - 1);
+        t[u] = __ldg(xr + (long long)j * a.x.sD);
+      }
 #pragma unroll
       for (int u = 0; u < 8; ++u) { const int j = j0 + lane + 32 * u; if (j < D) xs[j] = t[u]; }
     }

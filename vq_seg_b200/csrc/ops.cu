@@ -298,6 +298,28 @@ __global__ void __launch_bounds__(256) code_stats_atomic_kernel(Rows x, const lo
   }
 }
 
+// packed rows: one warp per row, lanes along d, 16-byte vector reductions (red.global.add.v4.f32)
+__global__ void __launch_bounds__(256) code_stats_atomic_rows_kernel(const float* __restrict__ x, long long row_stride,
+                                                                     long long n_rows, int D,
+                                                                     const long long* __restrict__ idx, int K,
+                                                                     unsigned long long* __restrict__ counts,
+                                                                     float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long n = w0; n < n_rows; n += nw) {
+    const long long k = idx[n];
+    if (k < 0 || k >= K) continue;
+    const float* xr = x + n * row_stride;
+    float* sr = sums + k * D;
+    for (int d = 4 * lane; d < D; d += 128) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xr + d));
+      atomicAdd(reinterpret_cast<float4*>(sr + d), v);
+    }
+    if (lane == 0) atomicAdd(counts + k, 1ull);
+  }
+}
+
 // deterministic path ---------------------------------------------------------------------------
 constexpr int kSortBlock = 1024;   // rows per ranking block
 
@@ -372,7 +394,54 @@ __global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __
     __syncthreads();
   }
 }
-// (5) ordered per-code sums: one warp per (code, 32-dim slab); ascending-row fp32 chain per (k, d)
+// (5) ordered per-code sums: ascending-row fp32 chain per (k, d).
+// Packed rows (sD == 1, B == 1): one warp per (code, 128-dim slab), float4 per lane, 16 rows in flight (the row
+// ids of the next batch are fetched lane-parallel and broadcast with shuffles).  The chain of a code is
+// inherently sequential (that is what makes it bit-exact), so the critical path is max_k count[k] * latency / 16.
+__global__ void __launch_bounds__(256) stats_ordered_sum_rows_kernel(const float* __restrict__ x, long long row_stride,
+                                                                     int D, const int* __restrict__ perm,
+                                                                     const long long* __restrict__ code_start, int K,
+                                                                     float* __restrict__ sums) {
+  const int slabs = (D + 127) / 128;
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)K * slabs) return;
+  const int k = (int)(wid / slabs), d = (int)(wid % slabs) * 128 + 4 * lane;
+  const long long beg = code_start[k], end = code_start[k + 1];
+  const bool act = d < D;                       // D % 4 == 0 is guaranteed by the launcher
+  float4 s = act ? *reinterpret_cast<const float4*>(sums + (long long)k * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* xd = x + (act ? d : 0);
+  long long j = beg;
+  int nxt = (j + lane < end) ? __ldg(perm + j + lane) : 0;          // row ids of the next 32 rows, one per lane
+  while (j < end) {
+    const int ids = nxt;
+    const long long jn = j + 32;
+    nxt = (jn + lane < end) ? __ldg(perm + jn + lane) : 0;
+    const int cnt = (int)min((long long)32, end - j);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        // UNCONDITIONAL loads (rows past the end re-read the last valid row and are simply not added): with a
+        // predicate on the load the compiler fuses it with the predicated add below and the 16 loads serialise
+        const int r = __shfl_sync(0xffffffffu, ids, min(16 * h + u, cnt - 1));
+        v[u] = __ldg(reinterpret_cast<const float4*>(xd + (long long)r * row_stride));
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (16 * h + u < cnt) {
+          s.x = __fadd_rn(s.x, v[u].x); s.y = __fadd_rn(s.y, v[u].y);
+          s.z = __fadd_rn(s.z, v[u].z); s.w = __fadd_rn(s.w, v[u].w);
+        }
+      }
+    }
+    j = jn;
+  }
+  if (act) *reinterpret_cast<float4*>(sums + (long long)k * D + d) = s;
+}
+
+// Any strides (NCHW feature maps): one warp per (code, 32-dim slab), lanes along d.
 __global__ void __launch_bounds__(256) stats_ordered_sum_kernel(Rows x, const int* __restrict__ perm,
                                                                 const long long* __restrict__ code_start, int K,
                                                                 float* __restrict__ sums) {
@@ -383,18 +452,31 @@ __global__ void __launch_bounds__(256) stats_ordered_sum_kernel(Rows x, const in
   if (wid >= (long long)K * slabs) return;
   const int k = (int)(wid / slabs), d = (int)(wid % slabs) * 32 + lane;
   const long long beg = code_start[k], end = code_start[k + 1];
-  if (d >= D) return;
-  float s = sums[(long long)k * D + d];     // accumulate on top (caller zeroes; ranks chain)
+  const bool act = d < D;
+  float s = act ? sums[(long long)k * D + d] : 0.f;     // accumulate on top (caller zeroes; ranks chain)
   long long j = beg;
-  for (; j + 8 <= end; j += 8) {
-    float v[8];
+  int nxt = (j + lane < end) ? __ldg(perm + j + lane) : 0;
+  while (j < end) {
+    const int ids = nxt;
+    const long long jn = j + 32;
+    nxt = (jn + lane < end) ? __ldg(perm + jn + lane) : 0;
+    const int cnt = (int)min((long long)32, end - j);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(x.row(perm[j + u]) + (long long)d * x.sD);
+    for (int h = 0; h < 2; ++h) {
+      float v[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
+      for (int u = 0; u < 16; ++u) {
+        const int r = __shfl_sync(0xffffffffu, ids, min(16 * h + u, cnt - 1));     // unconditional loads, see above
+        const long long b = r / x.P, p = r - b * x.P;
+        v[u] = __ldg(x.ptr + b * x.sB + p * x.sP + (long long)(act ? d : 0) * x.sD);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (16 * h + u < cnt) s = __fadd_rn(s, v[u]);
+    }
+    j = jn;
   }
-  for (; j < end; ++j) s = __fadd_rn(s, __ldg(x.row(perm[j]) + (long long)d * x.sD));
-  sums[(long long)k * D + d] = s;
+  if (act) sums[(long long)k * D + d] = s;
 }
 
 // means = where(counts==0, means, sums / max(counts,1)) [ + l2norm ]      (vq_img.py:44-45,:53-61)
@@ -515,6 +597,49 @@ static inline unsigned grid_for(long long total, int threads, int waves = 8) {
 
 using namespace vqseg;
 
+// one pass of the deterministic statistics over a row range (accumulates on top of counts / sums)
+static int stats_det_range(const float* x, long long B, long long P, long long D, long long sB, long long sP, long long sD,
+                           const int64_t* idx, long long K, int64_t* counts, float* sums, void* ws, cudaStream_t st) {
+  const long long n_rows = B * P;
+  Rows xr{x, B, P, D, sB, sP, sD};
+  const long long nblk = (n_rows + kSortBlock - 1) / kSortBlock;
+  char* p = (char*)ws;
+  int* hist = (int*)p;                    p += round_up(nblk * K * sizeof(int), 256);
+  long long* code_total = (long long*)p;  p += round_up(K * sizeof(long long), 256);
+  long long* code_start = (long long*)p;  p += round_up((K + 1) * sizeof(long long), 256);
+  int* perm = (int*)p;
+  cudaError_t e = cudaMemsetAsync(hist, 0, nblk * K * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  stats_hist_kernel<<<(unsigned)nblk, kSortBlock, 0, st>>>((const long long*)idx, n_rows, (int)K, hist);
+  VQSEG_LAUNCH_CHECK();
+  stats_scan_blocks_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(hist, (int)nblk, (int)K,
+                                                                         (unsigned long long*)counts, code_total);
+  VQSEG_LAUNCH_CHECK();
+  stats_scan_codes_kernel<<<1, 1024, 0, st>>>(code_total, (int)K, code_start);
+  VQSEG_LAUNCH_CHECK();
+  size_t smem = (size_t)K * sizeof(int);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    e = cudaFuncSetAttribute(stats_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>((const long long*)idx, n_rows, (int)K, hist, code_start, perm);
+  VQSEG_LAUNCH_CHECK();
+  const bool packed = B == 1 && sD == 1 && D % 4 == 0 && sP % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0;
+  if (packed) {
+    const long long warps = K * ((D + 127) / 128);
+    stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(x, sP, (int)D, perm, code_start,
+                                                                                        (int)K, sums);
+  } else {
+    const long long warps = K * ((D + 31) / 32);
+    stats_ordered_sum_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(xr, perm, code_start, (int)K, sums);
+  }
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" {
 
 size_t vqseg_gather_workspace_bytes(int64_t n_rows, int64_t D) {
@@ -612,40 +737,51 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
   cudaStream_t st = (cudaStream_t)stream;
   Rows xr{x, B, P, D, sB, sP, sD};
   if (!deterministic) {
-    code_stats_atomic_kernel<<<grid_for(n_rows * D, 256, 16), 256, 0, st>>>(xr, (const long long*)idx, (int)K,
-                                                                            (unsigned long long*)counts, sums, sP == 1);
+    const bool packed_rows = B == 1 && sD == 1 && D % 4 == 0 && sP % 4 == 0 &&
+                             (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0;
+    if (packed_rows)
+      code_stats_atomic_rows_kernel<<<grid_for(n_rows * 32, 256, 16), 256, 0, st>>>(x, sP, n_rows, (int)D, (const long long*)idx,
+                                                                                   (int)K, (unsigned long long*)counts, sums);
+    else
+      code_stats_atomic_kernel<<<grid_for(n_rows * D, 256, 16), 256, 0, st>>>(xr, (const long long*)idx, (int)K,
+                                                                              (unsigned long long*)counts, sums, sP == 1);
     VQSEG_LAUNCH_CHECK();
     return 0;
   }
   if (ws_bytes < vqseg_code_stats_workspace_bytes(n_rows, D, K, 1) || !ws) return VQSEG_EWORKSPACE;
   if (K * sizeof(int) > 200 * 1024) return VQSEG_EUNSUPPORTED;
-  const long long nblk = (n_rows + kSortBlock - 1) / kSortBlock;
-  char* p = (char*)ws;
-  int* hist = (int*)p;                    p += round_up(nblk * K * sizeof(int), 256);
-  long long* code_total = (long long*)p;  p += round_up(K * sizeof(long long), 256);
-  long long* code_start = (long long*)p;  p += round_up((K + 1) * sizeof(long long), 256);
-  int* perm = (int*)p;
-  cudaError_t e = cudaMemsetAsync(hist, 0, nblk * K * sizeof(int), st);
-  if (e != cudaSuccess) return (int)e;
-  stats_hist_kernel<<<(unsigned)nblk, kSortBlock, 0, st>>>((const long long*)idx, n_rows, (int)K, hist);
-  VQSEG_LAUNCH_CHECK();
-  stats_scan_blocks_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(hist, (int)nblk, (int)K,
-                                                                         (unsigned long long*)counts, code_total);
-  VQSEG_LAUNCH_CHECK();
-  stats_scan_codes_kernel<<<1, 1024, 0, st>>>(code_total, (int)K, code_start);
-  VQSEG_LAUNCH_CHECK();
-  size_t smem = (size_t)K * sizeof(int);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    e = cudaFuncSetAttribute(stats_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
+  // The ordered sums visit rows grouped by code, i.e. in random order over the whole array: beyond the TLB reach
+  // (256 MB of 2 MB pages) every access misses and the chains crawl at ~1.3 us per row.  Row ranges of at most
+  // kDetChunkBytes are therefore processed one after the other; each (code, d) chain simply continues on top of
+  // `sums`, so the summation order -- ascending row id per code -- is unchanged.
+  const long long kDetChunkBytes = 64ll << 20;
+  const long long row_bytes = D * (long long)sizeof(float);
+  long long rows_per_chunk = kDetChunkBytes / row_bytes;
+  rows_per_chunk = rows_per_chunk < 4096 ? 4096 : rows_per_chunk / 1024 * 1024;
+  if (n_rows <= rows_per_chunk) return stats_det_range(x, B, P, D, sB, sP, sD, idx, K, counts, sums, ws, st);
+  if (B == 1) {
+    for (long long r0 = 0; r0 < n_rows; r0 += rows_per_chunk) {
+      const long long len = n_rows - r0 < rows_per_chunk ? n_rows - r0 : rows_per_chunk;
+      int rc = stats_det_range(x + r0 * sP, 1, len, D, sB, sP, sD, idx + r0, K, counts, sums, ws, st);
+      if (rc) return rc;
+    }
+    return 0;
   }
-  stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>((const long long*)idx, n_rows, (int)K, hist, code_start, perm);
-  VQSEG_LAUNCH_CHECK();
-  const long long warps = K * ((D + 31) / 32);
-  stats_ordered_sum_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(xr, perm, code_start, (int)K, sums);
-  VQSEG_LAUNCH_CHECK();
+  if (P <= rows_per_chunk) {                 // whole images per pass
+    const long long ipc = rows_per_chunk / P;
+    for (long long b0 = 0; b0 < B; b0 += ipc) {
+      const long long nb = B - b0 < ipc ? B - b0 : ipc;
+      int rc = stats_det_range(x + b0 * sB, nb, P, D, sB, sP, sD, idx + b0 * P, K, counts, sums, ws, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  for (long long b0 = 0; b0 < B; ++b0)
+    for (long long p0 = 0; p0 < P; p0 += rows_per_chunk) {
+      const long long len = P - p0 < rows_per_chunk ? P - p0 : rows_per_chunk;
+      int rc = stats_det_range(x + b0 * sB + p0 * sP, 1, len, D, sB, sP, sD, idx + b0 * P + p0, K, counts, sums, ws, st);
+      if (rc) return rc;
+    }
   return 0;
 }
 
