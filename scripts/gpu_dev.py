@@ -192,16 +192,22 @@ def stage_bw():
             ts.sort()
             print(f"[bw] {nm:26s} {'cold' if cold else 'L2-warm':8s}: median {ts[5]:7.1f} us -> {x.numel() * 4 / ts[5] / 1e6:6.2f} TB/s (best {ts[0]:.1f} us)")
     big = torch.randn(1 << 28, device=dev)     # 1 GiB
-    for (pat, nm) in [(2, "1 GiB contiguous 1 CTA/SM"), (82, "1 GiB contiguous 8 CTA/SM")]:
-        ts = []
-        for _ in range(5):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            L.vqseg_debug_load_bandwidth(big.data_ptr(), big.numel(), 4096, pat, 8, sink.data_ptr(), torch.cuda.current_stream().cuda_stream)
-            b.record(); torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b) * 1e3)
-        ts.sort()
-        print(f"[bw] {nm:26s}: median {ts[2]:7.1f} us -> {big.numel() * 4 / ts[2] / 1e6:6.2f} TB/s")
+    for (pat, depth, nm) in [(0, 8, "P0 LDG.128 8x64B depth 8"), (0, 24, "P0 LDG.128 8x64B depth 24"), (1, 4, "P1 LDG.256 8x128B depth 4"),
+                             (1, 12, "P1 LDG.256 8x128B depth 12"), (2, 8, "P2 contiguous depth 8"), (2, 24, "P2 contiguous depth 24"),
+                             (82, 8, "P2 contiguous 8 CTA/SM")]:
+        for buf, bn in ((big, "1 GiB"), (x, "33.5 MB")):
+            ts = []
+            for _ in range(5):
+                if bn != "1 GiB":
+                    junk.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                rc = L.vqseg_debug_load_bandwidth(buf.data_ptr(), buf.numel(), 4096, pat, depth, sink.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                b.record(); torch.cuda.synchronize()
+                assert rc == 0, rc
+                ts.append(a.elapsed_time(b) * 1e3)
+            ts.sort()
+            print(f"[bw2] {nm:30s} {bn:8s}: median {ts[2]:8.1f} us -> {buf.numel() * 4 / ts[2] / 1e6:6.2f} TB/s")
 
 
 def stage_shapes():

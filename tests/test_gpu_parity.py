@@ -56,6 +56,50 @@ def test_assign_matches_golden(dev, golden, name, algo):
     assert torch.equal(counts.cpu(), rec["counts"])
 
 
+@pytest.mark.parametrize("name", ["c2_randn", "c2_relu", "d64", "odd_7x7", "k_not_tile", "dup_codes", "equidistant", "x_equals_code"])
+def test_streaming_kernel_on_resident_shapes(dev, golden, name):
+    """Shapes that normally take the CTA-pair codebook-resident kernel, forced through the single-CTA
+    streaming tcgen05 kernel: both must reproduce the reference indices."""
+    from vq_seg_b200 import ops, _native
+    x, e = cases.FORWARD_CASES[name]()
+    rec = golden["forward"][name]
+    xd, ed = x.to(dev), e.to(dev)
+    blob = ops.prepare_codebook(ed)
+    L = _native.lib()
+    L.vqseg_debug_force_streaming_kernel(1)
+    try:
+        idx, counts = ops.assign(view(xd), ed, blob, ops.ALGO_TC)
+        torch.cuda.synchronize()
+    finally:
+        L.vqseg_debug_force_streaming_kernel(0)
+    assert torch.equal(idx.cpu(), rec["idx"].reshape(idx.shape).to(torch.int64))
+    assert torch.equal(counts.cpu(), rec["counts"])
+
+
+def test_kblock_override_changes_only_near_ties(dev):
+    """kblock is the fp32 chain split of the exact scorer; a different split may only move rows
+    whose two best reference distances are within 2 ulp."""
+    from vq_seg_b200 import ops
+    x, e = cases.FORWARD_CASES["c1_l4"]()
+    xd, ed = x.to(dev), e.to(dev)
+    i_auto, _ = ops.assign(view(xd), ed, None, ops.ALGO_EXACT, 0)
+    i_one, _ = ops.assign(view(xd), ed, None, ops.ALGO_EXACT, 1 << 20)       # one chain, no split
+    assert near_tie_ok(x, e, i_one.cpu(), i_auto.cpu())
+
+
+def test_large_codebook_streaming(dev):
+    """config-5-like: K = 8192 codes streamed through the single-CTA kernel (32 code chunks per tile)."""
+    from vq_seg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(2, 128, 2048, generator=g, device=dev)
+    e = torch.randn(8192, 128, generator=g, device=dev)
+    xv = x.permute(0, 2, 1)
+    i1, c1 = ops.assign(xv, e, None, ops.ALGO_EXACT)
+    i2, c2 = ops.assign(xv, e, ops.prepare_codebook(e), ops.ALGO_TC)
+    assert torch.equal(i1, i2) and torch.equal(c1, c2)
+    assert near_tie_ok(x.cpu().reshape(2, 128, 2048, 1), e.cpu(), i2.cpu(), O.assign_euclidean(xv.cpu(), e.cpu()))
+
+
 @pytest.mark.parametrize("name", ["c2_randn", "c2_relu", "c1_l3", "c1_l4", "c1_l5", "r448_l3", "r448_l5", "odd_7x7",
                                   "dup_codes", "x_equals_code", "equidistant", "all_zero_x", "n_lt_k", "k_not_tile",
                                   "d96_k1024", "c1_l5_uniform"])

@@ -223,7 +223,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
     int* cand = reinterpret_cast<int*>(smem + Tc2Smem::off_cand) + (half * k2Rows + r) * k2CandCap;
     const int* cand_hi = reinterpret_cast<const int*>(smem + Tc2Smem::off_cand) + (k2Rows + r) * k2CandCap;
     float2* xchg = reinterpret_cast<float2*>(smem + Tc2Smem::off_xchg) + r;
-    float scale = 0.f, emax = 0.f, de_max = 0.f;
+    // header scalars are fetched up front: their DRAM latency must not sit between "accumulator ready" and
+    // "accumulator drained" of the first unit, which gates the second tile's MMAs
+    const float scale = hdr->scale;
+    const float emax = sqrtf(hdr->max_enorm) * 1.0001f;
+    const float de_max = sqrtf(__uint_as_float(hdr->max_de2_bits)) * 1.0001f;
+    const bool bad_blob = (hdr->flags & 1u) != 0;
     int u = 0;
     for (int tt = 0; tt < my_tiles; ++tt) {
       const long long n = ((long long)pair + (long long)tt * n_pairs) * 256 + rank * 128 + r;
@@ -232,16 +237,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
       int cnt = 0;
       bool overflow = false;
       for (int cc = 0; cc < a.n_cc; ++cc, ++u) {
-        const int buf = u & 1;
+        const int buf = a.n_cc == 1 ? (tt & 1) : cc;
+        const uint32_t use = a.n_cc == 1 ? (uint32_t)(tt >> 1) : (uint32_t)tt;
         if (warp == 8) VQ2_TRACE(2, 4 * u);
-        mbar_wait(bar_tfull + 8 * buf, (uint32_t)(u >> 1) & 1);
+        mbar_wait(bar_tfull + 8 * buf, use & 1);
         tc_fence_after();
         if (warp == 8) VQ2_TRACE(2, 4 * u + 1);
         if (cc == 0) {
-          if (tt == 0) {
-            scale = hdr->scale; emax = sqrtf(hdr->max_enorm) * 1.0001f;
-            de_max = sqrtf(__uint_as_float(hdr->max_de2_bits)) * 1.0001f;
-          }
           const float2 nr = reinterpret_cast<const float2*>(xsq)[(tt & (k2XsqBufs - 1)) * k2Rows + r];
           const float xn = sqrtf(nr.x) * 1.0001f, dn = sqrtf(nr.y) * 1.0001f;
           const float e_s = emax * scale;
@@ -250,7 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
           // assign_tc.cu), two-sided, + fp32 accumulation / exact-chain error + limb residual of |e|^2
           slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum
                 + 1.0e-6f * e_s * emax;
-          if (!(slack < 3.0e38f) || (hdr->flags & 1u)) overflow = true;
+          if (!(slack < 3.0e38f) || bad_blob) overflow = true;
         }
         const uint32_t tb = lane_addr + buf * 256;
 #pragma unroll 1
@@ -364,36 +366,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
     } else if (warp == 16 && rank == 0) {
       // ================= MMA issuer (leader CTA) =================
       const uint64_t aaug = make_desc_noswz(sbase + Tc2Smem::off_aaug, 128, 256);
-      for (int u = 0; u < my_units; ++u) {
-        const int tt = u / a.n_cc, cc = u - tt * a.n_cc;
-        const int buf = u & 1;
-        VQ2_TRACE(1, 128 + 2 * u);
-        mbar_wait(bar_tempty + 8 * buf, (((uint32_t)u >> 1) & 1) ^ 1);   // both epilogues drained it
-        VQ2_TRACE(1, 128 + 2 * u + 1);
-        if (tt == 0) mbar_wait(bar_bready + 8 * cc, 0);                 // this code chunk is resident in both CTAs
+      // Dims-outer order: every 64-dim A chunk is multiplied against BOTH 256-code chunks as soon as it lands
+      // (the kernel is bound by how fast x arrives, so the MMAs hide under the loads), its smem slot is released
+      // at once, and the tile's two accumulators (TMEM columns 0-255 / 256-511) complete together.
+      // n_cc == 1: the two TMEM halves alternate between tiles instead.
+      for (int tt = 0; tt < my_tiles; ++tt) {
+        for (int cc = 0; cc < a.n_cc; ++cc) {
+          const int buf = a.n_cc == 1 ? (tt & 1) : cc;
+          const uint32_t use = a.n_cc == 1 ? (uint32_t)(tt >> 1) : (uint32_t)tt;
+          VQ2_TRACE(1, 128 + 2 * (tt * a.n_cc + cc));
+          mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);               // both CTAs' epilogues drained it
+          VQ2_TRACE(1, 128 + 2 * (tt * a.n_cc + cc) + 1);
+          if (tt == 0) mbar_wait(bar_bready + 8 * cc, 0);                // this code chunk is resident in both CTAs
+        }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 256;
         for (int dc = 0; dc < a.n_dc; ++dc) {
-          if (cc == 0) {
-            VQ2_TRACE(1, 2 * (tt * a.n_dc + dc));
-            mbar_wait(bar_full + 8 * dc, (uint32_t)tt & 1);    // both CTAs' halves of the A chunk landed
-            VQ2_TRACE(1, 2 * (tt * a.n_dc + dc) + 1);
-            tc_fence_after();
-          }
+          VQ2_TRACE(1, 2 * (tt * a.n_dc + dc));
+          mbar_wait(bar_full + 8 * dc, (uint32_t)tt & 1);                // both CTAs' halves of the A chunk landed
+          VQ2_TRACE(1, 2 * (tt * a.n_dc + dc) + 1);
+          tc_fence_after();
           if (lane == 0) {
             const uint64_t ad = make_desc(sbase + Tc2Smem::off_a + dc * kTileBytes);
-            const uint64_t bd = make_desc(sbase + Tc2Smem::off_b + (cc * a.n_dc + dc) * kTileBytes);
+            for (int cc = 0; cc < a.n_cc; ++cc) {
+              const int buf = a.n_cc == 1 ? (tt & 1) : cc;
+              const uint64_t bd = make_desc(sbase + Tc2Smem::off_b + (cc * a.n_dc + dc) * kTileBytes);
 #pragma unroll
-            for (int k = 0; k < kDChunk / 16; ++k)
-              tc_mma_f16_2cta(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), k2Idesc, (dc | k) ? 1u : 0u);
-            if (cc == a.n_cc - 1) tc_commit_2cta(bar_empty + 8 * dc);   // A slot free in both CTAs
+              for (int k = 0; k < kDChunk / 16; ++k)
+                tc_mma_f16_2cta(tmem_base + buf * 256, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), k2Idesc,
+                                (dc | k) ? 1u : 0u);
+            }
+            tc_commit_2cta(bar_empty + 8 * dc);                          // A slot free in both CTAs
           }
           __syncwarp();
         }
         if (lane == 0) {
-          const uint64_t baug = make_desc_noswz(sbase + Tc2Smem::off_baug + cc * k2AugBytes, 128, 256);
-          tc_mma_f16_2cta(d_tmem, aaug, baug, k2Idesc, 1u);             // + s |e_k|^2
-          tc_commit_2cta(bar_tfull + 8 * buf);
+          for (int cc = 0; cc < a.n_cc; ++cc) {
+            const int buf = a.n_cc == 1 ? (tt & 1) : cc;
+            const uint64_t baug = make_desc_noswz(sbase + Tc2Smem::off_baug + cc * k2AugBytes, 128, 256);
+            tc_mma_f16_2cta(tmem_base + buf * 256, aaug, baug, k2Idesc, 1u);   // + s |e_k|^2
+            tc_commit_2cta(bar_tfull + 8 * buf);
+          }
         }
         __syncwarp();
       }
@@ -424,7 +436,7 @@ static int launch_mode2(const Tc2Args& a, int grid, cudaStream_t st) {
   return 0;
 }
 
-bool tc2_supported(int n_cc, int n_dc) { return n_dc <= k2ASlots && n_cc <= k2MaxCC && n_cc * n_dc <= k2MaxBTiles; }
+bool tc2_supported(int n_cc, int n_dc) { return n_dc <= k2ASlots && n_cc <= 2 && n_cc * n_dc <= k2MaxBTiles; }
 
 int launch_assign_tc2(const Tc2Args& a, cudaStream_t st) {
   int pairs = num_sms() / 2;

@@ -14,11 +14,12 @@ __global__ void __launch_bounds__(256) load_bw_kernel(const float* __restrict__ 
   const long long px_per_row = row_stride;                 // floats per row
   const long long tiles_per_row = px_per_row / 128;
   const long long n_rows = n_floats / row_stride;
-  const long long n_tiles = tiles_per_row * (n_rows / 64);
+  constexpr int kGroups = (PATTERN == 1) ? (DEPTH + 3) / 4 : (DEPTH + 7) / 8;     // 64-row groups per iteration
+  const long long n_tiles = tiles_per_row * (n_rows / (64 * kGroups));
   float acc = 0.f;
   for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const long long rt = t / tiles_per_row, pt = t % tiles_per_row;
-    const float* base = x + rt * 64 * row_stride + pt * 128;
+    const float* base = x + rt * 64 * kGroups * row_stride + pt * 128;
     if (PATTERN == 0) {            // LDG.128: warp -> 16 px, lane = quad*8+g8, 8 rows per thread: 8 x 64 B per instr
       const int g8 = lane & 7, quad = lane >> 3;
       const float* p = base + (long long)(8 * g8) * row_stride + 16 * warp + 4 * quad;
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(256) load_bw_kernel(const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < DEPTH; ++j)
         asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
-                     : "l"(p + (long long)(j & 7) * row_stride + (j >> 3) * 0));
+                     : "l"(p + (long long)((j & 7) + 64 * (j >> 3)) * row_stride));
 #pragma unroll
       for (int j = 0; j < DEPTH; ++j) acc += v[j].x + v[j].y + v[j].z + v[j].w;
     } else if (PATTERN == 1) {     // LDG.256: warps 0-3 rows 0..31? -> warp pair covers 32 px: 8 x 128 B per instr
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(256) load_bw_kernel(const float* __restrict__ 
       for (int j = 0; j < DEPTH; ++j)
         asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=f"(v[j][0]), "=f"(v[j][1]), "=f"(v[j][2]), "=f"(v[j][3]), "=f"(v[j][4]), "=f"(v[j][5]), "=f"(v[j][6]), "=f"(v[j][7])
-                     : "l"(p + (long long)(j & 3) * row_stride));
+                     : "l"(p + (long long)((j & 3) + 64 * (j >> 2)) * row_stride));
 #pragma unroll
       for (int j = 0; j < DEPTH; ++j)
 #pragma unroll
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) load_bw_kernel(const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < DEPTH; ++j)
         asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
-                     : "l"(p + (long long)(j & 7) * row_stride));
+                     : "l"(p + (long long)((j & 7) + 64 * (j >> 3)) * row_stride));
 #pragma unroll
       for (int j = 0; j < DEPTH; ++j) acc += v[j].x + v[j].y + v[j].z + v[j].w;
     }
@@ -106,6 +107,9 @@ extern "C" int vqseg_debug_load_bandwidth(const float* x, int64_t n_floats, int6
   g_bw_blocks_per_sm = pattern >= 10 ? pattern / 10 : 1;     // pattern 42 -> 4 blocks per SM, pattern 2
   pattern %= 10;
   if (pattern == 0 && depth == 8) return launch_bw<0, 8>(x, n_floats, row_stride, sink, st);
+  if (pattern == 0 && depth == 24) return launch_bw<0, 24>(x, n_floats, row_stride, sink, st);
+  if (pattern == 1 && depth == 12) return launch_bw<1, 12>(x, n_floats, row_stride, sink, st);
+  if (pattern == 2 && depth == 24) return launch_bw<2, 24>(x, n_floats, row_stride, sink, st);
   if (pattern == 1 && depth == 4) return launch_bw<1, 4>(x, n_floats, row_stride, sink, st);
   if (pattern == 2 && depth == 8) return launch_bw<2, 8>(x, n_floats, row_stride, sink, st);
   return VQSEG_EINVAL;
