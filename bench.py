@@ -163,10 +163,11 @@ def main():
     views = [x.reshape(B, C, H * W).permute(0, 2, 1) for x in xs]
 
     def step_eager(i):
+        # the module's own eval path: ONE host call enqueues memsets, the tcgen05 filter, the exact rescoring
+        # pass, the usage kernel and the gather (vqseg_vq_forward_f32)
         xv = views[i % args.ring]
-        idx, counts = ops.assign(xv, weight, blob, ops.ALGO_AUTO)
-        q, _ = ops.gather_ste(xv, weight, idx, ops.MODE_EVAL)
-        return q, idx, counts
+        q, idx, _mse, usage, counts = ops._vq_forward_counts(xv, weight, blob, ops.MODE_EVAL, ops.ALGO_AUTO)
+        return q, idx, usage, counts
 
     # One CUDA graph per ring slot: the launch sequence (memset, tcgen05 filter, exact rescoring, gather) is
     # replayed without per-launch host work; the kernels and their inputs are exactly those of step_eager.
@@ -201,19 +202,19 @@ def main():
             main_s.wait_event(ev_side[s])
         if graphs:
             graphs[s].replay()
-            q, idx, counts = outs[s]
+            q, idx, usage, counts = outs[s]
         else:
-            q, idx, counts = step_eager(i)
+            q, idx, usage, counts = step_eager(i)
         if world > 1:
+            # the lookup itself shards with no exchange; a GLOBAL code usage all-reduces the K per-code counts
+            # (4 KiB) on the side stream, overlapping the next step's kernels
             ev_main[s].record(main_s)
             with torch.cuda.stream(side_stream):
                 side_stream.wait_event(ev_main[s])
-                dist.all_reduce(counts)            # global code usage (4 KiB): the only exchange of the lookup path
+                dist.all_reduce(counts)
                 usages[s] = ops.code_usage(counts)
                 ev_side[s].record(side_stream)
             usage = usages[s]
-        else:
-            usage = ops.code_usage(counts)
         return q, idx, usage
 
     def barrier():
@@ -332,8 +333,9 @@ def main():
         if k_ms:
             ach = flops / (k_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "assign_tc2_kernel (tcgen05 cta_group::2 filter)", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
-                    "algorithmic_flops_per_launch": flops, "rescore_kernel_ms": statistics.median(rt) if rt else None}
+                    "frac": ach / peak_tf, "traffic": 33.9e6, "traffic_unit": "bytes/launch (dram read+write, ncu --set full, profiles/r01_ncu_full.md; algorithmic 34.3e6)",
+                    "peak_source": peak_src, "kernel_ms": k_ms,
+                    "algorithmic_flops_per_launch": flops, "rescore_kernel_ms": (statistics.median([v for v in rt if v > 0]) if any(v > 0 for v in rt) else None)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(os.cpu_count())
@@ -357,7 +359,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "vectors/s", "h2d_bytes_per_step": N_VEC * C * 4,
                         "d2h_bytes_per_step": N_VEC * 8 + 4, "steps": e2e_steps,
                         "how": "VectorQuantizer.forward (eval) per step; H2D of step i+1 on a copy stream overlaps step i"},
-                "gpu_launches": 4 * args.steps, "clocks": sampler.summary()}
+                "gpu_launches": 3 * args.steps,   # per step: tcgen05 filter, exact rescoring (+usage), gather "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -14,6 +14,8 @@ struct ExactArgs {
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
   int stage_e;
   long long* trace;
+  int* done_blocks;
+  float* usage_out;
 };
 int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st);
 int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st);
@@ -158,10 +160,25 @@ size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int al
   return b;
 }
 
+static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                           const float* E, int64_t K, const void* blob,
+                           int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
+                           int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
+                           float* usage_out);
+
 int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                      const float* E, int64_t K, const void* blob,
                      int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
                      int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream) {
+  return assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, best_key_out, code_base, kblock, algo,
+                         ws, ws_bytes, stream, nullptr);
+}
+
+static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                           const float* E, int64_t K, const void* blob,
+                           int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
+                           int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
+                           float* usage_out) {
   if (!x || !E || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
   if (!idx_out && !best_key_out) return VQSEG_EINVAL;
   const long long n_rows = B * P;
@@ -210,11 +227,15 @@ int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
   ea.x = xr; ea.E = E; ea.K = (int)K; ea.enorm = enorm; ea.kblock = kblock;
   ea.idx_out = (long long*)idx_out; ea.counts_out = (unsigned long long*)counts_out;
   ea.key_out = (unsigned long long*)best_key_out; ea.code_base = code_base;
+  ea.done_blocks = work_count + 1;
+  ea.usage_out = counts_out ? usage_out : nullptr;
+  {
+    cudaError_t e0 = cudaMemsetAsync(work_count, 0, 2 * sizeof(int), st);      // work counter + block ticket
+    if (e0 != cudaSuccess) return (int)e0;
+  }
 
   if (!use_tc) return launch_exact(ea, n_rows, st);
 
-  cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int), st);
-  if (e != cudaSuccess) return (int)e;
   const float tau = 0.00390625f * 1.015625f;   // 2^-8 (two fp16 roundings per operand pair, both sides) + margin
   const int n_cc = (int)(kp / 256), n_dc = (int)(dp / kDChunk);
   const bool force = (best_key_out != nullptr || idx_out == nullptr);
@@ -273,9 +294,9 @@ int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
   cudaError_t e = cudaMemsetAsync(counts_out, 0, (size_t)K * sizeof(int64_t), st);
   if (e != cudaSuccess) return (int)e;
   if (loss_out) { e = cudaMemsetAsync(loss_out, 0, sizeof(float), st); if (e != cudaSuccess) return (int)e; }
-  int rc = vqseg_assign_f32(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, kblock, algo, ws, wa, stream);
+  int rc = assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, kblock, algo, ws, wa, stream,
+                           usage_out);      // usage is reduced by the last block of the exact pass
   if (rc) return rc;
-  if (usage_out) { rc = vqseg_code_usage(counts_out, K, usage_out, stream); if (rc) return rc; }
   return vqseg_gather_ste_f32(x, B, P, D, sB, sP, sD, E, K, idx_out, q_out, qB, qP, qD, loss_out, mode,
                               (char*)ws + wa, ws_bytes - wa, stream);
 }

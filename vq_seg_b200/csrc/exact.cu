@@ -182,6 +182,8 @@ struct ExactArgs {
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
   int stage_e;
   long long* trace;     // dev tool: [0] min start ns, [1] max end ns, [2..] per-phase clock sums
+  int* done_blocks;     // ticket counter (zeroed by the host) for the fused usage epilogue
+  float* usage_out;     // nullable: the last block to finish writes 100 * (#counts == 0) / K   (vq_img.py:174-175)
 };
 
 constexpr int kExactWarps = 8;
@@ -335,6 +337,29 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
     }
   }
   if (a.trace && threadIdx.x == 0) atomicMax((unsigned long long*)a.trace + 1, (unsigned long long)gtime());
+  if (a.usage_out) {
+    // all counts are final once every block is through: the last one (ticket) reduces them -- saves a launch
+    __shared__ int s_last;
+    __shared__ int s_zero[kExactWarps];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(a.done_blocks, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      int z = 0;
+      for (int k = threadIdx.x; k < a.K; k += blockDim.x) z += (__ldcg((const unsigned long long*)a.counts_out + k) == 0ull);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+      if (lane == 0) s_zero[wib] = z;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w2 = 0; w2 < kExactWarps; ++w2) t += s_zero[w2];
+        *a.usage_out = __fmul_rn(100.f, __fdiv_rn((float)t, (float)a.K));
+      }
+    }
+  }
 }
 
 int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st) {

@@ -356,8 +356,17 @@ def _(xn, codebook):
 
 
 # -------------------------------------------------------------------------------------------------
+def _vq_forward_counts(x, codebook, blob, mode, algo=0):
+    """_vq_forward_impl plus the per-code counts (for a global, all-reduced code usage)."""
+    return _vq_forward_raw(x, codebook, blob, mode, algo)
+
+
 def _vq_forward_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], mode: int,
                      algo: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    return _vq_forward_raw(x, codebook, blob, mode, algo)[:4]
+
+
+def _vq_forward_raw(x, codebook, blob, mode, algo=0):
     """(q (B,P,D) in NCHW memory order, idx (B,P) int64, mse (1,), code_usage ()): the whole forward of
     vq_img.py:228-244 (minus the k-means hook) enqueued by ONE host call."""
     _require_cuda(x, codebook, blob)
@@ -385,7 +394,7 @@ def _vq_forward_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[tor
                                              idx.data_ptr(), counts.data_ptr(), usage.data_ptr(),
                                              q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), loss.data_ptr(),
                                              mode, algo, 0, ws.data_ptr(), nws, _stream()), "vq_forward")
-    return q, idx, loss, usage
+    return q, idx, loss, usage, counts
 
 
 vq_forward = torch.library.custom_op("vqseg::vq_forward", mutates_args=())(_vq_forward_impl)
