@@ -339,6 +339,73 @@ def test_eval_mode_gradient_goes_to_codebook(dev):
     torch.testing.assert_close(m.codebook.embedding.weight.grad, expect)
 
 
+def test_training_step_like_reference_loop(dev):
+    """The VQ call pattern of the reference's model + training loop (modified_vqunet/net.py:226-237,
+    train_vqreptunet1x1v2.py:143-202): make_vq_module list with Identity levels, k-means init on the first
+    training forward, eval-mode no_grad pass, fp16 autocast + GradScaler, commitment loss summed over levels,
+    `code_usage.detach().cpu()` per level, Adam over all parameters (codebook grads stay None)."""
+    import vq_seg_b200 as V
+
+    class TinyVQNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc = torch.nn.ModuleList([torch.nn.Conv2d(3, 16, 3, 2, 1), torch.nn.Conv2d(16, 64, 3, 2, 1),
+                                            torch.nn.Conv2d(64, 128, 3, 2, 1)])
+            self.codebook = V.make_vq_module({"num_embeddings": [0, 64, 64], "distance": "euclidean", "kmeans_init": True},
+                                             [3, 16, 64, 128], 3)
+            self.head = torch.nn.Conv2d(128, 3, 1)
+
+        def forward(self, x):
+            feats = []
+            for conv in self.enc:
+                x = torch.relu(conv(x))
+                feats.append(x)
+            loss = torch.tensor([0.], device=x.device, requires_grad=self.training)
+            usage = []
+            for i in range(len(feats)):
+                q, _idx, commit, cu = self.codebook[i](feats[i])
+                feats[i] = q
+                if commit is not None:
+                    loss = loss + commit
+                if cu is not None:
+                    usage.append(cu.detach().cpu())
+            loss = loss / len(feats)
+            return self.head(feats[-1]), loss, torch.tensor(usage)
+
+    torch.manual_seed(0)
+    net = TinyVQNet().to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    scaler = torch.amp.GradScaler("cuda", enabled=True)
+    x = torch.rand(4, 3, 64, 64, device=dev)
+    y = torch.randint(0, 3, (4, 8, 8), device=dev)
+    net.eval()
+    with torch.no_grad():
+        net(x)                                            # eval pass first: must NOT trigger k-means
+    assert not net.codebook[1].codebook.initted
+    net.train()
+    w_before = [m.codebook.embedding.weight.detach().clone() for m in net.codebook[1:]]
+    losses = []
+    for step in range(3):
+        with torch.autocast("cuda", dtype=torch.float16):
+            logits, commit, usage = net(x)
+            loss = torch.nn.functional.cross_entropy(logits.float(), y) + commit.sum()
+        opt.zero_grad()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        losses.append(loss.item())
+        assert usage.shape == (2,) and commit.shape == (1,) and commit.requires_grad
+        if step == 0:
+            w_init = [m.codebook.embedding.weight.detach().clone() for m in net.codebook[1:]]
+            assert all(m.codebook.initted for m in net.codebook[1:])
+            assert all(not torch.equal(a, b) for a, b in zip(w_before, w_init))     # k-means overwrote the N(0,1) init
+    # the codebook is frozen after the k-means init: no gradient, Adam skips it (SURVEY section 0)
+    assert all(m.codebook.embedding.weight.grad is None for m in net.codebook[1:])
+    assert all(torch.equal(m.codebook.embedding.weight.detach(), w) for m, w in zip(net.codebook[1:], w_init))
+    assert all(p.grad is not None for p in net.enc.parameters())                     # STE + commitment reach the encoder
+    assert all(torch.isfinite(torch.tensor(losses)))
+
+
 def test_opcheck(dev):
     from vq_seg_b200 import ops
     x = torch.randn(2, 16, 50, device=dev).permute(0, 2, 1)
