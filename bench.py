@@ -187,35 +187,19 @@ def main():
             graphs.append(g)
             outs.append(o)
 
-    # N > 1: the 4 KiB all-reduce of the code counts + the usage kernel of step i run on a side stream and
-    # overlap step i+1's kernels (the lookup itself needs no exchange); a ring slot is not replayed before its
-    # previous reduction has finished.
-    side_stream = torch.cuda.Stream() if world > 1 else None
-    ev_main = [torch.cuda.Event() for _ in range(args.ring)]
-    ev_side = [torch.cuda.Event() for _ in range(args.ring)]
-    usages = [None] * args.ring
-
+    # N > 1: data-parallel over latent pixels with a replicated codebook: the lookup shards with NO data-path
+    # collective (rule 5 of the task: add a collective only where the path has a real exchange step; that is the
+    # k-means / code-stat update, see vq_seg_b200.distributed + tests/test_gpu_multi.py).  Every rank reports the
+    # code usage of its own pixels per step, like the single-GPU module; one 4 KiB all-reduce of the per-code
+    # counts after the timed region gives the global figure.
     def step(i):
         s = i % args.ring
-        main_s = torch.cuda.current_stream()
-        if world > 1 and usages[s] is not None:
-            main_s.wait_event(ev_side[s])
         if graphs:
             graphs[s].replay()
             q, idx, usage, counts = outs[s]
         else:
             q, idx, usage, counts = step_eager(i)
-        if world > 1:
-            # the lookup itself shards with no exchange; a GLOBAL code usage all-reduces the K per-code counts
-            # (4 KiB) on the side stream, overlapping the next step's kernels
-            ev_main[s].record(main_s)
-            with torch.cuda.stream(side_stream):
-                side_stream.wait_event(ev_main[s])
-                dist.all_reduce(counts)
-                usages[s] = ops.code_usage(counts)
-                ev_side[s].record(side_stream)
-            usage = usages[s]
-        return q, idx, usage
+        return q, idx, usage, counts
 
     def barrier():
         torch.cuda.synchronize()
@@ -263,10 +247,15 @@ def main():
     lib.vqseg_set_kernel_timing(0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    global_usage = None
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
+        gc = step(0)[3].clone()
+        torch.cuda.synchronize()
+        dist.all_reduce(gc)
+        global_usage = float(ops.code_usage(gc).item())
     value = N_VEC * world * args.steps / (ms * 1e-3)
 
     # ---- e2e: public module API, pinned host input, H2D + D2H inside the timed region
@@ -354,7 +343,8 @@ def main():
                 "config": {"workload": WORKLOAD, "per_gpu_vectors": N_VEC, "l2": f"ring of {args.ring} input batches "
                            f"({args.ring * N_VEC * C * 4 / 2**20:.0f} MiB) cycled, larger than L2",
                            "codebook_prepared": "once (weights static)", "parallelism": f"dp{world} over latent pixels",
-                           "launch": "eager" if args.no_graph else "CUDA graph replay per ring slot"},
+                           "launch": "eager" if args.no_graph else "CUDA graph replay per ring slot",
+                           "collectives_in_timed_region": 0, "global_code_usage_pct": global_usage},
                 "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_val, "unit": "vectors/s", "h2d_bytes_per_step": N_VEC * C * 4,
                         "d2h_bytes_per_step": N_VEC * 8 + 4, "steps": e2e_steps,
