@@ -40,7 +40,7 @@ def test_error_strings_and_sizes(native):
 
 
 def test_sass_is_blackwell_native():
-    """The shipped .so must contain tcgen05 / TMEM / bulk-copy SASS (UTCHMMA, LDTM, STTM, UBLKCP)."""
+    """The shipped .so must contain tcgen05 / TMEM / bulk-copy SASS (UTCHMMA, LDTM, UBLKCP)."""
     import shutil
     import subprocess
     from vq_seg_b200 import build
@@ -48,7 +48,7 @@ def test_sass_is_blackwell_native():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UBLKCP"):
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16" not in sass                       # no legacy mma.sync path
 
