@@ -210,6 +210,33 @@ def stage_bw():
             print(f"[bw2] {nm:30s} {bn:8s}: median {ts[2]:8.1f} us -> {buf.numel() * 4 / ts[2] / 1e6:6.2f} TB/s")
 
 
+def stage_bwbulk():
+    """bulk-copy (cp.async.bulk) loader vs register loaders: can one CTA per SM stream x at HBM rate?"""
+    from vq_seg_b200 import _native
+    L = _native.lib()
+    x = torch.randn(8 * 256 * 4096, device=dev)
+    big = torch.randn(1 << 28, device=dev)
+    sink = torch.zeros(4, device=dev)
+    junk = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for (pat, depth, nm) in [(0, 24, "registers LDG.128 depth 24"), (2, 24, "registers contiguous d24"), (82, 8, "registers contig 8 CTA/SM"),
+                             (3, 4, "bulk 512B strided, 4 st"), (3, 16, "bulk 512B strided, 16 st"),
+                             (4, 4, "bulk 8KiB linear, 4 st"), (4, 16, "bulk 8KiB linear, 16 st"),
+                             (5, 4, "bulk 512B, 4 warps, 4 st"), (5, 16, "bulk 512B, 4 warps, 16 st")]:
+        for buf, bn in ((big, "1 GiB"), (x, "33.5 MB")):
+            ts = []
+            for _ in range(7):
+                if bn != "1 GiB":
+                    junk.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                rc = L.vqseg_debug_load_bandwidth(buf.data_ptr(), buf.numel(), 4096, pat, depth, sink.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                b.record(); torch.cuda.synchronize()
+                assert rc == 0, rc
+                ts.append(a.elapsed_time(b) * 1e3)
+            ts.sort()
+            print(f"[bwbulk] {nm:28s} {bn:8s}: median {ts[3]:8.1f} us -> {buf.numel() * 4 / ts[3] / 1e6:6.2f} TB/s (best {ts[0]:.1f})")
+
+
 def stage_shapes():
     """filter / rescoring kernel times (CUDA events inside the C ABI) over the BASELINE shapes"""
     from vq_seg_b200 import _native
@@ -320,5 +347,5 @@ def stage_trace():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "shapes": stage_shapes, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "shapes": stage_shapes, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

@@ -2,6 +2,7 @@
 // producer-style access patterns under the same conditions as the tcgen05 kernels (8 loading warps per SM,
 // large shared-memory carve-out, data resident in L2 or not).  Exposed as vqseg_debug_load_bandwidth.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vqseg {
 
@@ -58,6 +59,78 @@ __global__ void __launch_bounds__(256) load_bw_kernel(const float* __restrict__ 
   if (acc == 12345.678f) sink[0] = acc;
 }
 
+// Pattern 3: the same tiles, fetched by the bulk-copy engine (cp.async.bulk, 512 B per copy = one 128-pixel row
+// segment, 16 segments = one 8 KiB stage) into a ring of STAGES stages; 8 consumer warps read each stage back
+// from shared memory.  One issuing warp, so the bytes in flight are set by the ring, not by registers.
+template <int STAGES, int VARIANT>
+__global__ void __launch_bounds__(384) load_bw_bulk_kernel(const float* __restrict__ x, long long n_floats,
+                                                           long long row_stride, float* __restrict__ sink) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  const uint32_t base = smem_u32(bulk_smem);
+  const uint32_t bar_full = base + STAGES * 8192, bar_empty = bar_full + 8 * STAGES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, VARIANT == 2 ? 4 : 1); mbar_init(bar_empty + 8 * s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long tiles_per_row = row_stride / 128;
+  const long long n_rows = n_floats / row_stride;
+  const long long n_tiles = tiles_per_row * (n_rows / 64);
+  float acc = 0.f;
+  long long q = 0;
+  if (warp >= 8) {
+    const int lw = warp - 8;                     // loader warp 0..3
+    if (VARIANT != 2 && lw != 0) return;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const long long rt = t / tiles_per_row, pt = t % tiles_per_row;
+      const float* tb = x + rt * 64 * row_stride + pt * 128;
+      for (int sub = 0; sub < 4; ++sub, ++q) {
+        const int s = (int)(q % STAGES);
+        const uint32_t use = (uint32_t)(q / STAGES);
+        mbar_wait(bar_empty + 8 * s, (use & 1) ^ 1);
+        if (VARIANT == 0) {
+          if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 8192);
+          __syncwarp();
+          if (lane < 16) bulk_g2s(base + s * 8192 + lane * 512, tb + (long long)(sub * 16 + lane) * row_stride, 512, bar_full + 8 * s);
+        } else if (VARIANT == 1) {               // linear: stage q of this CTA = 8 KiB contiguous
+          if (lane == 0) {
+            mbar_arrive_expect_tx(bar_full + 8 * s, 8192);
+            bulk_g2s(base + s * 8192, x + (t * 4 + sub) * 2048, 8192, bar_full + 8 * s);
+          }
+        } else {                                 // four loader warps, 4 segments each (barrier count 4)
+          if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, 2048);
+          __syncwarp();
+          if (lane < 4) bulk_g2s(base + s * 8192 + (lw * 4 + lane) * 512, tb + (long long)(sub * 16 + lw * 4 + lane) * row_stride, 512, bar_full + 8 * s);
+        }
+      }
+    }
+  } else {
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int sub = 0; sub < 4; ++sub, ++q) {
+        const int s = (int)(q % STAGES);
+        const uint32_t use = (uint32_t)(q / STAGES);
+        mbar_wait(bar_full + 8 * s, use & 1);
+        const float4* st = reinterpret_cast<const float4*>(bulk_smem + s * 8192);
+        const float4 v0 = st[threadIdx.x], v1 = st[threadIdx.x + 256];
+        acc += v0.x + v0.y + v0.z + v0.w + v1.x + v1.y + v1.z + v1.w;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+      }
+    }
+  }
+  if (acc == 12345.678f) sink[0] = acc;
+}
+template <int STAGES, int VARIANT>
+static int launch_bw_bulk(const float* x, long long n, long long rs, float* sink, cudaStream_t st) {
+  const int smem = STAGES * 8192 + 16 * STAGES + 128;
+  const int pad = 200 * 1024 > smem ? 200 * 1024 : smem;      // one CTA per SM, like the filter kernel
+  cudaFuncSetAttribute(load_bw_bulk_kernel<STAGES, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+  load_bw_bulk_kernel<STAGES, VARIANT><<<num_sms(), 384, pad, st>>>(x, n, rs, sink);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 static int g_bw_blocks_per_sm = 1;
 template <int P, int D>
 static int launch_bw(const float* x, long long n, long long rs, float* sink, cudaStream_t st) {
@@ -106,6 +179,12 @@ extern "C" int vqseg_debug_load_bandwidth(const float* x, int64_t n_floats, int6
   cudaStream_t st = (cudaStream_t)stream;
   g_bw_blocks_per_sm = pattern >= 10 ? pattern / 10 : 1;     // pattern 42 -> 4 blocks per SM, pattern 2
   pattern %= 10;
+  if (pattern == 3 && depth == 4) return launch_bw_bulk<4, 0>(x, n_floats, row_stride, sink, st);
+  if (pattern == 3 && depth == 16) return launch_bw_bulk<16, 0>(x, n_floats, row_stride, sink, st);
+  if (pattern == 4 && depth == 4) return launch_bw_bulk<4, 1>(x, n_floats, row_stride, sink, st);
+  if (pattern == 4 && depth == 16) return launch_bw_bulk<16, 1>(x, n_floats, row_stride, sink, st);
+  if (pattern == 5 && depth == 4) return launch_bw_bulk<4, 2>(x, n_floats, row_stride, sink, st);
+  if (pattern == 5 && depth == 16) return launch_bw_bulk<16, 2>(x, n_floats, row_stride, sink, st);
   if (pattern == 0 && depth == 8) return launch_bw<0, 8>(x, n_floats, row_stride, sink, st);
   if (pattern == 0 && depth == 24) return launch_bw<0, 24>(x, n_floats, row_stride, sink, st);
   if (pattern == 1 && depth == 12) return launch_bw<1, 12>(x, n_floats, row_stride, sink, st);
