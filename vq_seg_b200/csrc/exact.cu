@@ -88,19 +88,35 @@ __device__ __forceinline__ float chain_dist2_smem(const float* __restrict__ xs, 
     int j = blk;
     for (; j < dend && (j & 7); ++j) t = __fmaf_rn(xs[j], es[j], t);
     if (j + 8 <= dend) {
-      // the next 8 terms are fetched from smem while the current 8 dependent FMAs retire
-      float4 x0 = *reinterpret_cast<const float4*>(xs + j), x1 = *reinterpret_cast<const float4*>(xs + j + 4);
-      float4 e0 = *reinterpret_cast<const float4*>(es + j), e1 = *reinterpret_cast<const float4*>(es + j + 4);
-      for (; j + 16 <= dend; j += 8) {
-        const float4 nx0 = *reinterpret_cast<const float4*>(xs + j + 8), nx1 = *reinterpret_cast<const float4*>(xs + j + 12);
-        const float4 ne0 = *reinterpret_cast<const float4*>(es + j + 8), ne1 = *reinterpret_cast<const float4*>(es + j + 12);
-        t = __fmaf_rn(x0.x, e0.x, t); t = __fmaf_rn(x0.y, e0.y, t); t = __fmaf_rn(x0.z, e0.z, t); t = __fmaf_rn(x0.w, e0.w, t);
-        t = __fmaf_rn(x1.x, e1.x, t); t = __fmaf_rn(x1.y, e1.y, t); t = __fmaf_rn(x1.z, e1.z, t); t = __fmaf_rn(x1.w, e1.w, t);
-        x0 = nx0; x1 = nx1; e0 = ne0; e1 = ne1;
+      // the next 8 terms are fetched from smem while the current 8 dependent FMAs retire; two register sets
+      // alternate (16 terms per trip) so no register moves sit between the FMAs -- several warps share a
+      // scheduler here and the loop is issue-bound
+#define VQSEG_LD8(X0, X1, E0, E1, at)                                                     \
+      X0 = *reinterpret_cast<const float4*>(xs + (at)); X1 = *reinterpret_cast<const float4*>(xs + (at) + 4); \
+      E0 = *reinterpret_cast<const float4*>(es + (at)); E1 = *reinterpret_cast<const float4*>(es + (at) + 4)
+#define VQSEG_FMA8(X0, X1, E0, E1)                                                        \
+      t = __fmaf_rn(X0.x, E0.x, t); t = __fmaf_rn(X0.y, E0.y, t); t = __fmaf_rn(X0.z, E0.z, t); t = __fmaf_rn(X0.w, E0.w, t); \
+      t = __fmaf_rn(X1.x, E1.x, t); t = __fmaf_rn(X1.y, E1.y, t); t = __fmaf_rn(X1.z, E1.z, t); t = __fmaf_rn(X1.w, E1.w, t)
+      float4 ax0, ax1, ae0, ae1, bx0, bx1, be0, be1;
+      VQSEG_LD8(ax0, ax1, ae0, ae1, j);                       // A holds terms [j, j + 8)
+      while (j + 24 <= dend) {
+        VQSEG_LD8(bx0, bx1, be0, be1, j + 8);
+        VQSEG_FMA8(ax0, ax1, ae0, ae1);
+        VQSEG_LD8(ax0, ax1, ae0, ae1, j + 16);
+        VQSEG_FMA8(bx0, bx1, be0, be1);
+        j += 16;
       }
-      t = __fmaf_rn(x0.x, e0.x, t); t = __fmaf_rn(x0.y, e0.y, t); t = __fmaf_rn(x0.z, e0.z, t); t = __fmaf_rn(x0.w, e0.w, t);
-      t = __fmaf_rn(x1.x, e1.x, t); t = __fmaf_rn(x1.y, e1.y, t); t = __fmaf_rn(x1.z, e1.z, t); t = __fmaf_rn(x1.w, e1.w, t);
-      j += 8;
+      if (j + 16 <= dend) {
+        VQSEG_LD8(bx0, bx1, be0, be1, j + 8);
+        VQSEG_FMA8(ax0, ax1, ae0, ae1);
+        VQSEG_FMA8(bx0, bx1, be0, be1);
+        j += 16;
+      } else {
+        VQSEG_FMA8(ax0, ax1, ae0, ae1);
+        j += 8;
+      }
+#undef VQSEG_LD8
+#undef VQSEG_FMA8
     }
     for (; j < dend; ++j) t = __fmaf_rn(xs[j], es[j], t);
     float s = -2.f * t;

@@ -8,10 +8,11 @@ namespace vqseg {
 // =================================================================================================
 // gather + STE + commitment loss      (vq_img.py:169-170 one_hot+matmul, :236 STE, :239 mse_loss)
 // =================================================================================================
-// Pixel-contiguous layout (NCHW: sP == 1).  A block owns a 64-pixel x 64-dim tile: codebook rows
+// Pixel-contiguous layout (NCHW: sP == 1).  A block owns a 128-pixel x 32-dim tile: codebook rows
 // are read along d (coalesced 128 B per code row segment) into a padded smem tile, then x / q are
 // streamed along pixels (coalesced).  algorithmic bytes: 4ND (x) + 4ND (q) + 8N (idx) + 4KD (E).
-constexpr int kGTile = 64;       // dims per tile
+constexpr int kGTile = 32;       // dims per tile (128 x 32 tiles: 2048 blocks at C2, 8 resident per SM -> 1.7 waves;
+                                 // 128 x 64 tiles gave 1024 blocks on 888 slots, i.e. a second wave 15 % full)
 constexpr int kGPix = 128;       // pixels per tile
 
 __device__ __forceinline__ float round_fp16(float v) { return __half2float(__float2half_rn(v)); }
@@ -40,12 +41,12 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
   // phase 1: gather code row segments (256 B each), lanes along d
 #pragma unroll 2
   for (int p0 = warp; p0 < kGPix; p0 += 64) {           // 16 loads in flight per lane before the smem stores
-    float v[8][2];
+    float v[8][kGTile / 32];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const float* er = E + (long long)s_idx[p0 + 8 * u] * D + d0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < kGTile / 32; ++h) {
         const int d = lane + 32 * h;
         v[u][h] = (d0 + d < D) ? __ldg(er + d) : 0.f;
       }
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) tile[lane + 32 * h][p0 + 8 * u] = kAmp ? round_fp16(v[u][h]) : v[u][h];
+      for (int h = 0; h < kGTile / 32; ++h) tile[lane + 32 * h][p0 + 8 * u] = kAmp ? round_fp16(v[u][h]) : v[u][h];
   }
   __syncthreads();
   // phase 2: stream pixels; lane owns 4 consecutive pixels, warps take the dims round-robin
