@@ -173,6 +173,27 @@ int    vqseg_l2norm_rows_f32(const float* x, int64_t B, int64_t P, int64_t D,
 int    vqseg_assign_cosine_f32(const float* xn, int64_t N, int64_t D, const float* E, int64_t K,
                                int64_t* idx_out, int64_t* counts_out, void* stream);
 
+/* ---- VQ segmentation head (models/modules/vq_segmentation_head.py) ------------------------------
+ * The head classifies every decoder pixel by its distance to K class prototypes and RETURNS the distance map.
+ * dist_out[b, p, k] (element strides oB, oP, oK; (K*P, 1, P) gives the (B, K, H, W) score layout directly):
+ *   cosine == 0: torch.cdist(flatten_x, weight, p=2)  (EuclideanSegHead.forward :167), bit-equal to ATen's CPU
+ *                result; idx = first argmin (:168);
+ *   cosine != 0: einsum('n d, e d -> n e') over rows the caller has already l2-normalised
+ *                (CosinesimSegHead.forward :104); idx = first argmax (:107).
+ * counts_out (nullable) = bincount(idx, K) (:174), zeroed by the call.  K <= 32, D <= 382, K*D small enough for
+ * shared memory (VQSEG_EUNSUPPORTED otherwise: a segmentation head has K = classes, D = last decoder width). */
+int    vqseg_dist_map_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                          const float* E, int64_t K, int cosine,
+                          float* dist_out, int64_t oB, int64_t oP, int64_t oK,
+                          int64_t* idx_out, int64_t* counts_out, void* stream);
+/* backward of the Euclidean map (autograd of torch.cdist, p=2): with w = g / dist (0 where dist == 0),
+ *   gx[n,:] = sum_k w[n,k] (x[n,:] - e_k),   gE[k,:] = sum_n w[n,k] (e_k - x[n,:])   (gE zeroed by the call;
+ * accumulated with fp32 atomics: sums within 1e-5 relative, not bit-reproducible).  g and dist share strides. */
+int    vqseg_dist_map_bwd_f32(const float* g, const float* dist, int64_t oB, int64_t oP, int64_t oK,
+                              const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                              const float* E, int64_t K,
+                              float* gx_out, int64_t gxB, int64_t gxP, int64_t gxD, float* gE_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,3 +28,17 @@ def load_reference_vq_img():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference_seghead():
+    """models/modules/vq_segmentation_head.py of the live reference (needs only torch + einops)."""
+    root = reference_root()
+    if root is None:
+        return None
+    path = os.path.join(root, "models", "modules", "vq_segmentation_head.py")
+    if not os.path.isfile(path):
+        return None
+    spec = importlib.util.spec_from_file_location("ref_vq_segmentation_head", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -237,6 +237,72 @@ def stage_bwbulk():
             print(f"[bwbulk] {nm:28s} {bn:8s}: median {ts[3]:8.1f} us -> {buf.numel() * 4 / ts[3] / 1e6:6.2f} TB/s (best {ts[0]:.1f})")
 
 
+def stage_seghead():
+    """VQ segmentation head at the reference's decoder-output size (resnet50 U-Net, 4 x 32 x 256 x 256, 3 classes):
+    map kernel and its backward by CUDA events, module forward / forward+backward against the same module written
+    with torch ops (the oracle restatement moved to the GPU)."""
+    import vq_seg_b200 as V
+    from oracle.seghead_oracle import OracleVQSegmentationHead
+    b, c, h, w, k = 4, 32, 256, 256, 3
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xs = [torch.relu(torch.randn(b, c, h, w, generator=g, device=dev)) for _ in range(6)]     # 6 x 33.5 MB > L2
+    e = torch.rand(k, c, generator=g, device=dev)
+
+    def timeit(fn, n=30):
+        for i in range(3):
+            fn(xs[i % len(xs)])
+        torch.cuda.synchronize()
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(xs[i % len(xs)])
+        bb.record(); torch.cuda.synchronize()
+        return a.elapsed_time(bb) * 1e3 / n
+
+    def timeit_graph(fn, n=12):
+        """n calls (cycling the inputs) captured into one CUDA graph: no host time between the launches"""
+        for i in range(3):
+            fn(xs[i % len(xs)])
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(n):
+                fn(xs[i % len(xs)])
+        gr.replay(); torch.cuda.synchronize()
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            gr.replay()
+        bb.record(); torch.cuda.synchronize()
+        return a.elapsed_time(bb) * 1e3 / (5 * n)
+
+    view_ = lambda x: x.reshape(b, c, h * w).permute(0, 2, 1)
+    t_map = timeit_graph(lambda x: ops._dist_map_impl(view_(x), e, False))
+    dist, idx, counts = ops._dist_map_impl(view_(xs[0]), e, False)
+    gd = torch.randn_like(dist)
+    t_bwd = timeit_graph(lambda x: ops._dist_map_bwd_impl(gd, dist, view_(x), e))
+    n = b * h * w
+    by_f = 4 * n * c + 4 * n * k + 8 * n
+    by_b = 4 * n * c * 2 + 8 * n * k
+    print(f"[seghead] map kernel   : {t_map:7.1f} us  ({by_f / t_map / 1e6:5.2f} TB/s of {by_f / 1e6:.1f} MB algorithmic)")
+    print(f"[seghead] map backward : {t_bwd:7.1f} us  ({by_b / t_bwd / 1e6:5.2f} TB/s of {by_b / 1e6:.1f} MB algorithmic)")
+    ours = V.VQSegmentationHead(dim=c, num_embeddings=k).to(dev)
+    ref = OracleVQSegmentationHead(dim=c, num_embeddings=k).to(dev)
+    ours.codebook.embedding.weight.data.copy_(e); ref.embedding.weight.data.copy_(e)
+    for nm, m in (("vq_seg_b200", ours), ("torch ops (oracle module on the GPU)", ref)):
+        m.eval()
+        with torch.no_grad():
+            t_eval = timeit(lambda x: m(x))
+        m.train()
+
+        def step(x):
+            xg = x.detach().requires_grad_(True)
+            q, score, i_, loss, u = m(xg)
+            (score.sum() + q.sum() + loss.sum()).backward()
+        t_train = timeit(step, n=10)
+        print(f"[seghead] {nm:38s}: eval forward {t_eval:8.1f} us, train forward+backward {t_train:8.1f} us")
+
+
 def stage_shapes():
     """filter / rescoring kernel times (CUDA events inside the C ABI) over the BASELINE shapes"""
     from vq_seg_b200 import _native
@@ -347,5 +413,5 @@ def stage_trace():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "shapes": stage_shapes, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "seghead": stage_seghead, "shapes": stage_shapes, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

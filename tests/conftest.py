@@ -20,6 +20,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_seghead():
+    path = os.path.join(ROOT, "tests", "golden", "golden_seghead_v1.pt")
+    return torch.load(path, weights_only=False)
+
+
+@pytest.fixture(scope="session")
 def ref_vq():
     """The live reference vq_img module, or None when /root/reference is absent (GPU box)."""
     from oracle.ref_loader import load_reference_vq_img

@@ -142,3 +142,29 @@ def kmeans_case(name):
 KMEANS_CASES = ["km_small", "km_c1_l5", "km_one_iter", "km_n_lt_k", "km_cosine"]
 COSINE_CASES = {"cos_small": (lambda: _randn_case(70, 2, 64, 16, 16, 48)),
                 "cos_c2ish": (lambda: _relu_case(71, 2, 256, 32, 32, 512))}
+
+
+# VQ segmentation head: (seed, B, C=dim, H, W, K=classes, distance).  Decoder features are
+# post-ReLU (non-negative); prototypes are perturbed feature rows.  "sh_dup" has a pixel equal to a prototype
+# (distance ~0: catastrophic cancellation in the augmented form) and two identical prototypes (tie -> lower index).
+# "sh_odd" is the single-image case (B = 1): there ATen skips cdist's contiguous copy and sums |x|^2 over the
+# strided dim in its "outer" order (which depends on the host thread partition); distances then differ from the
+# B >= 2 arithmetic by an ulp or two -- see DESIGN.md "known divergences".
+def _seghead_case(seed, b, c, h, w, k, exact_hit=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.relu(torch.randn(b, c, h, w, generator=g)) + 0.01
+    flat = x.permute(0, 2, 3, 1).reshape(-1, c)
+    e = flat[torch.randperm(flat.shape[0], generator=g)[:k]] + 0.3 * torch.randn(k, c, generator=g)
+    if exact_hit:
+        e[1] = flat[7]
+        e[k - 1] = e[0]
+    return x, e.contiguous()
+
+
+SEGHEAD_CASES = {
+    "sh_c3_d32": (lambda: _seghead_case(80, 2, 32, 32, 32, 3), "euclidean"),
+    "sh_odd": (lambda: _seghead_case(81, 1, 16, 24, 40, 5), "euclidean"),
+    "sh_k19_d64": (lambda: _seghead_case(82, 2, 64, 16, 16, 19), "euclidean"),
+    "sh_dup": (lambda: _seghead_case(83, 2, 24, 8, 12, 4, exact_hit=True), "euclidean"),
+    "sh_cos": (lambda: _seghead_case(84, 2, 32, 16, 16, 3), "cosine"),
+}

@@ -114,3 +114,22 @@ def test_custom_ops_registered_with_fake_impls():
     assert idx.shape == (2, 9) and idx.dtype == torch.int64 and counts.shape == (8,)
     q, mse = torch.ops.vqseg.gather_ste(x, e, idx, 1)
     assert q.shape == (2, 9, 16) and q.stride() == (144, 1, 9) and mse.shape == (1,)
+
+
+def test_seghead_module_surface():
+    """VQSegmentationHead: reference kwargs / defaults / state_dict key, KeyError on an unknown distance, loud
+    error (no CPU fallback) on a CPU tensor."""
+    import inspect
+    import torch
+    import vq_seg_b200 as V
+    sig = inspect.signature(V.VQSegmentationHead.__init__)
+    assert list(sig.parameters)[1:] == ["dim", "num_embeddings", "embedding_dim", "decay", "eps", "kmeans_init",
+                                        "kmeans_iters", "distance", "commitment_weight", "num_codebook", "activation"]
+    m = V.VQSegmentationHead(dim=16, num_embeddings=3)
+    assert list(m.state_dict()) == ["codebook.embedding.weight"] and m.codebook.initted
+    assert m.codebook.embedding.weight.abs().max().item() <= 1 / 3
+    assert not V.VQSegmentationHead(dim=16, num_embeddings=3, kmeans_init=True).codebook.initted
+    with pytest.raises(KeyError):
+        V.VQSegmentationHead(dim=16, num_embeddings=3, distance="manhattan")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 16, 4, 4))

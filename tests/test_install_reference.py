@@ -63,6 +63,20 @@ def test_reference_model_builds_with_b200_codebooks():
                                                     vq_cfg=EasyDict(num_embeddings=[0, 0, 512, 512, 512], distance="euclidean",
                                                                     kmeans_init=True), encoder_weights=None)
         assert sum(isinstance(m, V.VectorQuantizer) for m in v2.codebook) == 3
+        # the VQ segmentation head and the other copies of kmeans
+        import models.modules.prototype as ref_proto
+        import models.modules.segmentation_head as ref_sh
+        import models.modules.vq_segmentation_head as ref_vsh
+        patched = V.install(kmeans=True)
+        assert "models.modules.vq_segmentation_head:VQSegmentationHead" in patched
+        assert "models.networks.vqseghead.net:VQSegmentationHead" in patched
+        assert ref_proto.kmeans is V.kmeans and ref_sh.kmeans is V.kmeans and ref_vsh.kmeans is V.kmeans
+        net = ref_networks.network_dict["vqsegheadnet"](encoder_name="resnet50", num_classes=3, encoder_weights=None,
+                                                        vq_cfg=EasyDict(num_embeddings=[0, 0, 512, 512, 512],
+                                                                        distance="euclidean", kmeans_init=True))
+        assert isinstance(net.segmentation_head, V.VQSegmentationHead)
+        assert tuple(net.segmentation_head.codebook.embedding.weight.shape) == (3, 32)
+        assert [k for k in net.state_dict() if k.startswith("segmentation_head.")] == ["segmentation_head.codebook.embedding.weight"]
     finally:
         added = set(sys.modules) - before
         for k in added:

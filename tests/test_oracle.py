@@ -127,3 +127,54 @@ def test_make_vq_module_port():
         O.oracle_make_vq_module({"num_embeddings": [-1]}, [3, 64], 1)
     with pytest.raises(TypeError):
         O.oracle_make_vq_module({"num_embeddings": 1.5}, [3, 64], 1)
+
+
+@pytest.mark.parametrize("name", list(cases.SEGHEAD_CASES))
+def test_seghead_oracle_matches_golden(golden_seghead, name):
+    """The restated segmentation head (oracle/seghead_oracle.py) against the live reference's outputs and
+    gradients: same torch build -> bit-equal."""
+    from oracle.seghead_oracle import OracleVQSegmentationHead
+    build, distance = cases.SEGHEAD_CASES[name]
+    x, e = build()
+    rec = golden_seghead["seghead"][name]
+    assert cases.sha(x) == rec["x_sha"] and cases.sha(e) == rec["e_sha"]
+    m = OracleVQSegmentationHead(dim=x.shape[1], num_embeddings=e.shape[0], distance=distance)
+    m.embedding.weight.data.copy_(e)
+    m.train()
+    xg = x.clone().requires_grad_(True)
+    quantize, score, idx, loss, usage = m(xg)
+    g = torch.Generator().manual_seed(4242)
+    gs = torch.randn(score.shape, generator=g)
+    gq = torch.randn(quantize.shape, generator=g)
+    ((score * gs).sum() + (quantize * gq).sum() + 1.5 * loss.sum()).backward()
+    assert torch.equal(idx.to(torch.int32), rec["idx"])
+    assert torch.equal(quantize.detach(), rec["quantize"]) and torch.equal(score.detach(), rec["score"])
+    assert torch.equal(loss.detach(), rec["loss"]) and torch.equal(usage, rec["usage"])
+    assert torch.equal(xg.grad, rec["gx"]) and torch.equal(m.embedding.weight.grad, rec["gw"])
+    assert torch.isfinite(rec["gx"]).all() and torch.isfinite(rec["gw"]).all()
+    m.eval()
+    with torch.no_grad():
+        q2, s2, i2, l2, u2 = m(x)
+    assert torch.equal(q2, rec["quantize_eval"]) and torch.equal(s2, rec["score_eval"]) and l2.item() == 0.0
+
+
+def test_live_reference_seghead_kmeans_init():
+    """First training forward with kmeans_init=True: the oracle and the live reference draw the same start rows
+    from the same RNG state and must agree bit for bit afterwards."""
+    from oracle.ref_loader import load_reference_seghead
+    from oracle.seghead_oracle import OracleVQSegmentationHead
+    R = load_reference_seghead()
+    if R is None:
+        pytest.skip("/root/reference not present (GPU box): golden vectors are the pin there")
+    x, _ = cases.SEGHEAD_CASES["sh_c3_d32"][0]()
+    for distance in ("euclidean", "cosine"):
+        torch.manual_seed(5)
+        ref = R.VQSegmentationHead(dim=32, num_embeddings=3, kmeans_init=True, kmeans_iters=4, distance=distance)
+        torch.manual_seed(5)
+        ora = OracleVQSegmentationHead(dim=32, num_embeddings=3, kmeans_init=True, kmeans_iters=4, distance=distance)
+        ora.embedding.weight.data.copy_(ref.codebook.embedding.weight.data)
+        torch.manual_seed(6); ref.train(); a = ref(x)
+        torch.manual_seed(6); ora.train(); b = ora(x)
+        assert torch.equal(ref.codebook.embedding.weight, ora.embedding.weight)
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)

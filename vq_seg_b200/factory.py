@@ -48,17 +48,38 @@ class Identity(nn.Module):
 # module globals of the reference that bind the class by name
 _PATCH_POINTS = ["vector_quantizer", "vector_quantizer.vq_img", "models.networks.unet.net",
                  "models.networks.vqvaev2.net"]
+# the segmentation head class and the three other copies of `kmeans` (same signature as
+# vq_img.py:29; prototype.py:36, segmentation_head.py:42, vq_segmentation_head.py:29)
+_SEGHEAD_PATCH_POINTS = ["models.modules.vq_segmentation_head", "models.networks.vqseghead.net"]
+_KMEANS_PATCH_POINTS = ["vector_quantizer.vq_img", "models.modules.prototype", "models.modules.segmentation_head",
+                        "models.modules.vq_segmentation_head"]
 
 
-def install(verbose=False):
+def install(verbose=False, seghead=True, kmeans=False):
     """Monkeypatch every already-imported reference module that binds `VectorQuantizer` by name, so
-    `make_model(cfg)` of the unmodified reference builds B200 codebooks.  Returns the patched names."""
+    `make_model(cfg)` of the unmodified reference builds B200 codebooks.  `seghead` also swaps the VQ segmentation
+    head class; `kmeans=True` replaces the reference's four copies of `kmeans` (prototype / segmentation-head
+    initialisation) with the B200 one -- GPU tensors only from then on.  Returns the patched names."""
     done = []
     for name in _PATCH_POINTS:
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "VectorQuantizer"):
             setattr(mod, "VectorQuantizer", VectorQuantizer)
             done.append(name)
+    if seghead:
+        from .vq_segmentation_head import VQSegmentationHead
+        for name in _SEGHEAD_PATCH_POINTS:
+            mod = sys.modules.get(name)
+            if mod is not None and hasattr(mod, "VQSegmentationHead"):
+                setattr(mod, "VQSegmentationHead", VQSegmentationHead)
+                done.append(name + ":VQSegmentationHead")
+    if kmeans:
+        from .vq_img import kmeans as b200_kmeans
+        for name in _KMEANS_PATCH_POINTS:
+            mod = sys.modules.get(name)
+            if mod is not None and hasattr(mod, "kmeans"):
+                setattr(mod, "kmeans", b200_kmeans)
+                done.append(name + ":kmeans")
     if verbose:
         print("vq_seg_b200.install: patched", done)
     return done

@@ -356,6 +356,103 @@ def _(xn, codebook):
 
 
 # -------------------------------------------------------------------------------------------------
+# distance map of the VQ segmentation head (models/modules/vq_segmentation_head.py:167-176 / :104-111)
+def _dist_map_impl(x: torch.Tensor, codebook: torch.Tensor, cosine: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x (B, P, D) view (any strides; for cosine: rows already l2-normalised), codebook (K, D).
+    Returns (dist (B, P, K) fp32 laid out as (B, K, P) in memory, idx (B, P) int64, counts (K,) int64)."""
+    _require_cuda(x, codebook)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    cb = codebook.detach()
+    if cb.dtype != torch.float32 or not cb.is_contiguous():
+        cb = cb.contiguous().float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    k = cb.shape[0]
+    if cb.shape[1] != d:
+        raise RuntimeError(f"X1 and X2 must have the same number of columns. X1: {d} X2: {cb.shape[1]}")
+    dev = x.device
+    dist = torch.empty_strided((b, p, k), (k * p, 1, p), dtype=torch.float32, device=dev)
+    idx = torch.empty((b, p), dtype=torch.int64, device=dev)
+    counts = torch.empty(k, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(L.vqseg_dist_map_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k, 1 if cosine else 0,
+                                           dist.data_ptr(), dist.stride(0), dist.stride(1), dist.stride(2),
+                                           idx.data_ptr(), counts.data_ptr(), _stream()), "dist_map")
+    return dist, idx, counts
+
+
+dist_map = torch.library.custom_op("vqseg::dist_map", mutates_args=())(_dist_map_impl)
+
+
+@dist_map.register_fake
+def _(x, codebook, cosine=False):
+    b, p, d = x.shape
+    k = codebook.shape[0]
+    return (torch.empty_strided((b, p, k), (k * p, 1, p), dtype=torch.float32, device=x.device),
+            x.new_empty((b, p), dtype=torch.int64), x.new_empty((k,), dtype=torch.int64))
+
+
+def _dist_map_bwd_impl(grad: torch.Tensor, dist: torch.Tensor, x: torch.Tensor,
+                       codebook: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Backward of the Euclidean map (torch.cdist p=2): (gx with x's (B, P, D) shape in NCHW memory order, gE (K, D))."""
+    _require_cuda(grad, dist, x, codebook)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    cb = codebook.detach()
+    if cb.dtype != torch.float32 or not cb.is_contiguous():
+        cb = cb.contiguous().float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    k = cb.shape[0]
+    g = grad.float()
+    if g.stride() != dist.stride():
+        g2 = torch.empty_strided(dist.shape, dist.stride(), dtype=torch.float32, device=dist.device)
+        g2.copy_(g)
+        g = g2
+    gx = torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=x.device)
+    ge = torch.empty((k, d), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_dist_map_bwd_f32(g.data_ptr(), dist.data_ptr(), dist.stride(0), dist.stride(1), dist.stride(2),
+                                               x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
+                                               gx.data_ptr(), gx.stride(0), gx.stride(1), gx.stride(2), ge.data_ptr(),
+                                               _stream()), "dist_map_bwd")
+    return gx, ge
+
+
+dist_map_bwd = torch.library.custom_op("vqseg::dist_map_bwd", mutates_args=())(_dist_map_bwd_impl)
+
+
+@dist_map_bwd.register_fake
+def _(grad, dist, x, codebook):
+    b, p, d = x.shape
+    return (torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=x.device),
+            codebook.new_empty(codebook.shape, dtype=torch.float32))
+
+
+class _EuclideanDistMap(torch.autograd.Function):
+    """torch.cdist(x, weight, p=2) + argmin + bincount with the map as a differentiable output
+    (vq_segmentation_head.py:167-174): gradients to the features AND to the prototypes."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        dist, idx, counts = (_dist_map_impl if _fast() else dist_map)(x, weight, False)
+        ctx.save_for_backward(x, weight, dist)
+        ctx.mark_non_differentiable(idx, counts)
+        return dist, idx, counts
+
+    @staticmethod
+    def backward(ctx, g_dist, g_idx, g_counts):
+        x, weight, dist = ctx.saved_tensors
+        gx, ge = (_dist_map_bwd_impl if _fast() else dist_map_bwd)(g_dist, dist, x, weight)
+        return (gx if ctx.needs_input_grad[0] else None), (ge if ctx.needs_input_grad[1] else None)
+
+
+def euclidean_dist_map(x, weight):
+    return _EuclideanDistMap.apply(x, weight)
+
+
+# -------------------------------------------------------------------------------------------------
 def _vq_forward_counts(x, codebook, blob, mode, algo=0):
     """_vq_forward_impl plus the per-code counts (for a global, all-reduced code usage)."""
     return _vq_forward_raw(x, codebook, blob, mode, algo)
