@@ -178,3 +178,33 @@ def test_live_reference_seghead_kmeans_init():
         assert torch.equal(ref.codebook.embedding.weight, ora.embedding.weight)
         for u, v in zip(a, b):
             assert torch.equal(u, v)
+
+
+def test_cpu_sqrt_is_not_correctly_rounded():
+    """ATen's CPU sqrt (MKL VML in this build) is 1 ulp off on a fraction of a percent of inputs, so
+    distances can only be pinned to 1 ulp; the kernels use the IEEE sqrt."""
+    g = torch.Generator().manual_seed(0)
+    c = torch.rand(200_000, generator=g) * 60 + 1
+    exact = c.double().sqrt().float()
+    live = c.sqrt()
+    frac = (live != exact).float().mean().item()
+    assert frac < 0.02                                             # a correctly rounded build gives 0: also fine
+    assert ((live - exact).abs() <= torch.finfo(torch.float32).eps * exact).all()
+
+
+def test_single_image_batch_takes_the_strided_norm_order():
+    """with B == 1 cdist works on the permuted NCHW view itself and sums |x|^2 over the strided dim in
+    another order than for B >= 2 (where it copies first).  The oracle and the kernels use the B >= 2 arithmetic for
+    every B: distances within a few ulp, same indices on these inputs."""
+    g = torch.Generator().manual_seed(1)
+    for (b, c, h, w, k) in [(1, 256, 32, 32, 512), (1, 64, 16, 16, 100), (2, 40, 9, 9, 33)]:
+        x = torch.randn(b, c, h, w, generator=g)
+        e = torch.randn(k, c, generator=g)
+        xv = x.reshape(b, c, h * w).permute(0, 2, 1)
+        live = torch.cdist(xv, e, p=2)
+        ours = O.euclidean_dist(xv, e)
+        assert torch.equal(ours, torch.cdist(xv.contiguous(), e, p=2))
+        if b >= 2:
+            assert torch.equal(live, ours)
+        assert ((live - ours).abs() <= 4 * torch.finfo(torch.float32).eps * ours.abs().clamp_min(1e-3)).all()
+        assert torch.equal(live.argmin(-1), ours.argmin(-1))
