@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvqseg.so")
 SOURCES = ["api.cu", "exact.cu", "assign_tc.cu", "assign_tc2.cu", "ops.cu", "seghead.cu", "debug_bw.cu"]
-HEADERS = ["common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "vqseg.h")]
+HEADERS = ["common.cuh", "tc_common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "vqseg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

@@ -1,55 +1,9 @@
 // C ABI entry points for codebook preparation and nearest-code assignment (see include/vqseg.h).
 #include "common.cuh"
+#include "kernels.cuh"
 #include <string.h>
 
 namespace vqseg {
-// exact.cu
-struct ExactArgs {
-  Rows x;
-  const float* E; int K;
-  const float* enorm;
-  int kblock;
-  const int* work_rows; const int* work_count;
-  const int* cand_idx; const int* cand_cnt; int cand_cap;
-  long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
-  int stage_e;
-  long long* trace;
-  int* done_blocks;
-  float* usage_out;
-};
-int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st);
-int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st);
-// assign_tc.cu
-struct TcArgs {
-  Rows x;
-  const unsigned char* blob;
-  long long n_rows;
-  int n_tiles, n_cc, n_dc;
-  int K;
-  float tau;
-  long long* idx_out; unsigned long long* counts_out; long long code_base;
-  int force_rescore;
-  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
-  long long* trace;
-};
-int launch_pack(const float* E, int K, int D, unsigned char* blob, cudaStream_t st);
-// assign_tc2.cu
-struct Tc2Args {
-  Rows x;
-  const unsigned char* blob;
-  long long n_rows;
-  int n_ptiles, n_cc, n_dc;
-  int K, K_pad;
-  unsigned long long off_image, off_aug, off_enorm;
-  float tau;
-  long long* idx_out; unsigned long long* counts_out; long long code_base;
-  int force_rescore;
-  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
-  long long* trace;
-};
-bool tc2_supported(int n_cc, int n_dc);
-int launch_assign_tc2(const Tc2Args& a, cudaStream_t st);
-int launch_assign_tc(const TcArgs& a, cudaStream_t st);
 constexpr int kCandCapHost = 8;
 
 __global__ void blob_init_kernel(BlobHeader* h, int K, int D, int K_pad, int D_pad, unsigned long long off_enorm,

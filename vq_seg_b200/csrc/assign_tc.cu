@@ -20,6 +20,7 @@
 // Pipelines: smem full/empty mbarriers (3 stages), TMEM full/empty (2 x 256 columns), limb-tile full/empty (2);
 // setmaxnreg moves the register budget to the producers (144 / 72 / 40).
 #include "tc_common.cuh"
+#include "kernels.cuh"
 
 namespace vqseg {
 
@@ -51,19 +52,6 @@ struct TcSmem {
 };
 static_assert(TcSmem::total <= 232448, "smem budget");
 
-struct TcArgs {
-  Rows x;
-  const unsigned char* blob;      // prepared codebook
-  long long n_rows;
-  int n_tiles, n_cc, n_dc;        // tiles of 128 rows, code chunks of 256, dim chunks of 64
-  int K;
-  float tau;                      // relative error bound of one fp16 x fp16 score vs the exact fp32 scorer
-  // outputs
-  long long* idx_out; unsigned long long* counts_out; long long code_base;
-  int force_rescore;              // 1 -> every row goes to the exact pass (sharded mode needs exact distances)
-  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
-  long long* trace;               // optional (dev tool): [cta][role][256] clock64 stamps
-};
 
 #define VQ_TRACE(role, slot) do { if (a.trace && lane == 0 && (slot) < 256) \
     a.trace[((long long)blockIdx.x * 4 + (role)) * 256 + (slot)] = clock64(); } while (0)

@@ -18,6 +18,7 @@
 // each), 16 MMA issuer (leader CTA) + TMEM alloc, 17 codebook loader (cp.async.bulk), 18-19 idle (they
 // only donate registers).
 #include "tc_common.cuh"
+#include "kernels.cuh"
 
 namespace vqseg {
 
@@ -46,19 +47,6 @@ struct Tc2Smem {
 };
 static_assert(Tc2Smem::total <= 232448, "smem budget");
 
-struct Tc2Args {
-  Rows x;
-  const unsigned char* blob;
-  long long n_rows;
-  int n_ptiles, n_cc, n_dc;       // pair tiles of 256 rows, code chunks of 256, dim chunks of 64
-  int K, K_pad;
-  unsigned long long off_image, off_aug, off_enorm;
-  float tau;
-  long long* idx_out; unsigned long long* counts_out; long long code_base;
-  int force_rescore;
-  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
-  long long* trace;
-};
 
 #define VQ2_TRACE(role, slot) do { if (a.trace && lane == 0 && (slot) < 256) \
     a.trace[((long long)blockIdx.x * 4 + (role)) * 256 + (slot)] = clock64(); } while (0)
@@ -103,7 +91,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
   const int n_pairs = (int)gridDim.x >> 1;
   const int pair = (int)blockIdx.x >> 1;
   const int my_tiles = a.n_ptiles > pair ? (a.n_ptiles - 1 - pair) / n_pairs + 1 : 0;
-  const int my_units = my_tiles * a.n_cc;
   const uint32_t lead_full = mapa_u32(bar_full, 0);
   const uint32_t lead_tempty = mapa_u32(bar_tempty, 0);
 

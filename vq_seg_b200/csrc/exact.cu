@@ -15,6 +15,7 @@
 // exact path over all K codes, (b) the rescoring pass over the short-list written by the tcgen05
 // filter (assign_tc.cu).  Ties: the lowest code index wins, like torch.argmin.
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace vqseg {
 
@@ -187,20 +188,6 @@ __device__ __forceinline__ void lexmin(float& d, int& k, float d2, int k2) {
   if (d2 < d || (d2 == d && k2 < k)) { d = d2; k = k2; }
 }
 
-struct ExactArgs {
-  Rows x;
-  const float* E; int K;
-  const float* enorm;
-  int kblock;
-  // candidate mode (null -> all rows x all codes)
-  const int* work_rows; const int* work_count;        // flagged row ids, device counter
-  const int* cand_idx; const int* cand_cnt; int cand_cap;   // per row: up to cand_cap codes; cnt > cap => all codes
-  long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
-  int stage_e;
-  long long* trace;     // dev tool: [0] min start ns, [1] max end ns, [2..] per-phase clock sums
-  int* done_blocks;     // ticket counter (zeroed by the host) for the fused usage epilogue
-  float* usage_out;     // nullable: the last block to finish writes 100 * (#counts == 0) / K   (vq_img.py:174-175)
-};
 
 constexpr int kExactWarps = 8;
 
