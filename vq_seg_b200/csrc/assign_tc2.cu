@@ -358,6 +358,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
       // at once, and the tile's two accumulators (TMEM columns 0-255 / 256-511) complete together.
       // n_cc == 1: the two TMEM halves alternate between tiles instead.
       for (int tt = 0; tt < my_tiles; ++tt) {
+        if (a.n_cc == 2 && tt == my_tiles - 1) {
+          // LAST tile, codes-outer: nothing waits for its A slots any more, so code chunk 0 is multiplied against
+          // all dim chunks first and its accumulator is handed to the epilogue while chunk 1's MMAs still run
+          // (dims-outer would deliver both accumulators together and leave the tensor pipe idle during the drain).
+          for (int cc = 0; cc < 2; ++cc) {
+            VQ2_TRACE(1, 128 + 2 * (tt * a.n_cc + cc));
+            mbar_wait(bar_tempty + 8 * cc, ((uint32_t)tt & 1) ^ 1);
+            VQ2_TRACE(1, 128 + 2 * (tt * a.n_cc + cc) + 1);
+            if (tt == 0) mbar_wait(bar_bready + 8 * cc, 0);
+            tc_fence_after();
+            for (int dc = 0; dc < a.n_dc; ++dc) {
+              if (cc == 0) {
+                VQ2_TRACE(1, 2 * (tt * a.n_dc + dc));
+                mbar_wait(bar_full + 8 * dc, (uint32_t)tt & 1);
+                VQ2_TRACE(1, 2 * (tt * a.n_dc + dc) + 1);
+                tc_fence_after();
+              }
+              if (lane == 0) {
+                const uint64_t ad = make_desc(sbase + Tc2Smem::off_a + dc * kTileBytes);
+                const uint64_t bd = make_desc(sbase + Tc2Smem::off_b + (cc * a.n_dc + dc) * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kDChunk / 16; ++k)
+                  tc_mma_f16_2cta(tmem_base + cc * 256, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), k2Idesc,
+                                  (dc | k) ? 1u : 0u);
+                if (cc == 1) tc_commit_2cta(bar_empty + 8 * dc);
+              }
+              __syncwarp();
+            }
+            if (lane == 0) {
+              const uint64_t baug = make_desc_noswz(sbase + Tc2Smem::off_baug + cc * k2AugBytes, 128, 256);
+              tc_mma_f16_2cta(tmem_base + cc * 256, aaug, baug, k2Idesc, 1u);   // + s |e_k|^2
+              tc_commit_2cta(bar_tfull + 8 * cc);
+            }
+            __syncwarp();
+          }
+          continue;
+        }
         for (int cc = 0; cc < a.n_cc; ++cc) {
           const int buf = a.n_cc == 1 ? (tt & 1) : cc;
           const uint32_t use = a.n_cc == 1 ? (uint32_t)(tt >> 1) : (uint32_t)tt;
