@@ -349,7 +349,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "vectors/s", "h2d_bytes_per_step": N_VEC * C * 4,
                         "d2h_bytes_per_step": N_VEC * 8 + 4, "steps": e2e_steps,
                         "how": "VectorQuantizer.forward (eval) per step; H2D of step i+1 on a copy stream overlaps step i"},
-                "gpu_launches": 3 * args.steps, "clocks": sampler.summary()}
+                "gpu_launches": 4 * args.steps,   # per step: zeroing, tcgen05 filter, exact pass, gather
+                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -14,6 +14,13 @@ __global__ void blob_init_kernel(BlobHeader* h, int K, int D, int K_pad, int D_p
   h->off_enorm = off_enorm; h->off_image = off_image;
 }
 
+// one launch instead of three memset nodes at the head of the fused forward: per-code counts, the loss scalar and
+// the assignment's {work counter, block ticket}
+__global__ void forward_zero_kernel(unsigned long long* counts, int K, float* loss, int* work2) {
+  for (int k = threadIdx.x; k < K; k += blockDim.x) counts[k] = 0ull;
+  if (threadIdx.x == 0) { if (loss) *loss = 0.f; work2[0] = 0; work2[1] = 0; }
+}
+
 // MKL's sgemm K-blocking as probed on the reference CPU path: one chain up to
 // 384 terms, two halves up to 768, 384-blocks beyond.
 static int auto_kblock(long long D) {
@@ -118,7 +125,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
                            const float* E, int64_t K, const void* blob,
                            int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
                            int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
-                           float* usage_out);
+                           float* usage_out, float* zero_loss = nullptr, bool zero_outputs = false);
 
 int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                      const float* E, int64_t K, const void* blob,
@@ -132,7 +139,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
                            const float* E, int64_t K, const void* blob,
                            int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
                            int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
-                           float* usage_out) {
+                           float* usage_out, float* zero_loss, bool zero_outputs) {
   if (!x || !E || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
   if (!idx_out && !best_key_out) return VQSEG_EINVAL;
   const long long n_rows = B * P;
@@ -183,7 +190,10 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   ea.key_out = (unsigned long long*)best_key_out; ea.code_base = code_base;
   ea.done_blocks = work_count + 1;
   ea.usage_out = counts_out ? usage_out : nullptr;
-  {
+  if (zero_outputs) {                                            // fused forward: counts + loss + work counter + ticket
+    forward_zero_kernel<<<1, 256, 0, st>>>((unsigned long long*)counts_out, (int)K, zero_loss, work_count);
+    VQSEG_LAUNCH_CHECK();
+  } else {
     cudaError_t e0 = cudaMemsetAsync(work_count, 0, 2 * sizeof(int), st);      // work counter + block ticket
     if (e0 != cudaSuccess) return (int)e0;
   }
@@ -244,12 +254,14 @@ int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
   if (!idx_out || !counts_out || !q_out || K <= 0) return VQSEG_EINVAL;
   const size_t wa = (size_t)round_up(vqseg_assign_workspace_bytes(B * P, D, K, algo), 256);
   if (!ws || ws_bytes < wa + vqseg_gather_workspace_bytes(B * P, D)) return VQSEG_EWORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(counts_out, 0, (size_t)K * sizeof(int64_t), st);
-  if (e != cudaSuccess) return (int)e;
-  if (loss_out) { e = cudaMemsetAsync(loss_out, 0, sizeof(float), st); if (e != cudaSuccess) return (int)e; }
+  if (B * P == 0) {                                              // nothing to launch: outputs of an empty batch
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(counts_out, 0, (size_t)K * sizeof(int64_t), st);
+    if (e == cudaSuccess && loss_out) e = cudaMemsetAsync(loss_out, 0, sizeof(float), st);
+    return (int)e;
+  }
   int rc = assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, kblock, algo, ws, wa, stream,
-                           usage_out);      // usage is reduced by the last block of the exact pass
+                           usage_out, loss_out, true);   // one zeroing launch; usage reduced by the exact pass's last block
   if (rc) return rc;
   return vqseg_gather_ste_f32(x, B, P, D, sB, sP, sD, E, K, idx_out, q_out, qB, qP, qD, loss_out, mode,
                               (char*)ws + wa, ws_bytes - wa, stream);
