@@ -14,11 +14,16 @@ __global__ void blob_init_kernel(BlobHeader* h, int K, int D, int K_pad, int D_p
   h->off_enorm = off_enorm; h->off_image = off_image;
 }
 
+extern "C" int vqseg_internal_gather_ticket(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                                            const float* E, int64_t K, const int64_t* idx,
+                                            float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out, int mode,
+                                            void* ws, size_t ws_bytes, void* stream, int* ticket);
+
 // one launch instead of three memset nodes at the head of the fused forward: per-code counts, the loss scalar and
 // the assignment's {work counter, block ticket}
 __global__ void forward_zero_kernel(unsigned long long* counts, int K, float* loss, int* work2) {
   for (int k = threadIdx.x; k < K; k += blockDim.x) counts[k] = 0ull;
-  if (threadIdx.x == 0) { if (loss) *loss = 0.f; work2[0] = 0; work2[1] = 0; }
+  if (threadIdx.x == 0) { if (loss) *loss = 0.f; work2[0] = 0; work2[1] = 0; work2[2] = 0; }   // [2]: gather's loss ticket
 }
 
 // MKL's sgemm K-blocking as probed on the reference CPU path: one chain up to
@@ -263,8 +268,9 @@ int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
   int rc = assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, kblock, algo, ws, wa, stream,
                            usage_out, loss_out, true);   // one zeroing launch; usage reduced by the exact pass's last block
   if (rc) return rc;
-  return vqseg_gather_ste_f32(x, B, P, D, sB, sP, sD, E, K, idx_out, q_out, qB, qP, qD, loss_out, mode,
-                              (char*)ws + wa, ws_bytes - wa, stream);
+  // the first 256 bytes of the assignment workspace hold {work counter, block ticket, loss ticket}, all zeroed above
+  return vqseg_internal_gather_ticket(x, B, P, D, sB, sP, sD, E, K, idx_out, q_out, qB, qP, qD, loss_out, mode,
+                                      (char*)ws + wa, ws_bytes - wa, stream, (int*)ws + 2);
 }
 
 }  // extern "C"

@@ -17,11 +17,34 @@ constexpr int kGPix = 128;       // pixels per tile
 
 __device__ __forceinline__ float round_fp16(float v) { return __half2float(__float2half_rn(v)); }
 
+// Last-block loss reduction (fused forward): every block publishes its partial, takes a ticket, and the block that
+// draws the last one sums all partials in the same fixed order as loss_finalize_kernel -- one launch less.
+struct LossTail { int* ticket; float* loss_out; double inv_numel; };
+__device__ __forceinline__ void loss_tail(const LossTail& t, const float* partial, int n_partial, int n_blocks) {
+  __shared__ double s_dred[256];
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(t.ticket, 1) == n_blocks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n_partial; i += 256) s += (double)__ldcg(partial + i);
+  s_dred[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) s_dred[threadIdx.x] += s_dred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *t.loss_out = (float)(s_dred[0] * t.inv_numel);
+}
+
 // VEC: pixel quads are 16-byte aligned and never straddle an image (P % 4 == 0, aligned bases)
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float* __restrict__ E, int K,
                                                              const long long* __restrict__ idx, RowsOut q,
-                                                             float* __restrict__ partial) {
+                                                             float* __restrict__ partial, LossTail tail) {
   __shared__ float tile[kGTile][kGPix + 1];
   __shared__ int s_idx[kGPix];
   __shared__ float s_red[8];
@@ -128,6 +151,7 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
       for (int w = 0; w < 8; ++w) s += s_red[w];
       partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = s;
     }
+    if (tail.ticket) loss_tail(tail, partial, (int)(gridDim.x * gridDim.y), (int)(gridDim.x * gridDim.y));
   }
 }
 
@@ -135,7 +159,7 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
 template <int MODE>
 __global__ void __launch_bounds__(256) gather_ste_generic_kernel(Rows x, const float* __restrict__ E, int K,
                                                                  const long long* __restrict__ idx, RowsOut q,
-                                                                 float* __restrict__ partial) {
+                                                                 float* __restrict__ partial, LossTail tail) {
   __shared__ float s_red[8];
   const int D = (int)x.D;
   const long long n_rows = x.n_rows();
@@ -172,6 +196,7 @@ __global__ void __launch_bounds__(256) gather_ste_generic_kernel(Rows x, const f
       for (int w = 0; w < 8; ++w) s += s_red[w];
       partial[blockIdx.x] = s;
     }
+    if (tail.ticket) loss_tail(tail, partial, (int)gridDim.x, (int)gridDim.x);
   }
 }
 
@@ -192,10 +217,12 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restr
 
 template <int MODE>
 static int launch_gather(const Rows& x, const float* E, int K, const long long* idx, const RowsOut& q,
-                         float* loss_out, float* partial, size_t partial_cap, cudaStream_t st) {
+                         float* loss_out, float* partial, size_t partial_cap, cudaStream_t st, int* ticket = nullptr) {
   const long long n_rows = x.n_rows();
   const bool train = (MODE == VQSEG_MODE_TRAIN || MODE == VQSEG_MODE_TRAIN_AMP);
   const bool want_loss = train && loss_out != nullptr;
+  // ticket (zeroed by the caller): the kernel's last block reduces the loss itself
+  LossTail tail{want_loss ? ticket : nullptr, loss_out, 1.0 / ((double)n_rows * (double)x.D)};
   int n_partial = 0;
   if (x.sP == 1 && q.sP == 1) {
     dim3 grid((unsigned)((n_rows + kGPix - 1) / kGPix), (unsigned)((x.D + kGTile - 1) / kGTile));
@@ -204,18 +231,18 @@ static int launch_gather(const Rows& x, const float* E, int K, const long long* 
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool vec = (x.P % 4 == 0) && al(q.ptr) && (q.sD % 4 == 0) && (q.sB % 4 == 0) &&
                      (!train || (al(x.ptr) && (x.sD % 4 == 0) && (x.sB % 4 == 0)));
-    if (vec) gather_ste_pxc_kernel<MODE, true><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr);
-    else     gather_ste_pxc_kernel<MODE, false><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr);
+    if (vec) gather_ste_pxc_kernel<MODE, true><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr, tail);
+    else     gather_ste_pxc_kernel<MODE, false><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr, tail);
   } else {
     long long blocks = (n_rows + 7) / 8;
     long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
     n_partial = (int)blocks;
     if (want_loss && (size_t)n_partial > partial_cap) return VQSEG_EWORKSPACE;
-    gather_ste_generic_kernel<MODE><<<(unsigned)blocks, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr);
+    gather_ste_generic_kernel<MODE><<<(unsigned)blocks, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr, tail);
   }
   VQSEG_LAUNCH_CHECK();
-  if (want_loss) {
+  if (want_loss && !ticket) {
     loss_finalize_kernel<<<1, 256, 0, st>>>(partial, n_partial, 1.0 / ((double)n_rows * (double)x.D), loss_out);
     VQSEG_LAUNCH_CHECK();
   }
@@ -670,6 +697,32 @@ int vqseg_gather_ste_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     case VQSEG_MODE_EVAL_AMP:  return launch_gather<VQSEG_MODE_EVAL_AMP>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st);
     case VQSEG_MODE_TRAIN:     return launch_gather<VQSEG_MODE_TRAIN>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st);
     case VQSEG_MODE_TRAIN_AMP: return launch_gather<VQSEG_MODE_TRAIN_AMP>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st);
+  }
+  return VQSEG_EINVAL;
+}
+
+// vqseg_gather_ste_f32 for the fused forward: `ticket` (an int the caller has zeroed on this stream) lets the
+// kernel's last block reduce the loss, so no separate reduction launch follows
+int vqseg_internal_gather_ticket(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                                 const float* E, int64_t K, const int64_t* idx,
+                                 float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out, int mode,
+                                 void* ws, size_t ws_bytes, void* stream, int* ticket) {
+  if (!E || !idx || !q_out || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
+  const bool train = mode == VQSEG_MODE_TRAIN || mode == VQSEG_MODE_TRAIN_AMP;
+  if (train && !x) return VQSEG_EINVAL;
+  if (B * P == 0) return 0;
+  Rows xr{x, B, P, D, sB, sP, sD};
+  if (!train) { xr.ptr = nullptr; xr.sB = qB; xr.sP = qP; xr.sD = qD; }
+  RowsOut qr{q_out, B, P, D, qB, qP, qD};
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = (float*)ws;
+  size_t cap = ws ? ws_bytes / sizeof(float) : 0;
+  const long long* ix = (const long long*)idx;
+  switch (mode) {
+    case VQSEG_MODE_EVAL:      return launch_gather<VQSEG_MODE_EVAL>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st, ticket);
+    case VQSEG_MODE_EVAL_AMP:  return launch_gather<VQSEG_MODE_EVAL_AMP>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st, ticket);
+    case VQSEG_MODE_TRAIN:     return launch_gather<VQSEG_MODE_TRAIN>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st, ticket);
+    case VQSEG_MODE_TRAIN_AMP: return launch_gather<VQSEG_MODE_TRAIN_AMP>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st, ticket);
   }
   return VQSEG_EINVAL;
 }
