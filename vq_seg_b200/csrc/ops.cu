@@ -16,6 +16,9 @@ constexpr int kGTile = 32;       // dims per tile (128 x 32 tiles: 2048 blocks a
 constexpr int kGPix = 128;       // pixels per tile
 
 __device__ __forceinline__ float round_fp16(float v) { return __half2float(__float2half_rn(v)); }
+// pixel p of a tile lives in column (p % 4) * 32 + p / 4: a lane that owns pixels 4*lane .. 4*lane+3 then reads
+// columns lane, 32 + lane, 64 + lane, 96 + lane -- conflict-free (straight columns gave 4-way bank conflicts)
+__device__ __forceinline__ int gcol(int p) { return ((p & 3) << 5) | (p >> 2); }
 
 // Last-block loss reduction (fused forward): every block publishes its partial, takes a ticket, and the block that
 // draws the last one sums all partials in the same fixed order as loss_finalize_kernel -- one launch less.
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int h = 0; h < kGTile / 32; ++h) tile[lane + 32 * h][p0 + 8 * u] = kAmp ? round_fp16(v[u][h]) : v[u][h];
+      for (int h = 0; h < kGTile / 32; ++h) tile[lane + 32 * h][gcol(p0 + 8 * u)] = kAmp ? round_fp16(v[u][h]) : v[u][h];
   }
   __syncthreads();
   // phase 2: stream pixels; lane owns 4 consecutive pixels, warps take the dims round-robin
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
       for (int u = 0; u < kGTile / 8; ++u) {
         const int d = warp + 8 * u;
         if (d0 + d < D) {
-          float4 e = make_float4(tile[d][p4], tile[d][p4 + 1], tile[d][p4 + 2], tile[d][p4 + 3]);
+          float4 e = make_float4(tile[d][lane], tile[d][32 + lane], tile[d][64 + lane], tile[d][96 + lane]);   // = pixels p4 .. p4+3
           float4 o = e;
           if (kTrain) {
             const float4 xv = xr[u];
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
         float* qb = q.ptr + b * q.sB + pp * q.sP;
         for (int d = warp; d < kGTile; d += 8) {
           if (d0 + d < D) {
-            float e = tile[d][p4 + i];
+            float e = tile[d][32 * i + lane];
             float o = e;
             if (kTrain) {
               float xv = __ldg(xb + (long long)(d0 + d) * x.sD);
