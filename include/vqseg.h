@@ -173,6 +173,15 @@ int    vqseg_l2norm_rows_f32(const float* x, int64_t B, int64_t P, int64_t D,
 int    vqseg_assign_cosine_f32(const float* xn, int64_t N, int64_t D, const float* E, int64_t K,
                                int64_t* idx_out, int64_t* counts_out, void* stream);
 
+/* ---- EMA codebook update: OPT-IN EXTENSION, no reference counterpart (the reference stores `decay` and `eps`,
+ * vq_img.py:150-151,199-200, and never reads them: there is no EMA, so parity is unpinned). Standard VQ-VAE
+ * equations: cluster_size <- decay*cluster_size + (1-decay)*counts; embed_avg <- decay*embed_avg + (1-decay)*sums;
+ * n = sum(cluster_size); cs = (cluster_size + eps) / (n + K*eps) * n; weight = embed_avg / cs.  counts / sums come
+ * from vqseg_code_stats_f32 (all-reduced by the caller in data-parallel training).  ws: >= 4 bytes.           */
+int    vqseg_ema_update_f32(const int64_t* counts, const float* sums, float* cluster_size_inout,
+                            float* embed_avg_inout, float* weight_out, int64_t K, int64_t D,
+                            float decay, float eps, void* ws, void* stream);
+
 /* ---- VQ segmentation head (models/modules/vq_segmentation_head.py) ------------------------------
  * The head classifies every decoder pixel by its distance to K class prototypes and RETURNS the distance map.
  * dist_out[b, p, k] (element strides oB, oP, oK; (K*P, 1, P) gives the (B, K, H, W) score layout directly):

@@ -191,6 +191,20 @@ def kmeans(samples: torch.Tensor, num_clusters: int, num_iters: int,
     return means, bins
 
 
+def ema_update(counts: torch.Tensor, sums: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
+               decay: float, eps: float):
+    """EMA codebook update -- OPT-IN EXTENSION WITHOUT A REFERENCE COUNTERPART (parity unpinned): the reference
+    stores `decay` / `eps` (vq_img.py:150-151) and never reads them.  This restates the standard VQ-VAE rule
+    (ema_inplace + laplace_smoothing of lucidrains/vector-quantize-pytorch, the code base the reference derives
+    from) for the tests of vqseg_ema_update_f32.  Returns (cluster_size, embed_avg, weight)."""
+    k = counts.numel()
+    cluster_size = cluster_size * decay + (1 - decay) * counts.float()
+    embed_avg = embed_avg * decay + (1 - decay) * sums
+    n = cluster_size.sum()
+    cs = (cluster_size + eps) / (n + k * eps) * n
+    return cluster_size, embed_avg, embed_avg / cs.unsqueeze(1)
+
+
 class OracleIdentity(torch.nn.Module):
     """vector_quantizer/__init__.py:27-32"""
 

@@ -303,6 +303,49 @@ def stage_seghead():
         print(f"[seghead] {nm:38s}: eval forward {t_eval:8.1f} us, train forward+backward {t_train:8.1f} us")
 
 
+def stage_big():
+    """BASELINE configs 4 and 5 on one GPU: k-means iteration at N = 1e7, K = 1024, D = 512 (20 GB of samples) and a
+    full-codebook assignment at N = 4 Mi, K = 65536, D = 256 (140.7 TFLOP)."""
+    def ev_time(fn, n=1):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            r = fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / n, r
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n, d, k = 10_000_000, 512, 1024
+    x = torch.empty(1, n, d, device=dev)
+    for i in range(0, n, 1_000_000):
+        x[0, i:i + 1_000_000].normal_(generator=g)
+    means = x[0, :k].clone()
+    blob = ops.prepare_codebook(means)
+    ops.assign(x, means, blob, ops.ALGO_TC)                                   # warm-up
+    t_as, (idx, counts) = ev_time(lambda: ops.assign(x, means, blob, ops.ALGO_TC))
+    t_at, _ = ev_time(lambda: ops.code_stats(x, idx, k, False))
+    t_dt, (bins, sums) = ev_time(lambda: ops.code_stats(x, idx, k, True))
+    assert counts.sum().item() == n and torch.equal(bins, counts)
+    fl = 2.0 * n * k * d
+    print(f"[big] C4 N=1e7 K=1024 D=512: assign {t_as:.2f} ms ({fl / t_as / 1e9:.0f} TFLOP/s), stats atomic {t_at:.2f} ms "
+          f"({(4.0 * n * d) / t_at / 1e9:.2f} TB/s), stats ordered {t_dt:.2f} ms -> iteration {t_as + t_at:.1f} / {t_as + t_dt:.1f} ms")
+    del x, idx, sums
+    torch.cuda.empty_cache()
+    n, d, k = 4 << 20, 256, 65536
+    x = torch.randn(1, n, d, generator=g, device=dev)
+    e = torch.randn(k, d, generator=g, device=dev)
+    blob = ops.prepare_codebook(e)
+    t5, (idx, counts) = ev_time(lambda: ops.assign(x, e, blob, ops.ALGO_TC))
+    fl = 2.0 * n * k * d
+    print(f"[big] C5 N=4Mi K=65536 D=256 (whole codebook on one GPU): assign {t5:.1f} ms ({fl / t5 / 1e9:.0f} TFLOP/s), "
+          f"codes used {int((counts > 0).sum())}")
+    # spot check of 2048 rows against the exact scorer
+    sub = x[:, 12345:12345 + 2048]
+    i_ex, _ = ops.assign(sub, e, None, ops.ALGO_EXACT)
+    assert torch.equal(i_ex, idx[:, 12345:12345 + 2048]), "C5 spot check failed"
+    print("[big] C5 spot check vs exact scorer: ok")
+
+
 def stage_shapes():
     """filter / rescoring kernel times (CUDA events inside the C ABI) over the BASELINE shapes"""
     from vq_seg_b200 import _native
@@ -413,5 +456,5 @@ def stage_trace():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "seghead": stage_seghead, "shapes": stage_shapes, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "seghead": stage_seghead, "big": stage_big, "shapes": stage_shapes, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

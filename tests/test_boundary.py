@@ -133,3 +133,20 @@ def test_seghead_module_surface():
         V.VQSegmentationHead(dim=16, num_embeddings=3, distance="manhattan")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 16, 4, 4))
+
+
+def test_ema_extension_surface_and_oracle():
+    """enable_ema() keeps the reference's state_dict keys (moving averages are non-persistent buffers); the restated
+    rule reduces to the smoothed batch means when decay == 0."""
+    from oracle import vq_oracle as O
+    m = V.VectorQuantizer(dim=8, num_embeddings=5, decay=0.7, eps=1e-4)
+    assert not m.codebook.ema_enabled
+    m.enable_ema()
+    assert m.codebook.ema_enabled and list(m.state_dict()) == ["codebook.embedding.weight"]
+    assert m.codebook.decay == 0.7 and m.codebook.ema_eps == 1e-4 and m.codebook.cluster_size.shape == (5,)
+    counts = torch.tensor([4, 0, 2, 1, 3]); sums = torch.randn(5, 8) * counts.unsqueeze(1)
+    cs, ea, w = O.ema_update(counts, sums, torch.zeros(5), torch.zeros(5, 8), 0.0, 0.0)
+    assert torch.equal(cs, counts.float()) and torch.equal(ea, sums)
+    nz = counts > 0
+    assert torch.allclose(w[nz], sums[nz] / counts[nz].unsqueeze(1).float())
+    assert V.stack_code_usage([torch.tensor(1.0), None, torch.tensor(3.0)]).tolist() == [1.0, 3.0]

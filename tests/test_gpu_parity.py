@@ -414,3 +414,44 @@ def test_opcheck(dev):
     idx, _ = ops.assign(x, e, None, 1)
     torch.library.opcheck(torch.ops.vqseg.gather_ste, (x, e, idx, 1), test_utils=("test_schema", "test_faketensor"))
     torch.library.opcheck(torch.ops.vqseg.code_stats, (x, idx, 24, True), test_utils=("test_schema", "test_faketensor"))
+
+
+def test_ema_extension_matches_standard_equations(dev):
+    """Opt-in EMA codebook update (no reference counterpart, parity unpinned): kernel against the restated standard
+    VQ-VAE rule, then through the module: one training forward moves the codebook as the rule predicts and leaves
+    the state_dict keys alone."""
+    import vq_seg_b200 as V
+    from vq_seg_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    k, d = 300, 96
+    counts = torch.randint(0, 50, (k,), generator=g)
+    counts[::7] = 0
+    sums = torch.randn(k, d, generator=g) * counts.unsqueeze(1).float()
+    cs0 = torch.rand(k, generator=g) * 20
+    ea0 = torch.randn(k, d, generator=g)
+    cs_ref, ea_ref, w_ref = O.ema_update(counts, sums, cs0, ea0, 0.8, 1e-5)
+    cs, ea, w = cs0.to(dev), ea0.to(dev), torch.empty(k, d, device=dev)
+    ops.ema_update(counts.to(dev), sums.to(dev), cs, ea, w, 0.8, 1e-5)
+    # fp32 throughout; sums of opposite sign cancel in embed_avg, hence the absolute term
+    assert torch.allclose(cs.cpu(), cs_ref, rtol=1e-6, atol=1e-6) and torch.allclose(ea.cpu(), ea_ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(w.cpu(), w_ref, rtol=1e-5, atol=1e-6)
+    x, e = cases.FORWARD_CASES["d64"]()
+    m = V.VectorQuantizer(dim=64, num_embeddings=e.shape[0], decay=0.9).to(dev)
+    m.codebook.embedding.weight.data.copy_(e.to(dev))
+    m.enable_ema()
+    assert list(m.state_dict()) == ["codebook.embedding.weight"]
+    m.train()
+    q, idx, loss, usage = m(x.to(dev))
+    xv = view(x)
+    cnt = torch.bincount(idx.cpu().reshape(-1), minlength=e.shape[0])
+    sm = torch.zeros_like(e).index_add_(0, idx.cpu().reshape(-1), xv.reshape(-1, 64))
+    _, _, w_exp = O.ema_update(cnt, sm, torch.zeros(e.shape[0]), e.clone(), 0.9, 1e-5)
+    assert torch.equal(idx.cpu().reshape(xv.shape[:2]), O.assign_euclidean(xv, e))     # the lookup used the OLD codebook
+    assert torch.allclose(m.codebook.embedding.weight.detach().cpu(), w_exp, rtol=1e-4, atol=1e-5)
+    w1 = m.codebook.embedding.weight.detach().cpu().clone()
+    q2, idx2, _, _ = m(x.to(dev))                                              # and the next forward the NEW one
+    assert near_tie_ok(x, w1, idx2.cpu().reshape(xv.shape[:2]), O.assign_euclidean(xv, w1))
+    m.eval()
+    w_before = m.codebook.embedding.weight.detach().clone()
+    m(x.to(dev))
+    assert torch.equal(m.codebook.embedding.weight.detach(), w_before)         # no update outside training

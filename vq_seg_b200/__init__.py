@@ -10,4 +10,13 @@ from .vq_segmentation_head import VQSegmentationHead, EuclideanSegHead, Cosinesi
 from .factory import make_vq_module, Identity, install  # noqa: F401
 from . import ops  # noqa: F401
 
+
+def stack_code_usage(usages):
+    """One device tensor from the per-layer code-usage scalars (None entries of Identity levels skipped): the callers'
+    `code_usage.detach().cpu()` per layer per forward (modified_vqunet/net.py:233) serialises the stream three times a
+    step; `stack_code_usage(lst).cpu()` synchronises once."""
+    import torch
+    vals = [u.detach().reshape(()) for u in usages if u is not None]
+    return torch.stack(vals) if vals else torch.empty(0)
+
 __version__ = "0.1.0"

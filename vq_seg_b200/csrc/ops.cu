@@ -624,6 +624,45 @@ static inline unsigned grid_for(long long total, int threads, int waves = 8) {
   return (unsigned)blocks;
 }
 
+// =================================================================================================
+// EMA codebook update (opt-in extension; NOT in the reference, which stores `decay` / `eps` unused:
+// parity unpinned -- the standard VQ-VAE equations, as in lucidrains/vector-quantize-pytorch from which the
+// reference derives):  cluster_size <- decay cluster_size + (1 - decay) counts;  embed_avg <- decay embed_avg +
+// (1 - decay) sums;  n = sum(cluster_size);  cs = (cluster_size + eps) / (n + K eps) n;  weight = embed_avg / cs.
+// =================================================================================================
+__global__ void __launch_bounds__(256) ema_cluster_kernel(const long long* __restrict__ counts, float* __restrict__ cluster_size,
+                                                          int K, float decay, float* __restrict__ total_out) {
+  __shared__ double s_red[256];
+  double s = 0.0;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const float cs = __fadd_rn(__fmul_rn(cluster_size[k], decay), __fmul_rn(1.f - decay, (float)counts[k]));
+    cluster_size[k] = cs;
+    s += (double)cs;
+  }
+  s_red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = (float)s_red[0];
+}
+
+__global__ void __launch_bounds__(256) ema_embed_kernel(const float* __restrict__ sums, const float* __restrict__ cluster_size,
+                                                        const float* __restrict__ total, float* __restrict__ embed_avg,
+                                                        float* __restrict__ weight, int K, int D, float decay, float eps) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const float n = __ldg(total);
+  const float cs = __fmul_rn(__fdiv_rn(__fadd_rn(cluster_size[k], eps), __fadd_rn(n, __fmul_rn((float)K, eps))), n);
+  for (int d = lane; d < D; d += 32) {
+    const long long i = (long long)k * D + d;
+    const float ea = __fadd_rn(__fmul_rn(embed_avg[i], decay), __fmul_rn(1.f - decay, sums[i]));
+    embed_avg[i] = ea;
+    weight[i] = __fdiv_rn(ea, cs);
+  }
+}
+
 }  // namespace vqseg
 
 using namespace vqseg;
@@ -847,6 +886,18 @@ int vqseg_kmeans_finalize_f32(const float* sums, const int64_t* counts, float* m
   if (!sums || !counts || !means_inout || K <= 0 || D <= 0) return VQSEG_EINVAL;
   kmeans_finalize_kernel<<<(unsigned)((K * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       sums, (const long long*)counts, means_inout, (int)K, (int)D, cosine);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+int vqseg_ema_update_f32(const int64_t* counts, const float* sums, float* cluster_size_inout, float* embed_avg_inout,
+                         float* weight_out, int64_t K, int64_t D, float decay, float eps, void* ws, void* stream) {
+  if (!counts || !sums || !cluster_size_inout || !embed_avg_inout || !weight_out || !ws || K <= 0 || D <= 0) return VQSEG_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  ema_cluster_kernel<<<1, 256, 0, st>>>((const long long*)counts, cluster_size_inout, (int)K, decay, (float*)ws);
+  VQSEG_LAUNCH_CHECK();
+  ema_embed_kernel<<<(unsigned)((K * 32 + 255) / 256), 256, 0, st>>>(sums, cluster_size_inout, (const float*)ws, embed_avg_inout,
+                                                                    weight_out, (int)K, (int)D, decay, eps);
   VQSEG_LAUNCH_CHECK();
   return 0;
 }

@@ -356,6 +356,27 @@ def _(xn, codebook):
 
 
 # -------------------------------------------------------------------------------------------------
+# opt-in EMA codebook update (no reference counterpart: SURVEY.md 8f-4, parity unpinned)
+def _ema_update_impl(counts: torch.Tensor, sums: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
+                     weight: torch.Tensor, decay: float, eps: float) -> None:
+    """In place: cluster_size, embed_avg (moving averages) and weight (the new codebook)."""
+    _require_cuda(counts, sums, cluster_size, embed_avg, weight)
+    L = _native.lib()
+    k, d = weight.shape
+    assert counts.dtype == torch.int64 and counts.is_contiguous() and counts.numel() == k
+    for t in (sums, cluster_size, embed_avg, weight):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    ws = torch.empty(4, dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _native.check(L.vqseg_ema_update_f32(counts.data_ptr(), sums.data_ptr(), cluster_size.data_ptr(),
+                                             embed_avg.data_ptr(), weight.data_ptr(), k, d, float(decay), float(eps),
+                                             ws.data_ptr(), _stream()), "ema_update")
+
+
+ema_update = torch.library.custom_op("vqseg::ema_update", mutates_args=("cluster_size", "embed_avg", "weight"))(_ema_update_impl)
+
+
+# -------------------------------------------------------------------------------------------------
 # distance map of the VQ segmentation head (models/modules/vq_segmentation_head.py:167-176 / :104-111)
 def _dist_map_impl(x: torch.Tensor, codebook: torch.Tensor, cosine: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """x (B, P, D) view (any strides; for cosine: rows already l2-normalised), codebook (K, D).

@@ -92,6 +92,7 @@ class _CodebookBase(nn.Module):
         self.kmeans_init = kmeans_init
         self.kmeans_iters = kmeans_iters
         self.initted = False                    # plain attribute, NOT in the state_dict (like the reference)
+        self.ema_enabled = False
         self.num_codebook = num_codebook
         self.decay = decay                      # accepted and stored, never read (the reference has no EMA)
         self.embedding = nn.Embedding(num_embeddings, embedding_dim)
@@ -117,6 +118,34 @@ class _CodebookBase(nn.Module):
 
     def invalidate(self):
         self._blob = None
+
+    # ---- opt-in EMA codebook update (extension; the reference never reads decay / eps) ----
+    def enable_ema(self, decay=None, eps=1e-5, reduce_fn=None, deterministic=False):
+        """After every TRAINING forward move the codebook towards the per-code means of that batch with the
+        standard VQ-VAE EMA rule (include/vqseg.h, vqseg_ema_update_f32), using the `decay` the constructor stored
+        (VectorQuantizer.enable_ema() also passes its stored `eps`).  `reduce_fn(counts, sums)` all-reduces the statistics in data-parallel training
+        (vq_seg_b200.distributed.allreduce_code_stats).  The moving averages are non-persistent buffers, so
+        state_dict keys stay the reference's."""
+        if decay is not None:
+            self.decay = decay
+        self.ema_eps = eps
+        w = self.embedding.weight
+        self.register_buffer("cluster_size", torch.zeros(self.num_embeddings, dtype=torch.float32, device=w.device),
+                             persistent=False)
+        self.register_buffer("embed_avg", w.detach().clone().float().contiguous(), persistent=False)
+        self.ema_reduce_fn = reduce_fn
+        self.ema_deterministic = deterministic
+        self.ema_enabled = True
+        return self
+
+    @torch.no_grad()
+    def _ema_step(self, x, idx):
+        counts, sums = ops.code_stats(x, idx, self.num_embeddings, self.ema_deterministic)
+        if self.ema_reduce_fn is not None:
+            self.ema_reduce_fn(counts, sums)
+        w = self.embedding.weight
+        ops.ema_update(counts, sums, self.cluster_size, self.embed_avg, w.data, self.decay, self.ema_eps)
+        self.invalidate()                       # the prepared fp16 image of the codebook is stale now
 
     def _kmeans_init(self, flatten_x, cosine):
         if self.initted:
@@ -188,6 +217,12 @@ class VectorQuantizer(nn.Module):
                                        eps=eps, num_codebook=num_codebook)
         self.amp_compat = True    # under fp16 autocast round the gathered code through fp16 like the reference's matmul
 
+    def enable_ema(self, **kw):
+        """Opt-in EMA codebook update with the stored `decay` and `eps` (extension; see the codebook's enable_ema)."""
+        kw.setdefault("eps", self.eps)
+        self.codebook.enable_ema(**kw)
+        return self
+
     def forward(self, x):
         if x.dim() != 4:
             raise ValueError(f"VectorQuantizer expects a (B, C, H, W) tensor, got shape {tuple(x.shape)}")
@@ -220,6 +255,10 @@ class VectorQuantizer(nn.Module):
             quantize, idx, mse, code_usage = ops.fused_forward(xv, cb.embedding.weight, blob, self.training, amp16, cb.algo)
         if self.training and self.commitment_weight > 0:
             loss = loss + mse * self.commitment_weight
+        if self.training and cb.ema_enabled:
+            if cb.embed_avg.device != device:    # enable_ema() ran before .to(device)
+                cb.enable_ema(eps=cb.ema_eps, reduce_fn=cb.ema_reduce_fn, deterministic=cb.ema_deterministic)
+            cb._ema_step(ops.l2norm_rows(xv) if cosine else xv, idx)
         quantize = quantize.permute(0, 2, 1).reshape(b, c, h, w)     # memory is already (B, C, H*W): a view
         embed_index = idx.reshape(b, h, w)
         return quantize, embed_index, loss, code_usage
