@@ -138,8 +138,10 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_kernel(Rows x, const floa
 }
 
 // backward of the Euclidean map: w = g / d (0 where d == 0);  gx[n,:] = sum_k w[n,k] (x[n,:] - e_k);
-// gE[k,:] = sum_n w[n,k] (e_k - x[n,:])  (warp shuffle reduction -> shared accumulators -> one global atomic per
-// (block, k, d)).
+// gE[k,:] = sum_n w[n,k] (e_k - x[n,:]) = e_k * sum_n w[n,k] - sum_n w[n,k] x[n,:].
+// A block owns 128 pixels.  Per chunk of 32 dims every thread (= pixel) loads its 32 values once, writes gx, and
+// parks them in a padded smem tile; then thread (k, d) of the block reduces sum_p w[k][p] * x[p][d] over the 128
+// pixels straight from shared memory (no shuffles) and issues ONE global atomic per (block, k, d).
 template <int KMAX>
 __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const float* __restrict__ E, int K,
                                                                  const float* __restrict__ g, const float* __restrict__ dist,
@@ -147,14 +149,15 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
                                                                  RowsOut gx, float* __restrict__ gE) {
   extern __shared__ __align__(16) float dmb_smem[];
   const int D = (int)x.D;
-  float* s_e = dmb_smem;                     // [K][D]
-  float* s_g = s_e + K * D;                  // [K][D] block accumulators
-  for (int i = threadIdx.x; i < K * D; i += blockDim.x) { s_e[i] = __ldg(E + i); s_g[i] = 0.f; }
-  __syncthreads();
+  float* s_e = dmb_smem;                          // [K][D]
+  float* s_w = s_e + K * D;                       // [K][128] weights of this block's pixels
+  float* s_ws = s_w + K * kDmThreads;             // [K] sum_p w[k][p]
+  float* s_x = s_ws + KMAX;                       // [32][129] tile of x
+  for (int i = threadIdx.x; i < K * D; i += blockDim.x) s_e[i] = __ldg(E + i);
   const long long n_rows = x.n_rows();
   const long long n = (long long)blockIdx.x * kDmThreads + threadIdx.x;
   const bool in = n < n_rows;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float w[KMAX];
   float wsum = 0.f;
   long long b = 0, pp = 0;
@@ -162,39 +165,65 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     w[k] = 0.f;
-    if (in && k < K) {
-      const long long o = b * oB + pp * oP + (long long)k * oK;
-      const float dv = __ldg(dist + o);
-      w[k] = dv == 0.f ? 0.f : __fdiv_rn(__ldg(g + o), dv);
+    if (k < K) {
+      if (in) {
+        const long long o = b * oB + pp * oP + (long long)k * oK;
+        const float dv = __ldg(dist + o);
+        w[k] = dv == 0.f ? 0.f : __fdiv_rn(__ldg(g + o), dv);
+      }
+      s_w[k * kDmThreads + threadIdx.x] = w[k];
       wsum += w[k];
     }
   }
+  __syncthreads();
+  // s_ws[k] = sum over the block's pixels (fixed order: warp tree, then the 4 warp sums)
+  for (int k = warp; k < K; k += kDmThreads / 32) {
+    float v = s_w[k * kDmThreads + lane] + s_w[k * kDmThreads + 32 + lane] + s_w[k * kDmThreads + 64 + lane] +
+              s_w[k * kDmThreads + 96 + lane];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_ws[k] = v;
+  }
   const float* xr = x.ptr + b * x.sB + pp * x.sP;
   float* gxr = gx.ptr + b * gx.sB + pp * gx.sP;
-  for (int d = 0; d < D; ++d) {
-    const float xv = in ? __ldg(xr + (long long)d * x.sD) : 0.f;
-    float acc = 0.f;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    float xv[32];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        const float diff = xv - s_e[k * D + d];
-        acc = fmaf(w[k], diff, acc);
-        float r = -w[k] * diff;                              // contribution to gE[k][d]
+    for (int u = 0; u < 32; ++u) xv[u] = (in && d0 + u < D) ? __ldg(xr + (long long)(d0 + u) * x.sD) : 0.f;
+    __syncthreads();                               // previous chunk's tile fully consumed (and s_ws visible)
 #pragma unroll
-        for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-        if (lane == 0 && r != 0.f) atomicAdd(&s_g[k * D + d], r);
+    for (int u = 0; u < 32; ++u) {
+      s_x[u * (kDmThreads + 1) + threadIdx.x] = xv[u];
+      if (in && d0 + u < D) {
+        float acc = xv[u] * wsum;                  // sum_k w_k (x - e_k) = x sum_k w_k - sum_k w_k e_k
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) acc = fmaf(-w[k], s_e[k * D + d0 + u], acc);
+        gxr[(long long)(d0 + u) * gx.sD] = acc;
       }
     }
-    if (in) gxr[(long long)d * gx.sD] = acc;
+    __syncthreads();
+    // thread (kk, dd): dd = lane (dim within the chunk), kk = warp, warp + 4, ...
+    const int dd = lane;
+    if (d0 + dd < D) {
+      for (int k = warp; k < K; k += kDmThreads / 32) {
+        const float* wr = s_w + k * kDmThreads;
+        const float* xc = s_x + dd * (kDmThreads + 1);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int p = 0; p < kDmThreads; p += 4) {
+          a0 = fmaf(wr[p], xc[p], a0); a1 = fmaf(wr[p + 1], xc[p + 1], a1);
+          a2 = fmaf(wr[p + 2], xc[p + 2], a2); a3 = fmaf(wr[p + 3], xc[p + 3], a3);
+        }
+        const float r = s_e[k * D + d0 + dd] * s_ws[k] - ((a0 + a1) + (a2 + a3));
+        if (r != 0.f) atomicAdd(gE + (long long)k * D + d0 + dd, r);
+      }
+    }
   }
-  (void)wsum;
-  __syncthreads();
-  for (int i = threadIdx.x; i < K * D; i += blockDim.x)
-    if (s_g[i] != 0.f) atomicAdd(gE + i, s_g[i]);
 }
 
 static bool dm_supported(long long K, long long D) {
-  return K >= 1 && K <= 32 && D >= 1 && D + 2 <= 384 && (2 * K * D + K + 64) * 4 <= 96 * 1024;
+  return K >= 1 && K <= 32 && D >= 1 && D + 2 <= 384 && (K * D + K * 128 + 32 * 129 + 64) * 4 <= 96 * 1024;
 }
 
 template <int KMAX>
@@ -216,7 +245,7 @@ static int launch_dm(const Rows& x, const float* E, int K, bool cosine, float* d
 template <int KMAX>
 static int launch_dm_bwd(const Rows& x, const float* E, int K, const float* g, const float* dist, long long oB, long long oP,
                          long long oK, const RowsOut& gx, float* gE, cudaStream_t st) {
-  const size_t smem = (size_t)2 * K * x.D * sizeof(float);
+  const size_t smem = ((size_t)K * x.D + (size_t)K * kDmThreads + KMAX + 32 * (kDmThreads + 1)) * sizeof(float);
   const unsigned grid = (unsigned)((x.n_rows() + kDmThreads - 1) / kDmThreads);
   if (smem > 48 * 1024) cudaFuncSetAttribute(dist_map_bwd_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   dist_map_bwd_kernel<KMAX><<<grid, kDmThreads, smem, st>>>(x, E, K, g, dist, oB, oP, oK, gx, gE);
