@@ -455,3 +455,35 @@ def test_ema_extension_matches_standard_equations(dev):
     w_before = m.codebook.embedding.weight.detach().clone()
     m(x.to(dev))
     assert torch.equal(m.codebook.embedding.weight.detach(), w_before)         # no update outside training
+
+
+def test_baseline_config_sizes_properties(dev):
+    """BASELINE configs 4 and 5 at (or near) their full sizes, through properties that need no CPU pass:
+    config 5's codebook (K = 65536, D = 256): filter + rescoring == brute-force exact scorer on 16 Ki rows;
+    config 4's k-means (K = 1024, D = 512) on 2 Mi rows: counts add up, the ordered statistics are reproducible
+    bit for bit, the atomic ones agree to 1e-5, assignment is a pure function of (x, means)."""
+    from vq_seg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(41)
+    n, d, k = 16384, 256, 65536
+    x = torch.randn(1, n, d, generator=g, device=dev)
+    e = torch.randn(k, d, generator=g, device=dev)
+    i_tc, c_tc = ops.assign(x, e, ops.prepare_codebook(e), ops.ALGO_TC)
+    i_ex, c_ex = ops.assign(x, e, None, ops.ALGO_EXACT)
+    assert torch.equal(i_tc, i_ex) and torch.equal(c_tc, c_ex) and c_tc.sum().item() == n
+    del x, e
+    n, d, k = 1 << 21, 512, 1024
+    x = torch.randn(1, n, d, generator=g, device=dev)
+    means = x[0, torch.randperm(n, device=dev, generator=g)[:k]].contiguous()
+    blob = ops.prepare_codebook(means)
+    idx, counts = ops.assign(x, means, blob, ops.ALGO_TC)
+    idx2, counts2 = ops.assign(x, means, blob, ops.ALGO_TC)
+    assert torch.equal(idx, idx2) and torch.equal(counts, counts2) and counts.sum().item() == n
+    b1, s1 = ops.code_stats(x, idx, k, True)
+    b2, s2 = ops.code_stats(x, idx, k, True)
+    b3, s3 = ops.code_stats(x, idx, k, False)
+    assert torch.equal(b1, counts) and torch.equal(b3, counts)
+    assert torch.equal(s1, s2)                                                  # deterministic order
+    assert (s1 - s3).abs().max().item() <= 1e-5 * s1.abs().max().item()
+    # the k-means start rows are samples: each is its own nearest code (distance exactly 0 up to fp32 cancellation)
+    sub = x[:, :4096]
+    assert torch.equal(ops.assign(sub, means, None, ops.ALGO_EXACT)[0], idx[:, :4096])
