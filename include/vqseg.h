@@ -190,18 +190,23 @@ int    vqseg_ema_update_f32(const int64_t* counts, const float* sums, float* clu
  *   cosine != 0: einsum('n d, e d -> n e') over rows the caller has already l2-normalised
  *                (CosinesimSegHead.forward :104); idx = first argmax (:107).
  * counts_out (nullable) = bincount(idx, K) (:174), zeroed by the call.  K <= 32, D <= 382, K*D small enough for
- * shared memory (VQSEG_EUNSUPPORTED otherwise: a segmentation head has K = classes, D = last decoder width). */
+ * shared memory (VQSEG_EUNSUPPORTED otherwise: a segmentation head has K = classes, D = last decoder width).
+ * score_out (nullable, Euclidean only, same strides): the wrapper's class scores softmax_k(1 - d_k / sum_j d_j)
+ * (VQSegmentationHead.forward :243-247 with the default nn.Softmax2d activation), written by the same kernel.  */
 int    vqseg_dist_map_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                           const float* E, int64_t K, int cosine,
                           float* dist_out, int64_t oB, int64_t oP, int64_t oK,
-                          int64_t* idx_out, int64_t* counts_out, void* stream);
+                          int64_t* idx_out, int64_t* counts_out, float* score_out, void* stream);
 /* backward of the Euclidean map (autograd of torch.cdist, p=2): with w = g / dist (0 where dist == 0),
  *   gx[n,:] = sum_k w[n,k] (x[n,:] - e_k),   gE[k,:] = sum_n w[n,k] (e_k - x[n,:])   (gE zeroed by the call;
- * accumulated with fp32 atomics: sums within 1e-5 relative, not bit-reproducible).  g and dist share strides. */
+ * accumulated with fp32 atomics: sums within 1e-5 relative, not bit-reproducible).  g and dist share strides.
+ * score (nullable): when given, g is the gradient w.r.t. score_out and the kernel first chains it through the
+ * softmax and the 1 - d / sum(d) normalisation.                                                           */
 int    vqseg_dist_map_bwd_f32(const float* g, const float* dist, int64_t oB, int64_t oP, int64_t oK,
                               const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                               const float* E, int64_t K,
-                              float* gx_out, int64_t gxB, int64_t gxP, int64_t gxD, float* gE_out, void* stream);
+                              float* gx_out, int64_t gxB, int64_t gxP, int64_t gxD, float* gE_out,
+                              const float* score, void* stream);
 
 #ifdef __cplusplus
 }

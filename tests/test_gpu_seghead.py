@@ -141,3 +141,27 @@ def test_seghead_limits_are_loud(dev):
         ops.dist_map(x, torch.randn(3, 400, device=dev), False)       # D + 2 > 384
     with pytest.raises(Exception):
         ops.dist_map(torch.randn(1, 64, 16, device=dev), torch.randn(40, 16, device=dev), False)   # K > 32
+
+
+def test_seghead_other_activation_takes_the_unfused_path(dev):
+    """Softmax2d (the default) is fused into the map kernels; any other activation goes through the distance map
+    + torch ops.  Both against the CPU oracle on the same inputs."""
+    import vq_seg_b200 as V
+    from torch import nn
+    from oracle.seghead_oracle import OracleVQSegmentationHead
+    x, e = cases.SEGHEAD_CASES["sh_c3_d32"][0]()
+    for act in (nn.Sigmoid, nn.Softmax2d):
+        m = V.VQSegmentationHead(dim=32, num_embeddings=3, activation=act).to(dev)
+        o = OracleVQSegmentationHead(dim=32, num_embeddings=3, activation=act)
+        m.codebook.embedding.weight.data.copy_(e.to(dev)); o.embedding.weight.data.copy_(e)
+        m.train(); o.train()
+        xg = x.to(dev).requires_grad_(True); xc = x.clone().requires_grad_(True)
+        a = m(xg); b = o(xc)
+        g = torch.Generator().manual_seed(7)
+        gs = torch.randn(b[1].shape, generator=g)
+        ((a[1] * gs.to(dev)).sum() + a[3].sum()).backward()
+        ((b[1] * gs).sum() + b[3].sum()).backward()
+        assert torch.equal(a[2].cpu(), b[2]) and torch.equal(a[0].detach().cpu(), b[0].detach())
+        assert rel_to_max(a[1].detach().cpu(), b[1].detach()) <= 1e-5
+        assert rel_to_max(xg.grad.cpu(), xc.grad) <= 1e-5
+        assert rel_to_max(m.codebook.embedding.weight.grad.cpu(), o.embedding.weight.grad) <= 1e-5

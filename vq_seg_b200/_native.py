@@ -43,9 +43,9 @@ SIGNATURES = {
     "vqseg_l2norm_rows_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, vp]),
     "vqseg_assign_cosine_f32": (ci, [vp, i64, i64, vp, i64, vp, vp, vp]),
     "vqseg_ema_update_f32": (ci, [vp, vp, vp, vp, vp, i64, i64, f32, f32, vp, vp]),
-    "vqseg_dist_map_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, ci, vp, i64, i64, i64, vp, vp, vp]),
+    "vqseg_dist_map_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, ci, vp, i64, i64, i64, vp, vp, vp, vp]),
     "vqseg_dist_map_bwd_f32": (ci, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, vp, i64,
-                                    vp, i64, i64, i64, vp, vp]),
+                                    vp, i64, i64, i64, vp, vp, vp]),
 }
 
 

@@ -59,7 +59,8 @@ template <int KMAX, bool COSINE>
 __global__ void __launch_bounds__(kDmThreads) dist_map_kernel(Rows x, const float* __restrict__ E, int K,
                                                              float* __restrict__ dist, long long oB, long long oP, long long oK,
                                                              long long* __restrict__ idx_out,
-                                                             unsigned long long* __restrict__ counts) {
+                                                             unsigned long long* __restrict__ counts,
+                                                             float* __restrict__ score) {
   extern __shared__ __align__(16) float dm_smem[];
   const int D = (int)x.D;
   float* s_e = dm_smem;                      // [K][D]
@@ -112,8 +113,10 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_kernel(Rows x, const floa
     float best = 0.f;
     int best_k = 0;
     float* dr = dist + b * oB + pp * oP;
+    float dk[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
+      dk[k] = 0.f;
       if (k < K) {
         float v;
         if (COSINE) {
@@ -127,7 +130,29 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_kernel(Rows x, const floa
           if (k == 0 || v < best) { best = v; best_k = k; }
         }
         dr[(long long)k * oK] = v;
+        dk[k] = v;
       }
+    }
+    if (!COSINE && score) {
+      // class scores of the Euclidean head: softmax_k(1 - d_k / sum_j d_j)   (vq_segmentation_head.py:245-247)
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) if (k < K) sum = __fadd_rn(sum, dk[k]);
+      float tk[KMAX], tmax = -3.0e38f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        tk[k] = (k < K) ? __fsub_rn(1.f, __fdiv_rn(dk[k], sum)) : -3.0e38f;
+        tmax = fmaxf(tmax, tk[k]);
+      }
+      float esum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        tk[k] = (k < K) ? expf(tk[k] - tmax) : 0.f;
+        esum += tk[k];
+      }
+      float* sr = score + b * oB + pp * oP;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) if (k < K) sr[(long long)k * oK] = tk[k] / esum;
     }
     if (idx_out) idx_out[n] = best_k;
     if (counts) atomicAdd(&s_cnt[best_k], 1);
@@ -146,7 +171,8 @@ template <int KMAX>
 __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const float* __restrict__ E, int K,
                                                                  const float* __restrict__ g, const float* __restrict__ dist,
                                                                  long long oB, long long oP, long long oK,
-                                                                 RowsOut gx, float* __restrict__ gE) {
+                                                                 RowsOut gx, float* __restrict__ gE,
+                                                                 const float* __restrict__ score) {
   extern __shared__ __align__(16) float dmb_smem[];
   const int D = (int)x.D;
   float* s_e = dmb_smem;                          // [K][D]
@@ -162,17 +188,42 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
   float wsum = 0.f;
   long long b = 0, pp = 0;
   if (in) { b = n / x.P; pp = n - b * x.P; }
+  {
+    float gk[KMAX], dv[KMAX];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    w[k] = 0.f;
-    if (k < K) {
-      if (in) {
+    for (int k = 0; k < KMAX; ++k) {
+      gk[k] = 0.f; dv[k] = 0.f;
+      if (in && k < K) {
         const long long o = b * oB + pp * oP + (long long)k * oK;
-        const float dv = __ldg(dist + o);
-        w[k] = dv == 0.f ? 0.f : __fdiv_rn(__ldg(g + o), dv);
+        dv[k] = __ldg(dist + o);
+        gk[k] = __ldg(g + o);
       }
-      s_w[k * kDmThreads + threadIdx.x] = w[k];
-      wsum += w[k];
+    }
+    if (score) {
+      // g arrives w.r.t. score = softmax_k(t), t_k = 1 - d_k / s, s = sum_j d_j:
+      //   g_t[k] = score_k (g_k - sum_j g_j score_j);   g_d[j] = -g_t[j] / s + (sum_k g_t[k] d_k) / s^2
+      float sc[KMAX], dot = 0.f, ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        sc[k] = (in && k < K) ? __ldg(score + b * oB + pp * oP + (long long)k * oK) : 0.f;
+        dot = fmaf(gk[k], sc[k], dot);
+        ssum += dv[k];
+      }
+      float gtd = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) { gk[k] = sc[k] * (gk[k] - dot); gtd = fmaf(gk[k], dv[k], gtd); }
+      const float inv = ssum != 0.f ? 1.f / ssum : 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) gk[k] = (gtd * inv - gk[k]) * inv;
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      w[k] = 0.f;
+      if (k < K) {
+        if (in) w[k] = dv[k] == 0.f ? 0.f : __fdiv_rn(gk[k], dv[k]);
+        s_w[k * kDmThreads + threadIdx.x] = w[k];
+        wsum += w[k];
+      }
     }
   }
   __syncthreads();
@@ -228,15 +279,15 @@ static bool dm_supported(long long K, long long D) {
 
 template <int KMAX>
 static int launch_dm(const Rows& x, const float* E, int K, bool cosine, float* dist, long long oB, long long oP, long long oK,
-                     long long* idx, unsigned long long* counts, cudaStream_t st) {
+                     long long* idx, unsigned long long* counts, float* score, cudaStream_t st) {
   const size_t smem = ((size_t)K * x.D + K + KMAX) * sizeof(float);
   const unsigned grid = (unsigned)((x.n_rows() + kDmThreads - 1) / kDmThreads);
   if (cosine) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(dist_map_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    dist_map_kernel<KMAX, true><<<grid, kDmThreads, smem, st>>>(x, E, K, dist, oB, oP, oK, idx, counts);
+    dist_map_kernel<KMAX, true><<<grid, kDmThreads, smem, st>>>(x, E, K, dist, oB, oP, oK, idx, counts, nullptr);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(dist_map_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    dist_map_kernel<KMAX, false><<<grid, kDmThreads, smem, st>>>(x, E, K, dist, oB, oP, oK, idx, counts);
+    dist_map_kernel<KMAX, false><<<grid, kDmThreads, smem, st>>>(x, E, K, dist, oB, oP, oK, idx, counts, score);
   }
   VQSEG_LAUNCH_CHECK();
   return 0;
@@ -244,11 +295,11 @@ static int launch_dm(const Rows& x, const float* E, int K, bool cosine, float* d
 
 template <int KMAX>
 static int launch_dm_bwd(const Rows& x, const float* E, int K, const float* g, const float* dist, long long oB, long long oP,
-                         long long oK, const RowsOut& gx, float* gE, cudaStream_t st) {
+                         long long oK, const RowsOut& gx, float* gE, const float* score, cudaStream_t st) {
   const size_t smem = ((size_t)K * x.D + (size_t)K * kDmThreads + KMAX + 32 * (kDmThreads + 1)) * sizeof(float);
   const unsigned grid = (unsigned)((x.n_rows() + kDmThreads - 1) / kDmThreads);
   if (smem > 48 * 1024) cudaFuncSetAttribute(dist_map_bwd_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  dist_map_bwd_kernel<KMAX><<<grid, kDmThreads, smem, st>>>(x, E, K, g, dist, oB, oP, oK, gx, gE);
+  dist_map_bwd_kernel<KMAX><<<grid, kDmThreads, smem, st>>>(x, E, K, g, dist, oB, oP, oK, gx, gE, score);
   VQSEG_LAUNCH_CHECK();
   return 0;
 }
@@ -262,8 +313,8 @@ extern "C" {
 int vqseg_dist_map_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                        const float* E, int64_t K, int cosine,
                        float* dist_out, int64_t oB, int64_t oP, int64_t oK,
-                       int64_t* idx_out, int64_t* counts_out, void* stream) {
-  if (!x || !E || !dist_out || B < 0 || P < 0) return VQSEG_EINVAL;
+                       int64_t* idx_out, int64_t* counts_out, float* score_out, void* stream) {
+  if (!x || !E || !dist_out || B < 0 || P < 0 || (cosine && score_out)) return VQSEG_EINVAL;
   if (!dm_supported(K, D)) return VQSEG_EUNSUPPORTED;
   int rc = check_arch();
   if (rc) return rc;
@@ -276,16 +327,17 @@ int vqseg_dist_map_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t 
   Rows xr{x, B, P, D, sB, sP, sD};
   long long* ix = (long long*)idx_out;
   unsigned long long* cn = (unsigned long long*)counts_out;
-  if (K <= 4) return launch_dm<4>(xr, E, (int)K, cosine != 0, dist_out, oB, oP, oK, ix, cn, st);
-  if (K <= 8) return launch_dm<8>(xr, E, (int)K, cosine != 0, dist_out, oB, oP, oK, ix, cn, st);
-  if (K <= 16) return launch_dm<16>(xr, E, (int)K, cosine != 0, dist_out, oB, oP, oK, ix, cn, st);
-  return launch_dm<32>(xr, E, (int)K, cosine != 0, dist_out, oB, oP, oK, ix, cn, st);
+  if (K <= 4) return launch_dm<4>(xr, E, (int)K, cosine != 0, dist_out, oB, oP, oK, ix, cn, score_out, st);
+  if (K <= 8) return launch_dm<8>(xr, E, (int)K, cosine != 0, dist_out, oB, oP, oK, ix, cn, score_out, st);
+  if (K <= 16) return launch_dm<16>(xr, E, (int)K, cosine != 0, dist_out, oB, oP, oK, ix, cn, score_out, st);
+  return launch_dm<32>(xr, E, (int)K, cosine != 0, dist_out, oB, oP, oK, ix, cn, score_out, st);
 }
 
 int vqseg_dist_map_bwd_f32(const float* g, const float* dist, int64_t oB, int64_t oP, int64_t oK,
                            const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                            const float* E, int64_t K,
-                           float* gx_out, int64_t gxB, int64_t gxP, int64_t gxD, float* gE_out, void* stream) {
+                           float* gx_out, int64_t gxB, int64_t gxP, int64_t gxD, float* gE_out,
+                           const float* score, void* stream) {
   if (!g || !dist || !x || !E || !gx_out || !gE_out || B < 0 || P < 0) return VQSEG_EINVAL;
   if (!dm_supported(K, D)) return VQSEG_EUNSUPPORTED;
   int rc = check_arch();
@@ -296,10 +348,10 @@ int vqseg_dist_map_bwd_f32(const float* g, const float* dist, int64_t oB, int64_
   if (B * P == 0) return 0;
   Rows xr{x, B, P, D, sB, sP, sD};
   RowsOut gx{gx_out, B, P, D, gxB, gxP, gxD};
-  if (K <= 4) return launch_dm_bwd<4>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, st);
-  if (K <= 8) return launch_dm_bwd<8>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, st);
-  if (K <= 16) return launch_dm_bwd<16>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, st);
-  return launch_dm_bwd<32>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, st);
+  if (K <= 4) return launch_dm_bwd<4>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, score, st);
+  if (K <= 8) return launch_dm_bwd<8>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, score, st);
+  if (K <= 16) return launch_dm_bwd<16>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, score, st);
+  return launch_dm_bwd<32>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, score, st);
 }
 
 }  // extern "C"

@@ -378,9 +378,9 @@ ema_update = torch.library.custom_op("vqseg::ema_update", mutates_args=("cluster
 
 # -------------------------------------------------------------------------------------------------
 # distance map of the VQ segmentation head (models/modules/vq_segmentation_head.py:167-176 / :104-111)
-def _dist_map_impl(x: torch.Tensor, codebook: torch.Tensor, cosine: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def _dist_map_raw(x, codebook, cosine=False, with_score=False):
     """x (B, P, D) view (any strides; for cosine: rows already l2-normalised), codebook (K, D).
-    Returns (dist (B, P, K) fp32 laid out as (B, K, P) in memory, idx (B, P) int64, counts (K,) int64)."""
+    Returns (dist (B, P, K) fp32 laid out as (B, K, P) in memory, idx (B, P) int64, counts (K,) int64, score or None)."""
     _require_cuda(x, codebook)
     L = _native.lib()
     if x.dtype != torch.float32:
@@ -396,14 +396,38 @@ def _dist_map_impl(x: torch.Tensor, codebook: torch.Tensor, cosine: bool = False
     dist = torch.empty_strided((b, p, k), (k * p, 1, p), dtype=torch.float32, device=dev)
     idx = torch.empty((b, p), dtype=torch.int64, device=dev)
     counts = torch.empty(k, dtype=torch.int64, device=dev)
+    score = torch.empty_strided((b, p, k), (k * p, 1, p), dtype=torch.float32, device=dev) if with_score else None
     with torch.cuda.device(dev):
         _native.check(L.vqseg_dist_map_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k, 1 if cosine else 0,
                                            dist.data_ptr(), dist.stride(0), dist.stride(1), dist.stride(2),
-                                           idx.data_ptr(), counts.data_ptr(), _stream()), "dist_map")
-    return dist, idx, counts
+                                           idx.data_ptr(), counts.data_ptr(),
+                                           score.data_ptr() if with_score else None, _stream()), "dist_map")
+    return dist, idx, counts, score
+
+
+def _dist_map_impl(x: torch.Tensor, codebook: torch.Tensor, cosine: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return _dist_map_raw(x, codebook, cosine, False)[:3]
 
 
 dist_map = torch.library.custom_op("vqseg::dist_map", mutates_args=())(_dist_map_impl)
+
+
+def _dist_score_map_impl(x: torch.Tensor, codebook: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Euclidean map plus the head's class scores softmax_k(1 - d_k / sum_j d_j) from the same kernel:
+    (dist, score, idx, counts), dist and score (B, P, K) laid out as (B, K, P)."""
+    dist, idx, counts, score = _dist_map_raw(x, codebook, False, True)
+    return dist, score, idx, counts
+
+
+dist_score_map = torch.library.custom_op("vqseg::dist_score_map", mutates_args=())(_dist_score_map_impl)
+
+
+@dist_score_map.register_fake
+def _(x, codebook):
+    b, p, d = x.shape
+    k = codebook.shape[0]
+    mk = lambda: torch.empty_strided((b, p, k), (k * p, 1, p), dtype=torch.float32, device=x.device)  # noqa: E731
+    return mk(), mk(), x.new_empty((b, p), dtype=torch.int64), x.new_empty((k,), dtype=torch.int64)
 
 
 @dist_map.register_fake
@@ -415,8 +439,9 @@ def _(x, codebook, cosine=False):
 
 
 def _dist_map_bwd_impl(grad: torch.Tensor, dist: torch.Tensor, x: torch.Tensor,
-                       codebook: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Backward of the Euclidean map (torch.cdist p=2): (gx with x's (B, P, D) shape in NCHW memory order, gE (K, D))."""
+                       codebook: torch.Tensor, score: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Backward of the Euclidean map (torch.cdist p=2): (gx with x's (B, P, D) shape in NCHW memory order, gE (K, D)).
+    With `score` (the saved class scores) `grad` is the gradient w.r.t. those scores instead."""
     _require_cuda(grad, dist, x, codebook)
     L = _native.lib()
     if x.dtype != torch.float32:
@@ -437,6 +462,7 @@ def _dist_map_bwd_impl(grad: torch.Tensor, dist: torch.Tensor, x: torch.Tensor,
         _native.check(L.vqseg_dist_map_bwd_f32(g.data_ptr(), dist.data_ptr(), dist.stride(0), dist.stride(1), dist.stride(2),
                                                x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
                                                gx.data_ptr(), gx.stride(0), gx.stride(1), gx.stride(2), ge.data_ptr(),
+                                               score.data_ptr() if score is not None else None,
                                                _stream()), "dist_map_bwd")
     return gx, ge
 
@@ -445,7 +471,7 @@ dist_map_bwd = torch.library.custom_op("vqseg::dist_map_bwd", mutates_args=())(_
 
 
 @dist_map_bwd.register_fake
-def _(grad, dist, x, codebook):
+def _(grad, dist, x, codebook, score=None):
     b, p, d = x.shape
     return (torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=x.device),
             codebook.new_empty(codebook.shape, dtype=torch.float32))
@@ -471,6 +497,28 @@ class _EuclideanDistMap(torch.autograd.Function):
 
 def euclidean_dist_map(x, weight):
     return _EuclideanDistMap.apply(x, weight)
+
+
+class _EuclideanScoreMap(torch.autograd.Function):
+    """The whole score path of the Euclidean head in one kernel each way: cdist -> 1 - d / sum(d) -> softmax
+    (vq_segmentation_head.py:167,243-247).  Differentiable output: score; idx / counts are not."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        dist, score, idx, counts = (_dist_score_map_impl if _fast() else dist_score_map)(x, weight)
+        ctx.save_for_backward(x, weight, dist, score)
+        ctx.mark_non_differentiable(idx, counts)
+        return score, idx, counts
+
+    @staticmethod
+    def backward(ctx, g_score, g_idx, g_counts):
+        x, weight, dist, score = ctx.saved_tensors
+        gx, ge = (_dist_map_bwd_impl if _fast() else dist_map_bwd)(g_score, dist, x, weight, score)
+        return (gx if ctx.needs_input_grad[0] else None), (ge if ctx.needs_input_grad[1] else None)
+
+
+def euclidean_score_map(x, weight):
+    return _EuclideanScoreMap.apply(x, weight)
 
 
 # -------------------------------------------------------------------------------------------------

@@ -138,7 +138,14 @@ class VQSegmentationHead(nn.Module):
         cb = self.codebook
         if xv.shape[-1] != cb.embedding_dim:
             raise RuntimeError(f"X1 and X2 must have the same number of columns. X1: {xv.shape[-1]} X2: {cb.embedding_dim}")
-        distance, embed_idx, counts = cb.lookup(xv)
+        # default configuration (Euclidean + Softmax2d): distances, normalisation and softmax in ONE kernel each way
+        fused = self.code_distance == "euclidean" and type(self.activation) is nn.Softmax2d
+        if fused:
+            if cb.kmeans_init and self.training:
+                cb._kmeans_init(xv, cosine=False)
+            score_bpk, embed_idx, counts = ops.euclidean_score_map(xv, cb.embedding.weight)
+        else:
+            distance, embed_idx, counts = cb.lookup(xv)
         code_usage = ops.fast_code_usage(counts)
         loss = torch.zeros(1, device=x.device, dtype=torch.float32, requires_grad=self.training)
         if self.training:
@@ -148,11 +155,14 @@ class VQSegmentationHead(nn.Module):
                 loss = loss + mse * self.commitment_weight
         else:
             quantize = ops.eval_gather(cb.embedding.weight, xv, embed_idx)      # one_hot @ weight (:170-171)
-        # distance is stored as (B, K, HW): 'b (h w) c -> b c h w' is a view of it
-        score = distance.permute(0, 2, 1).reshape(b, -1, h, w)
-        if self.code_distance == "euclidean":
-            score = 1 - (score / torch.sum(score, dim=1, keepdim=True))        # :245
-        score = self.activation(score)
+        # the maps are stored as (B, K, HW): 'b (h w) c -> b c h w' is a view of them
+        if fused:
+            score = score_bpk.permute(0, 2, 1).reshape(b, -1, h, w)
+        else:
+            score = distance.permute(0, 2, 1).reshape(b, -1, h, w)
+            if self.code_distance == "euclidean":
+                score = 1 - (score / torch.sum(score, dim=1, keepdim=True))    # :245
+            score = self.activation(score)
         quantize = quantize.permute(0, 2, 1).reshape(b, c, h, w)
         embed_index = embed_idx.reshape(b, h, w)
         return quantize, score, embed_index, loss, code_usage
