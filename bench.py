@@ -142,10 +142,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own version banner (NCCL_DEBUG=VERSION prints it to stdout)
-        # must not precede it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line.  NCCL_DEBUG=VERSION (set in the GPU image) does nothing but print
+        # "NCCL version ..." to stdout ahead of it: drop that level; WARN / INFO requests are left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.lib()
     args.warmup = max(args.warmup, 3)
