@@ -12,12 +12,20 @@
 namespace vqseg {
 
 // Logical (B, P, D) view with element strides; row n = b*P + p.
+// n = b * P + p with 0 <= p < P.  Row counts stay below 2^31 (checked on entry), so the common case is one 32-bit
+// division instead of the 64-bit software routine (fewer instructions; no measurable change in kernel time).
+__host__ __device__ inline void split_row(long long n, long long P, long long& b, long long& p) {
+  if (((unsigned long long)n | (unsigned long long)P) >> 32) { b = n / P; p = n - b * P; }
+  else { const unsigned q = (unsigned)n / (unsigned)P; b = q; p = (unsigned)n - q * (unsigned)P; }
+}
+
 struct Rows {
   const float* ptr;
   long long B, P, D, sB, sP, sD;
   __host__ __device__ inline long long n_rows() const { return B * P; }
   __device__ inline const float* row(long long n) const {
-    long long b = n / P, p = n - b * P;
+    long long b, p;
+    split_row(n, P, b, p);
     return ptr + b * sB + p * sP;
   }
 };
@@ -25,7 +33,8 @@ struct RowsOut {
   float* ptr;
   long long B, P, D, sB, sP, sD;
   __device__ inline float* row(long long n) const {
-    long long b = n / P, p = n - b * P;
+    long long b, p;
+    split_row(n, P, b, p);
     return ptr + b * sB + p * sP;
   }
 };

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
   const long long n = n0 + p4;
   if (VEC) {
     if (n < n_rows) {
-      const long long b = n / x.P, pp = n - b * x.P;
+      long long b, pp;
+      split_row(n, x.P, b, pp);
       const float* xb = kTrain ? x.ptr + b * x.sB + pp : nullptr;
       float* qb = q.ptr + b * q.sB + pp;
       float4 xr[kGTile / 8];
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
     for (int i = 0; i < 4; ++i) {
       const long long ni = n + i;
       if (ni < n_rows) {
-        const long long b = ni / x.P, pp = ni - b * x.P;
+        long long b, pp;
+        split_row(ni, x.P, b, pp);
         const float* xb = kTrain ? x.ptr + b * x.sB + pp * x.sP : nullptr;
         float* qb = q.ptr + b * q.sB + pp * q.sP;
         for (int d = warp; d < kGTile; d += 8) {
@@ -498,7 +500,8 @@ __global__ void __launch_bounds__(256) stats_ordered_sum_kernel(Rows x, const in
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int r = __shfl_sync(0xffffffffu, ids, min(16 * h + u, cnt - 1));     // unconditional loads, see above
-        const long long b = r / x.P, p = r - b * x.P;
+        long long b, p;
+        split_row(r, x.P, b, p);
         v[u] = __ldg(x.ptr + b * x.sB + p * x.sP + (long long)(act ? d : 0) * x.sD);
       }
 #pragma unroll

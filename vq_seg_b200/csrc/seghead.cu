@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_kernel(Rows x, const floa
   const long long n_rows = x.n_rows();
   const long long n = (long long)blockIdx.x * kDmThreads + threadIdx.x;
   if (n < n_rows) {
-    const long long b = n / x.P, pp = n - b * x.P;
+    long long b, pp;
+    split_row(n, x.P, b, pp);
     const float* xr = x.ptr + b * x.sB + pp * x.sP;
     TorchSumSq sq;
     sq.init();
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
   float w[KMAX];
   float wsum = 0.f;
   long long b = 0, pp = 0;
-  if (in) { b = n / x.P; pp = n - b * x.P; }
+  if (in) split_row(n, x.P, b, pp);
   {
     float gk[KMAX], dv[KMAX];
 #pragma unroll
