@@ -61,20 +61,23 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
   if (threadIdx.x < kGPix) {
     long long n = n0 + threadIdx.x;
     long long k = n < n_rows ? idx[n] : 0;
-    s_idx[threadIdx.x] = (int)(k < 0 ? 0 : (k >= K ? K - 1 : k));
+    // element offset of the code row (K * D < 2^31 is checked by the launcher): the gather below then needs one
+    // 32-bit add per load instead of a 64-bit multiply -- address arithmetic was a third of this kernel's instructions
+    s_idx[threadIdx.x] = (int)(k < 0 ? 0 : (k >= K ? K - 1 : k)) * D;
   }
   __syncthreads();
-  // phase 1: gather code row segments (256 B each), lanes along d
+  // phase 1: gather code row segments (128 B each), lanes along d
+  const float* Ed = E + d0 + lane;
 #pragma unroll 2
   for (int p0 = warp; p0 < kGPix; p0 += 64) {           // 16 loads in flight per lane before the smem stores
     float v[8][kGTile / 32];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float* er = E + (long long)s_idx[p0 + 8 * u] * D + d0;
+      const float* er = Ed + s_idx[p0 + 8 * u];
 #pragma unroll
       for (int h = 0; h < kGTile / 32; ++h) {
         const int d = lane + 32 * h;
-        v[u][h] = (d0 + d < D) ? __ldg(er + d) : 0.f;
+        v[u][h] = (d0 + d < D) ? __ldg(er + 32 * h) : 0.f;
       }
     }
 #pragma unroll
@@ -94,11 +97,14 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
       const float* xb = kTrain ? x.ptr + b * x.sB + pp : nullptr;
       float* qb = q.ptr + b * q.sB + pp;
       float4 xr[kGTile / 8];
-      if (kTrain) {                                        // all 8 row loads in flight before the first use
+      const float* xd = kTrain ? xb + (long long)(d0 + warp) * x.sD : nullptr;   // rows d0 + warp + 8u: pointer stepping
+      float* qd = qb + (long long)(d0 + warp) * q.sD;
+      const long long xstep = 8 * x.sD, qstep = 8 * q.sD;
+      if (kTrain) {                                        // all row loads in flight before the first use
 #pragma unroll
         for (int u = 0; u < kGTile / 8; ++u) {
           const int d = warp + 8 * u;
-          xr[u] = (d0 + d < D) ? __ldg(reinterpret_cast<const float4*>(xb + (long long)(d0 + d) * x.sD))
+          xr[u] = (d0 + d < D) ? __ldg(reinterpret_cast<const float4*>(xd + u * xstep))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
             f = __fsub_rn(o.x, xv.x); acc = __fmaf_rn(f, f, acc); f = __fsub_rn(o.y, xv.y); acc = __fmaf_rn(f, f, acc);
             f = __fsub_rn(o.z, xv.z); acc = __fmaf_rn(f, f, acc); f = __fsub_rn(o.w, xv.w); acc = __fmaf_rn(f, f, acc);
           }
-          *reinterpret_cast<float4*>(qb + (long long)(d0 + d) * q.sD) = o;
+          *reinterpret_cast<float4*>(qd + u * qstep) = o;
         }
       }
     }
@@ -229,7 +235,7 @@ static int launch_gather(const Rows& x, const float* E, int K, const long long* 
   // ticket (zeroed by the caller): the kernel's last block reduces the loss itself
   LossTail tail{want_loss ? ticket : nullptr, loss_out, 1.0 / ((double)n_rows * (double)x.D)};
   int n_partial = 0;
-  if (x.sP == 1 && q.sP == 1) {
+  if (x.sP == 1 && q.sP == 1 && (long long)K * x.D < (1ll << 31)) {
     dim3 grid((unsigned)((n_rows + kGPix - 1) / kGPix), (unsigned)((x.D + kGTile - 1) / kGTile));
     n_partial = (int)(grid.x * grid.y);
     if (want_loss && (size_t)n_partial > partial_cap) return VQSEG_EWORKSPACE;
