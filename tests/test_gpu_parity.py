@@ -487,3 +487,39 @@ def test_baseline_config_sizes_properties(dev):
     # the k-means start rows are samples: each is its own nearest code (distance exactly 0 up to fp32 cancellation)
     sub = x[:, :4096]
     assert torch.equal(ops.assign(sub, means, None, ops.ALGO_EXACT)[0], idx[:, :4096])
+
+
+def test_random_shape_fuzz(dev):
+    """40 random small problems (odd dims, single pixels, K from 1 to 700, row-major and NCHW views, train and eval):
+    the fused forward must agree with the brute-force exact scorer + a torch gather on the same device, and with the
+    CPU oracle's indices up to provable near-ties."""
+    from vq_seg_b200 import ops
+    rng = torch.Generator().manual_seed(1234)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=rng))     # noqa: E731
+    for it in range(40):
+        b, c, hw, k = ri(1, 3), ri(1, 300), ri(1, 700), ri(1, 700)
+        if it % 5 == 0:
+            hw = 128 * ri(1, 6)
+        x = torch.randn(b, c, hw, generator=rng)
+        e = torch.randn(k, c, generator=rng)
+        if it % 3 == 0:
+            x = torch.relu(x)
+        xd, ed = x.to(dev), e.to(dev)
+        xv = xd.permute(0, 2, 1)
+        if it % 4 == 1:
+            xv = xv.contiguous()                                               # row-major samples
+        blob = ops.prepare_codebook(ed)
+        i_ex, c_ex = ops.assign(xv, ed, None, ops.ALGO_EXACT)
+        for mode in (ops.MODE_TRAIN, ops.MODE_EVAL):
+            q, idx, mse, usage = ops.vq_forward(xv, ed, blob, mode, ops.ALGO_AUTO)
+            tag = (it, b, c, hw, k, mode)
+            assert torch.equal(idx, i_ex), tag
+            eq = ed[idx]
+            want = xv + (eq - xv) if mode == ops.MODE_TRAIN else eq
+            assert torch.equal(q, want), tag
+            assert abs(usage.item() - 100.0 * (c_ex == 0).sum().item() / k) < 1e-4, tag
+            if mode == ops.MODE_TRAIN:
+                ref = ((want - xv) ** 2).double().mean().item()
+                assert abs(mse.item() - ref) <= 1e-5 * max(ref, 1e-30), tag
+        ref_idx = O.assign_euclidean(xv.cpu(), e)
+        assert near_tie_ok(x.reshape(b, c, hw, 1), e, i_ex.cpu(), ref_idx), (it, b, c, hw, k)
