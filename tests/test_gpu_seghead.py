@@ -165,3 +165,34 @@ def test_seghead_other_activation_takes_the_unfused_path(dev):
         assert rel_to_max(a[1].detach().cpu(), b[1].detach()) <= 1e-5
         assert rel_to_max(xg.grad.cpu(), xc.grad) <= 1e-5
         assert rel_to_max(m.codebook.embedding.weight.grad.cpu(), o.embedding.weight.grad) <= 1e-5
+
+
+def test_seghead_random_shape_fuzz(dev):
+    """Random class counts (1..32), widths (1..382) and pixel counts: the map against the host arithmetic bit for
+    bit, its backward against CPU autograd through torch.cdist."""
+    from vq_seg_b200 import ops
+    rng = torch.Generator().manual_seed(99)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=rng))     # noqa: E731
+    for it in range(16):
+        b, c, hw, k = ri(2, 3), ri(1, 382), ri(1, 600), ri(1, 32)
+        if it == 0:
+            c, k = 382, 32
+        x = torch.relu(torch.randn(b, c, hw, generator=rng)) + 0.01
+        e = torch.rand(k, c, generator=rng)
+        xv = x.permute(0, 2, 1)
+        ref = cdist_ieee(xv, e)
+        xg = x.to(dev).requires_grad_(True)
+        eg = e.to(dev).requires_grad_(True)
+        dist, idx, counts = ops.euclidean_dist_map(xg.permute(0, 2, 1), eg)
+        assert torch.equal(dist.detach().cpu(), ref), (it, b, c, hw, k)
+        assert torch.equal(idx.cpu(), ref.argmin(-1)) and counts.sum().item() == b * hw
+        gd = torch.randn(ref.shape, generator=rng)
+        (dist * gd.to(dev)).sum().backward()
+        xc = x.clone().requires_grad_(True)
+        ec = e.clone().requires_grad_(True)
+        (torch.cdist(xc.permute(0, 2, 1).contiguous(), ec, p=2) * gd).sum().backward()
+        # pixels (almost) on a prototype make g / d ill-conditioned in fp32 on BOTH sides (the augmented form cancels):
+        # one-dimensional features produce such pairs, and both results are then ~1e-2 off an fp64 evaluation
+        tol = 2e-5 if ref.min().item() >= 0.1 else 1e-3
+        assert rel_to_max(xg.grad.cpu(), xc.grad) <= tol, (it, rel_to_max(xg.grad.cpu(), xc.grad))
+        assert rel_to_max(eg.grad.cpu(), ec.grad) <= tol, (it, rel_to_max(eg.grad.cpu(), ec.grad))
