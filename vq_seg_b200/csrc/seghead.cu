@@ -18,6 +18,7 @@
 namespace vqseg {
 
 constexpr int kDmThreads = 128;
+constexpr int kDmXStride = kDmThreads + 4;     // backward: row stride of the staged x tile (words)
 
 // fl(v*v) summed in ATen's vectorized_inner_sum order for D < 512 (no cascade spill): element j goes to
 // accumulator j % 32 for the first (D/32)*32 elements, leftover 8-vectors to accumulators 0..7, then
@@ -177,9 +178,9 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
   extern __shared__ __align__(16) float dmb_smem[];
   const int D = (int)x.D;
   float* s_e = dmb_smem;                          // [K][D]
-  float* s_w = s_e + K * D;                       // [K][128] weights of this block's pixels
+  float* s_w = s_e + ((K * D + 3) & ~3);          // [K][128] weights of this block's pixels (16-byte aligned rows)
   float* s_ws = s_w + K * kDmThreads;             // [K] sum_p w[k][p]
-  float* s_x = s_ws + KMAX;                       // [32][129] tile of x
+  float* s_x = s_ws + KMAX;                       // [32][kDmXStride] tile of x (16-byte aligned rows; KMAX % 4 == 0)
   for (int i = threadIdx.x; i < K * D; i += blockDim.x) s_e[i] = __ldg(E + i);
   const long long n_rows = x.n_rows();
   const long long n = (long long)blockIdx.x * kDmThreads + threadIdx.x;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
     __syncthreads();                               // previous chunk's tile fully consumed (and s_ws visible)
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
-      s_x[u * (kDmThreads + 1) + threadIdx.x] = xv[u];
+      s_x[u * kDmXStride + threadIdx.x] = xv[u];
       if (in && d0 + u < D) {
         float acc = xv[u] * wsum;                  // sum_k w_k (x - e_k) = x sum_k w_k - sum_k w_k e_k
 #pragma unroll
@@ -259,13 +260,15 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
     const int dd = lane;
     if (d0 + dd < D) {
       for (int k = warp; k < K; k += kDmThreads / 32) {
-        const float* wr = s_w + k * kDmThreads;
-        const float* xc = s_x + dd * (kDmThreads + 1);
+        // 128-bit reads: the weights are a broadcast, a tile row (stride 132 words) is conflict-free per quarter warp
+        const float4* wr = reinterpret_cast<const float4*>(s_w + k * kDmThreads);
+        const float4* xc = reinterpret_cast<const float4*>(s_x + dd * kDmXStride);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-        for (int p = 0; p < kDmThreads; p += 4) {
-          a0 = fmaf(wr[p], xc[p], a0); a1 = fmaf(wr[p + 1], xc[p + 1], a1);
-          a2 = fmaf(wr[p + 2], xc[p + 2], a2); a3 = fmaf(wr[p + 3], xc[p + 3], a3);
+        for (int p = 0; p < kDmThreads / 4; ++p) {
+          const float4 w4 = wr[p], x4 = xc[p];
+          a0 = fmaf(w4.x, x4.x, a0); a1 = fmaf(w4.y, x4.y, a1);
+          a2 = fmaf(w4.z, x4.z, a2); a3 = fmaf(w4.w, x4.w, a3);
         }
         const float r = s_e[k * D + d0 + dd] * s_ws[k] - ((a0 + a1) + (a2 + a3));
         if (r != 0.f) atomicAdd(gE + (long long)k * D + d0 + dd, r);
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
 }
 
 static bool dm_supported(long long K, long long D) {
-  return K >= 1 && K <= 32 && D >= 1 && D + 2 <= 384 && (K * D + K * 128 + 32 * 129 + 64) * 4 <= 96 * 1024;
+  return K >= 1 && K <= 32 && D >= 1 && D + 2 <= 384 && (K * D + K * 128 + 32 * 132 + 64) * 4 <= 96 * 1024;
 }
 
 template <int KMAX>
@@ -297,7 +300,7 @@ static int launch_dm(const Rows& x, const float* E, int K, bool cosine, float* d
 template <int KMAX>
 static int launch_dm_bwd(const Rows& x, const float* E, int K, const float* g, const float* dist, long long oB, long long oP,
                          long long oK, const RowsOut& gx, float* gE, const float* score, cudaStream_t st) {
-  const size_t smem = ((size_t)K * x.D + (size_t)K * kDmThreads + KMAX + 32 * (kDmThreads + 1)) * sizeof(float);
+  const size_t smem = ((size_t)((K * x.D + 3) & ~3) + (size_t)K * kDmThreads + KMAX + 32 * kDmXStride) * sizeof(float);
   const unsigned grid = (unsigned)((x.n_rows() + kDmThreads - 1) / kDmThreads);
   if (smem > 48 * 1024) cudaFuncSetAttribute(dist_map_bwd_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   dist_map_bwd_kernel<KMAX><<<grid, kDmThreads, smem, st>>>(x, E, K, g, dist, oB, oP, oK, gx, gE, score);
