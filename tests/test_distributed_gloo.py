@@ -60,6 +60,8 @@ def _worker(rank, world, port, results):
     sums = torch.zeros(32, 48).scatter_add_(0, buckets.unsqueeze(1).expand(-1, 48).contiguous(), flat[b:en])
     D.allreduce_code_stats(cnt, sums)
     out["stats"] = (cnt, sums)
+    # --- data-parallel EMA extension: the all-reduced statistics feed the same update on every rank
+    out["ema"] = O.ema_update(cnt, sums, torch.full((32,), 3.0), means0.clone(), 0.8, 1e-5)
     # --- identical k-means start on every rank from rank 0's global choice
     ids = torch.randperm(n, generator=torch.Generator().manual_seed(7 + rank))[:16]      # ranks DISAGREE on purpose
     rows = D.dp_init_means(flat[b:en].unsqueeze(0), b, ids,
@@ -99,6 +101,12 @@ def test_world2_gloo_modes():
     for r in (r0, r1):
         assert torch.equal(r["stats"][0], cnt)               # counts bit-exact for any rank count
         torch.testing.assert_close(r["stats"][1], sums, rtol=1e-5, atol=1e-5)
+    # EMA extension: both ranks end with the codebook a single process computes from all rows
+    cs_ref, ea_ref, w_ref = O.ema_update(cnt, sums, torch.full((32,), 3.0), flat[:32].clone(), 0.8, 1e-5)
+    for r in (r0, r1):
+        assert torch.equal(r["ema"][0], cs_ref)
+        torch.testing.assert_close(r["ema"][2], w_ref, rtol=1e-5, atol=1e-6)
+    assert torch.equal(r0["ema"][2], r1["ema"][2])
     # identical start, taken from rank 0's ids
     ids0 = torch.randperm(1200, generator=torch.Generator().manual_seed(7))[:16]
     assert torch.equal(r0["init"][1], flat[ids0]) and torch.equal(r1["init"][1], flat[ids0])
