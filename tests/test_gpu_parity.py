@@ -523,3 +523,15 @@ def test_random_shape_fuzz(dev):
                 assert abs(mse.item() - ref) <= 1e-5 * max(ref, 1e-30), tag
         ref_idx = O.assign_euclidean(xv.cpu(), e)
         assert near_tie_ok(x.reshape(b, c, hw, 1), e, i_ex.cpu(), ref_idx), (it, b, c, hw, k)
+
+
+def test_empty_batch(dev):
+    """A batch of zero images: empty outputs, zero loss, every code unused (usage 100 %), no kernel fault."""
+    import vq_seg_b200 as V
+    m = V.VectorQuantizer(dim=64, num_embeddings=128).to(dev)
+    for train in (True, False):
+        m.train(train)
+        q, idx, loss, usage = m(torch.zeros(0, 64, 8, 8, device=dev))
+        torch.cuda.synchronize()
+        assert q.shape == (0, 64, 8, 8) and idx.shape == (0, 8, 8) and idx.dtype == torch.int64
+        assert loss.item() == 0.0 and usage.item() == 100.0

@@ -256,14 +256,16 @@ int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
                          int64_t* idx_out, int64_t* counts_out, float* usage_out,
                          float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out,
                          int mode, int algo, int kblock, void* ws, size_t ws_bytes, void* stream) {
-  if (!idx_out || !counts_out || !q_out || K <= 0) return VQSEG_EINVAL;
+  if (!counts_out || K <= 0 || B < 0 || P < 0) return VQSEG_EINVAL;
+  if (B * P != 0 && (!idx_out || !q_out)) return VQSEG_EINVAL;   // (empty tensors have null data pointers)
   const size_t wa = (size_t)round_up(vqseg_assign_workspace_bytes(B * P, D, K, algo), 256);
-  if (!ws || ws_bytes < wa + vqseg_gather_workspace_bytes(B * P, D)) return VQSEG_EWORKSPACE;
+  if (B * P != 0 && (!ws || ws_bytes < wa + vqseg_gather_workspace_bytes(B * P, D))) return VQSEG_EWORKSPACE;
   if (B * P == 0) {                                              // nothing to launch: outputs of an empty batch
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(counts_out, 0, (size_t)K * sizeof(int64_t), st);
     if (e == cudaSuccess && loss_out) e = cudaMemsetAsync(loss_out, 0, sizeof(float), st);
-    return (int)e;
+    if (e != cudaSuccess) return (int)e;
+    return usage_out ? vqseg_code_usage(counts_out, K, usage_out, stream) : 0;     // no code is used: 100 %
   }
   int rc = assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, kblock, algo, ws, wa, stream,
                            usage_out, loss_out, true);   // one zeroing launch; usage reduced by the exact pass's last block
