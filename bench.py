@@ -86,6 +86,7 @@ def build_cpu_model(e):
     else:
         from oracle.vq_oracle import OracleVectorQuantizer
         m, kind = OracleVectorQuantizer(dim=C, num_embeddings=K), "port"
+        m.faithful_ops = True          # the reference's literal op sequence: cdist -> argmin -> one_hot -> matmul -> bincount
     m.codebook.embedding.weight.data.copy_(e)
     m.eval()
     return m, kind
