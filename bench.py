@@ -229,7 +229,8 @@ def main():
     # (which=0) and rescoring (which=1) kernels.  Captured into a second set of graphs so the kernels are timed
     # under the same launch conditions as the timed region (graph replay, ring of cold inputs).
     kt, rt = [], []
-    lib.vqseg_set_kernel_timing(1)
+    prof = _native.ProfileEvents()
+    ops.set_profile_events(prof)
     if graphs:
         pgraphs = []
         for i in range(args.ring):
@@ -240,16 +241,16 @@ def main():
         for i in range(64):
             pgraphs[i % args.ring].replay()
             torch.cuda.synchronize()
-            kt.append(lib.vqseg_get_kernel_timing_ms(0))
-            rt.append(lib.vqseg_get_kernel_timing_ms(1))
+            kt.append(prof.filter_ms())
+            rt.append(prof.rescore_ms())
     kt = [v for v in kt if v > 0]
     if not kt:                                   # eager fallback
         for i in range(64):
             step_eager(i)
             torch.cuda.synchronize()
-            kt.append(lib.vqseg_get_kernel_timing_ms(0))
-            rt.append(lib.vqseg_get_kernel_timing_ms(1))
-    lib.vqseg_set_kernel_timing(0)
+            kt.append(prof.filter_ms())
+            rt.append(prof.rescore_ms())
+    ops.set_profile_events(None)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     global_usage = None

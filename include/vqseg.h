@@ -10,8 +10,8 @@
  *   - every function returns 0 on success, a positive cudaError_t, or a negative VQSEG_E* code;
  *   - all pointers are DEVICE pointers unless the name ends in _host; tensors stay owned by the
  *     caller, the kernels borrow them;
- *   - no cudaMalloc, no host synchronisation and no global state inside (except cached
- *     cudaFuncSetAttribute calls); everything is enqueued on `stream`;
+ *   - no cudaMalloc, no host synchronisation and no global state inside (except per-device caches of
+ *     cudaFuncSetAttribute calls / the SM count); everything is enqueued on `stream`;
  *   - latent vectors are described as a logical (B, P, D) array with ELEMENT strides
  *     (sB, sP, sD): NCHW feature maps are (B, H*W, C) with sB=C*H*W, sP=1, sD=H*W (the view made
  *     by `rearrange(x,'b c h w -> b (h w) c')`, vq_img.py:232); packed row-major samples are
@@ -38,7 +38,11 @@ extern "C" {
 /* assign algorithms */
 #define VQSEG_ALGO_AUTO   0          /* tensor-core filter + exact rescoring when the shape allows */
 #define VQSEG_ALGO_EXACT  1          /* exact fp32 scorer on every (row, code) pair                */
-#define VQSEG_ALGO_TC     2          /* tcgen05 fp16 filter + exact fp32 rescoring (error if unsupported) */
+#define VQSEG_ALGO_TC     2          /* tcgen05 fp16 filter + exact fp32 rescoring; the kernel is chosen by shape/layout: */
+#define VQSEG_ALGO_TC_STREAM 3       /*   ... the single-CTA streaming kernel (any K, D, strides)                  */
+#define VQSEG_ALGO_TC_PAIR   4       /*   ... the codebook-resident CTA-pair kernel, x through registers (any strides) */
+#define VQSEG_ALGO_TC_TMA    5       /*   ... the codebook-resident CTA-pair kernel, x by TMA tensor loads (NCHW maps) */
+/* 3-5 force one kernel (VQSEG_EUNSUPPORTED if the shape does not fit it): the tests cover all three on the same inputs */
 
 /* gather modes */
 #define VQSEG_MODE_EVAL        0     /* quantize = E[idx]                          (vq_img.py:170)     */
@@ -47,22 +51,6 @@ extern "C" {
 #define VQSEG_MODE_EVAL_AMP    3
 
 int         vqseg_version(void);
-/* profiling aid for bench.py: when enabled, vqseg_assign_f32 brackets its kernels with CUDA events on
- * the launching stream; which = 0 -> tcgen05 filter kernel, 1 -> exact rescoring kernel.  The getter
- * synchronises on the events of the LAST call and returns milliseconds (< 0 if nothing recorded).   */
-void        vqseg_set_kernel_timing(int enable);
-float       vqseg_get_kernel_timing_ms(int which);
-/* developer tool: per-CTA clock64 stamps of the tcgen05 kernel's pipeline roles into a device buffer
- * of n_ctas * 4 * 256 int64 (null disables).                                                      */
-void        vqseg_debug_set_trace(void* dev_buf);
-/* developer tool: 1 -> always use the streaming single-CTA tcgen05 kernel, even when the codebook-resident
- * CTA-pair kernel applies (lets the tests cover both on the same shapes).                              */
-void        vqseg_debug_force_streaming_kernel(int on);
-/* developer micro-benchmark: global->register bandwidth of the producer access patterns (csrc/debug_bw.cu) */
-/* developer micro-benchmark: fixed cost of an empty launch with the tcgen05 kernels' launch geometry */
-int         vqseg_debug_null_launch(int kind, void* stream);
-int         vqseg_debug_load_bandwidth(const float* x, int64_t n_floats, int64_t row_stride, int pattern, int depth,
-                                       float* sink, void* stream);
 const char* vqseg_error_string(int code);
 
 /* ---- codebook preparation --------------------------------------------------------------------
@@ -70,7 +58,11 @@ const char* vqseg_error_string(int code);
  * (ATen _euclidean_dist, reached from vq_img.py:167 and :39).  Fills an opaque, reusable
  * "prepared codebook" blob: fp32 |e_k|^2 in torch's CPU summation order, max |e_k|, the fp16
  * power-of-two prescale and the fp16 (-2 * s * E) image laid out as tcgen05 SWIZZLE_128B K-major
- * shared-memory tiles (one bulk copy per pipeline stage).  Must be re-run whenever E changes.  */
+ * shared-memory tiles (one bulk copy per pipeline stage), and a 64-bit fingerprint per code row.
+ * The blob is a CACHE: every assignment that is given one first compares those fingerprints with
+ * the live E (its prologue kernel) and rebuilds the blob in place when a row changed, so results
+ * never depend on a stale image (weight.data.copy_ / mul_ do not bump torch's version counter).
+ * Re-running this after a known change just moves the rebuild off the assignment's critical path. */
 size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D);
 int    vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D,
                                   void* blob, size_t blob_bytes, void* stream);
@@ -88,10 +80,12 @@ int    vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D,
 size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int algo);
 int    vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D,
                         int64_t sB, int64_t sP, int64_t sD,
-                        const float* E, int64_t K, const void* blob,
+                        const float* E, int64_t K, void* blob,
                         int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
                         int64_t code_base, int kblock, int algo,
-                        void* ws, size_t ws_bytes, void* stream);
+                        void* ws, size_t ws_bytes, void* stream, void* const* prof_events);
+/* prof_events (nullable): four cudaEvent_t owned by the caller; the call records [0],[1] around the tensor-core
+ * filter kernel and [2],[3] around the rescoring kernel on `stream` (bench.py's roofline line).  No library state. */
 
 /* unpack the keys of the sharded mode after the cross-rank min: idx = key & 0xffffffff           */
 int    vqseg_unpack_keys(const uint64_t* keys, int64_t n, int64_t* idx_out, float* dist_out,
@@ -116,10 +110,11 @@ int    vqseg_gather_ste_f32(const float* x, int64_t B, int64_t P, int64_t D,
 size_t vqseg_forward_workspace_bytes(int64_t n_rows, int64_t D, int64_t K);
 int    vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D,
                             int64_t sB, int64_t sP, int64_t sD,
-                            const float* E, int64_t K, const void* blob,
+                            const float* E, int64_t K, void* blob,
                             int64_t* idx_out, int64_t* counts_out, float* usage_out,
                             float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out,
-                            int mode, int algo, int kblock, void* ws, size_t ws_bytes, void* stream);
+                            int mode, int algo, int kblock, void* ws, size_t ws_bytes, void* stream,
+                            void* const* prof_events);
 
 /* ---- backward of the training forward w.r.t. x -----------------------------------------------
  * Replaces autograd through vq_img.py:236-240:  gx = g_q + coef * (x - q_ste), with

@@ -414,8 +414,10 @@ def stage_stats():
 
 
 def stage_trace():
-    from vq_seg_b200 import _native
-    L = _native.lib()
+    """clock64 / globaltimer stamps of the pipeline roles of the TMA-fed pair kernel (developer build of the library)"""
+    from vq_seg_b200 import _native, build
+    build.build(dev=True)
+    L = _native.use_dev_library()
     x, e = cases.FORWARD_CASES["c2_randn"]()
     xd, ed = x.to(dev), e.to(dev)
     xv = view(xd)
@@ -429,29 +431,23 @@ def stage_trace():
     torch.cuda.synchronize()
     L.vqseg_debug_set_trace(None)
     ex = buf[-8:].cpu()
-    print('rescoring kernel: globaltimer span us', (ex[1] - ex[0]).item() / 1e3, 'rows', ex[7].item(), 'mean cycles per row: rowid', ex[2].item() // max(ex[7].item(), 1), 'wave2', ex[3].item() // max(ex[7].item(), 1), 'wave3', ex[4].item() // max(ex[7].item(), 1), 'xnorm', ex[5].item() // max(ex[7].item(), 1), 'chain', ex[6].item() // max(ex[7].item(), 1))
+    print('rescoring kernel: globaltimer span us', (ex[1] - ex[0]).item() / 1e3)
     t = buf[:-8].cpu().reshape(148, 4, 256)
     torch.save(t, os.path.join(ROOT, "gpurun_out", "trace.pt"))
-    g = t[:, 3, :8]
+    g = t[:, 3, 240:248]
     g0 = g[:, 0].min().item()
-    print("globaltimer (ns since first CTA entry): entry min/max", (g[:, 0] - g0).min().item(), (g[:, 0] - g0).max().item(),
-          "| setup done min/max", (g[:, 1] - g0).min().item(), (g[:, 1] - g0).max().item(),
-          "| roles done (thread 0) min/max", (g[:, 2] - g0).min().item(), (g[:, 2] - g0).max().item(),
-          "| exit min/max", (g[:, 3] - g0).min().item(), (g[:, 3] - g0).max().item())
-    print("cta0 clocks: entry->setup", (g[0, 5] - g[0, 4]).item(), "setup->rolesdone(t0)", (g[0, 6] - g[0, 5]).item(), "teardown", (g[0, 7] - g[0, 6]).item())
-    L.vqseg_set_kernel_timing(1)
-    ops.assign(xv, ed, blob, ops.ALGO_TC); torch.cuda.synchronize()
-    print("event-timed filter kernel us:", L.vqseg_get_kernel_timing_ms(0) * 1e3)
-    L.vqseg_set_kernel_timing(0)
-    for cta in (0, 100):
+    for nm, col in (("entry", 0), ("setup done", 2), ("roles done (thread 0)", 4), ("exit", 6)):
+        v = g[:, col] - g0
+        print(f"globaltimer ns since first CTA entry: {nm:24s} min {v.min().item():7d} median {v.median().item():7d} max {v.max().item():7d}")
+    for cta in (0, 1, 100, 147):
         tt = t[cta].clone()
-        tt[3, :8] = 0
-        t0 = tt[tt > 0].min().item()
-        names = ["producer(w0)", "mma", "epilogue(q0)", "bloader"]
+        c0 = tt[3, 241].item()
+        print(f"cta {cta}: clocks entry->setup {tt[3, 243].item() - c0}, ->roles done {tt[3, 245].item() - c0}, ->exit {tt[3, 247].item() - c0}")
+        names = ["converter(w0)", "mma", "epilogue(w8)", "x loaders"]
         for role in range(4):
-            row = tt[role]
-            ev = [(i, row[i].item() - t0) for i in range(256) if row[i] > 0]
-            print(f"cta {cta} {names[role]}: " + " ".join(f"{i}:{v}" for i, v in ev))
+            row = tt[role, :240]
+            ev = [(i, row[i].item() - c0) for i in range(240) if row[i] > 0]
+            print(f"  {names[role]}: " + " ".join(f"{i}:{v}" for i, v in ev))
 
 
 if __name__ == "__main__":

@@ -56,22 +56,24 @@ def test_assign_matches_golden(dev, golden, name, algo):
     assert torch.equal(counts.cpu(), rec["counts"])
 
 
+@pytest.mark.parametrize("kernel", ["stream", "pair", "tma"])
 @pytest.mark.parametrize("name", ["c2_randn", "c2_relu", "d64", "odd_7x7", "k_not_tile", "dup_codes", "equidistant", "x_equals_code"])
-def test_streaming_kernel_on_resident_shapes(dev, golden, name):
-    """Shapes that normally take the CTA-pair codebook-resident kernel, forced through the single-CTA
-    streaming tcgen05 kernel: both must reproduce the reference indices."""
-    from vq_seg_b200 import ops, _native
+def test_every_tensor_core_kernel_on_resident_shapes(dev, golden, name, kernel):
+    """Shapes that fit the codebook-resident kernels, forced through each of the three tcgen05 filters in turn
+    (single-CTA streaming, CTA pair fed through registers, CTA pair fed by TMA): all must reproduce the reference."""
+    from vq_seg_b200 import ops
     x, e = cases.FORWARD_CASES[name]()
     rec = golden["forward"][name]
     xd, ed = x.to(dev), e.to(dev)
     blob = ops.prepare_codebook(ed)
-    L = _native.lib()
-    L.vqseg_debug_force_streaming_kernel(1)
-    try:
-        idx, counts = ops.assign(view(xd), ed, blob, ops.ALGO_TC)
-        torch.cuda.synchronize()
-    finally:
-        L.vqseg_debug_force_streaming_kernel(0)
+    algo = {"stream": ops.ALGO_TC_STREAM, "pair": ops.ALGO_TC_PAIR, "tma": ops.ALGO_TC_TMA}[kernel]
+    if kernel == "tma" and (x.shape[2] * x.shape[3]) % 4 != 0:
+        # a tensor map needs 16-byte strides: such maps are refused when forced (ALGO_TC / AUTO take the register-fed kernel)
+        with pytest.raises(RuntimeError, match="not supported"):
+            ops.assign(view(xd), ed, blob, algo)
+        return
+    idx, counts = ops.assign(view(xd), ed, blob, algo)
+    torch.cuda.synchronize()
     assert torch.equal(idx.cpu(), rec["idx"].reshape(idx.shape).to(torch.int64))
     assert torch.equal(counts.cpu(), rec["counts"])
 

@@ -33,14 +33,15 @@ def test_error_strings_and_sizes(native):
     assert b"workspace" in lib.vqseg_error_string(-2)
     assert b"sm_100" in lib.vqseg_error_string(-4)
     # blob = header + 2*K_pad fp32 norms + fp16 image of K_pad x D_pad + one 4 KiB |e|^2 limb tile per 128 codes
-    assert lib.vqseg_codebook_blob_bytes(512, 256) == 1024 + 4096 + 512 * 256 * 2 + 4 * 4096
-    assert lib.vqseg_codebook_blob_bytes(300, 100) == 1024 + 4096 + 512 * 128 * 2 + 4 * 4096
-    assert lib.vqseg_assign_workspace_bytes(32768, 256, 512, 0) >= 32768 * (4 + 4 + 32)
+    #        + one 64-bit fingerprint per code row (the codebook guard)
+    assert lib.vqseg_codebook_blob_bytes(512, 256) == 1024 + 4096 + 512 * 256 * 2 + 4 * 4096 + 4096
+    assert lib.vqseg_codebook_blob_bytes(300, 100) == 1024 + 4096 + 512 * 128 * 2 + 4 * 4096 + 4096
+    assert lib.vqseg_assign_workspace_bytes(32768, 256, 512, 0) >= 32768 * 48        # one 48-byte work record per row
     assert lib.vqseg_code_stats_workspace_bytes(1000, 64, 32, 0) == 256
 
 
 def test_sass_is_blackwell_native():
-    """The shipped .so must contain tcgen05 / TMEM / bulk-copy SASS (UTCHMMA, LDTM, UBLKCP)."""
+    """The shipped .so must contain tcgen05 / TMEM / bulk-copy / TMA tensor-load SASS (UTCHMMA, LDTM, UBLKCP, UTMALDG)."""
     import shutil
     import subprocess
     from vq_seg_b200 import build
@@ -48,9 +49,21 @@ def test_sass_is_blackwell_native():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "UTMALDG"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16" not in sass                       # no legacy mma.sync path
+
+
+def test_no_debug_symbols_in_the_product_library(native):
+    """Developer hooks (pipeline trace, micro-benchmarks) live in libvqseg_dev.so / scripts/dev, not in the product."""
+    import subprocess
+    from vq_seg_b200 import build
+    syms = subprocess.run(["nm", "-D", "--defined-only", build.LIB], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (vqseg_[a-z0-9_]+)", syms))
+    assert not [s for s in exported if "debug" in s or "kernel_timing" in s], exported
+    header = open(os.path.join(ROOT, "include", "vqseg.h")).read()
+    declared = set(re.findall(r"\b(vqseg_[a-z0-9_]+)\s*\(", header))
+    assert exported - declared <= {"vqseg_internal_gather_ticket"}, exported - declared
 
 
 def test_no_cpu_fallback():

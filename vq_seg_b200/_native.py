@@ -8,6 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqseg.so")
+DEV_LIB_PATH = os.path.join(_HERE, "libvqseg_dev.so")      # developer build (-DVQSEG_DEV): pipeline trace hooks, never shipped
 _lib = None
 
 i64, f32, vp, sz, ci = ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
@@ -16,22 +17,16 @@ i64, f32, vp, sz, ci = ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c
 SIGNATURES = {
     "vqseg_version": (ci, []),
     "vqseg_error_string": (ctypes.c_char_p, [ci]),
-    "vqseg_set_kernel_timing": (None, [ci]),
-    "vqseg_get_kernel_timing_ms": (f32, [ci]),
-    "vqseg_debug_set_trace": (None, [vp]),
-    "vqseg_debug_force_streaming_kernel": (None, [ci]),
-    "vqseg_debug_null_launch": (ci, [ci, vp]),
-    "vqseg_debug_load_bandwidth": (ci, [vp, i64, i64, ci, ci, vp, vp]),
     "vqseg_codebook_blob_bytes": (sz, [i64, i64]),
     "vqseg_codebook_prepare_f32": (ci, [vp, i64, i64, vp, sz, vp]),
     "vqseg_assign_workspace_bytes": (sz, [i64, i64, i64, ci]),
-    "vqseg_assign_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp]),
+    "vqseg_assign_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp, vp]),
     "vqseg_unpack_keys": (ci, [vp, i64, vp, vp, vp, i64, vp]),
     "vqseg_gather_workspace_bytes": (sz, [i64, i64]),
     "vqseg_gather_ste_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, i64, i64, i64, vp, ci, vp, sz, vp]),
     "vqseg_forward_workspace_bytes": (sz, [i64, i64, i64]),
     "vqseg_vq_forward_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64, vp,
-                                  ci, ci, ci, vp, sz, vp]),
+                                  ci, ci, ci, vp, sz, vp, vp]),
     "vqseg_ste_bwd_f32": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, f32,
                                vp, i64, i64, i64, i64, i64, i64, vp]),
     "vqseg_gather_bwd_codebook_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, vp]),
@@ -67,6 +62,43 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = handle
     return _lib
+
+
+def use_dev_library():
+    """scripts/gpu_dev.py only: bind the developer build (same ABI + vqseg_debug_set_trace) instead of the product .so."""
+    global _lib
+    handle = ctypes.CDLL(DEV_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype, fn.argtypes = res, args
+    handle.vqseg_debug_set_trace.restype, handle.vqseg_debug_set_trace.argtypes = None, [vp]
+    _lib = handle
+    return handle
+
+
+class ProfileEvents:
+    """Four caller-owned CUDA events handed to vqseg_assign_f32 / vqseg_vq_forward_f32 (`prof_events`): the call
+    records [0],[1] around the tensor-core filter kernel and [2],[3] around the rescoring kernel."""
+
+    def __init__(self):
+        import torch
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for e in self.events:
+            e.record()                      # torch creates the cudaEvent_t lazily, on the first record
+        torch.cuda.synchronize()
+        self.array = (vp * 4)(*[e.cuda_event for e in self.events])
+
+    def _ms(self, a, b):
+        try:                                # the caller has synchronised the stream / device
+            return self.events[a].elapsed_time(self.events[b])
+        except RuntimeError:
+            return -1.0
+
+    def filter_ms(self):
+        return self._ms(0, 1)
+
+    def rescore_ms(self):
+        return self._ms(2, 3)
 
 
 def check(rc: int, what: str = ""):

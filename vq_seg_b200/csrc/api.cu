@@ -1,29 +1,70 @@
 // C ABI entry points for codebook preparation and nearest-code assignment (see include/vqseg.h).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "codebook_prep.cuh"
 #include <string.h>
 
 namespace vqseg {
-constexpr int kCandCapHost = 8;
 
 __global__ void blob_init_kernel(BlobHeader* h, int K, int D, int K_pad, int D_pad, unsigned long long off_enorm,
-                                 unsigned long long off_image, unsigned long long off_aug) {
+                                 unsigned long long off_image, unsigned long long off_aug, unsigned long long off_hash) {
   h->off_aug = off_aug; h->aug_c = 1.f; h->flags = 0u; h->max_de2_bits = 0u;
   h->magic = kBlobMagic; h->K = K; h->D = D; h->K_pad = K_pad; h->D_pad = D_pad;
   h->scale = 1.f; h->max_enorm = 0.f; h->max_enorm_bits = 0u; h->max_abs_bits = 0u;
-  h->off_enorm = off_enorm; h->off_image = off_image;
+  h->off_enorm = off_enorm; h->off_image = off_image; h->off_hash = off_hash;
+  h->stale = 0u; h->ticket = 0u; h->rebuilds = 0u;
 }
 
 extern "C" int vqseg_internal_gather_ticket(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                                             const float* E, int64_t K, const int64_t* idx,
                                             float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out, int mode,
-                                            void* ws, size_t ws_bytes, void* stream, int* ticket);
+                                            void* ws, size_t ws_bytes, void* stream, int* ticket,
+                                            const int64_t* counts, float* usage_out);
 
-// one launch instead of three memset nodes at the head of the fused forward: per-code counts, the loss scalar and
-// the assignment's {work counter, block ticket}
-__global__ void forward_zero_kernel(unsigned long long* counts, int K, float* loss, int* work2) {
-  for (int k = threadIdx.x; k < K; k += blockDim.x) counts[k] = 0ull;
-  if (threadIdx.x == 0) { if (loss) *loss = 0.f; work2[0] = 0; work2[1] = 0; work2[2] = 0; }   // [2]: gather's loss ticket
+// Prologue of every assignment: ONE launch that
+//   (a) zeroes what the kernels behind it accumulate into -- the work counter and the tickets, and for the fused
+//       forward the per-code counts and the loss (three memset nodes cost 3 us more per step in a CUDA graph);
+//   (b) guards the prepared-codebook cache: `weight.data.copy_()` / `.data.mul_()` (k-means init, mean-teacher
+//       updates, vq_img.py:189) change the codebook without bumping the tensor version the host-side cache is keyed
+//       on, so every warp re-hashes code rows and compares with the fingerprints the blob was built from; the last
+//       block through (ticket) rebuilds the blob in place if any row differs.  One block, because a grid-wide
+//       rebuild needs grid barriers; it is the rare path (a rebuild per weight change, ~50 us at K=512, D=256).
+__global__ void __launch_bounds__(256) assign_prologue_kernel(unsigned long long* counts, int n_counts, float* loss, int* work4,
+                                                              const float* __restrict__ E, int K, int D, unsigned char* blob) {
+  if (blockIdx.x == 0) {
+    for (int k = threadIdx.x; k < n_counts; k += blockDim.x) counts[k] = 0ull;
+    if (threadIdx.x == 0) { if (loss) *loss = 0.f; work4[0] = 0; work4[1] = 0; work4[2] = 0; work4[3] = 0; }
+  }
+  if (!blob) return;
+  BlobHeader* hdr = reinterpret_cast<BlobHeader*>(blob);
+  const unsigned long long* hash = reinterpret_cast<const unsigned long long*>(blob + hdr->off_hash);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  bool differ = false;
+  for (int k = blockIdx.x * 8 + wib; k < K; k += gridDim.x * 8) {
+    const unsigned long long h = row_hash_warp(E + (long long)k * D, D, lane);
+    differ |= (h != hash[k]);
+  }
+  if (differ && lane == 0) atomicOr(&hdr->stale, 1u);
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&hdr->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const bool stale = *reinterpret_cast<volatile uint32_t*>(&hdr->stale) != 0u;
+  if (stale) {
+    if (threadIdx.x == 0) { hdr->flags = 0u; hdr->max_de2_bits = 0u; hdr->max_enorm_bits = 0u; hdr->max_abs_bits = 0u; }
+    __threadfence(); __syncthreads();
+    prep_enorm(E, K, D, hdr->K_pad, reinterpret_cast<float*>(blob + hdr->off_enorm), hdr,
+               reinterpret_cast<unsigned long long*>(blob + hdr->off_hash), wib, 8, lane);
+    __threadfence(); __syncthreads();
+    prep_pack(E, K, D, blob, threadIdx.x, blockDim.x);
+    __threadfence(); __syncthreads();
+    prep_rounding(E, K, D, blob, wib, 8, lane);
+    __threadfence(); __syncthreads();
+  }
+  if (threadIdx.x == 0) { hdr->ticket = 0u; hdr->stale = 0u; if (stale) hdr->rebuilds += 1u; }
 }
 
 // MKL's sgemm K-blocking as probed on the reference CPU path: one chain up to
@@ -34,42 +75,39 @@ static int auto_kblock(long long D) {
   if (L <= 768) return (int)((L + 1) / 2);
   return 384;
 }
+
+#ifdef VQSEG_DEV
+long long* g_dev_trace = nullptr;            // developer build only (libvqseg_dev.so): clock stamps of the pipeline roles
+#endif
+static long long* dev_trace() {
+#ifdef VQSEG_DEV
+  return g_dev_trace;
+#else
+  return nullptr;
+#endif
+}
 }  // namespace vqseg
 
 using namespace vqseg;
 
-static int g_timing = 0;
-static long long* g_trace = nullptr;
-static int g_force_tc1 = 0;
-static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-static int g_ev_valid[2] = {0, 0};
-static void ev_record(int i, cudaStream_t st) {
-  if (!g_timing || !g_ev[i]) return;
-  if (cudaEventRecord(g_ev[i], st) != cudaSuccess) (void)cudaGetLastError();   // never poison the launch checks
+// optional per-call profiling: the CALLER's four cudaEvent_t, recorded on `stream` around the filter ([0], [1]) and
+// the rescoring kernel ([2], [3]).  No library state.
+static void prof_record(void* const* ev, int i, cudaStream_t st) {
+  if (!ev || !ev[i]) return;
+  // inside a stream capture the record must be an EXTERNAL event node, or the event cannot be read after a replay
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { (void)cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+  const unsigned flags = cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault;
+  if (cudaEventRecordWithFlags((cudaEvent_t)ev[i], st, flags) != cudaSuccess) (void)cudaGetLastError();   // never poison the launch checks
 }
 
 extern "C" {
 
 int vqseg_version(void) { return VQSEG_VERSION; }
 
-void vqseg_debug_set_trace(void* dev_buf) { g_trace = (long long*)dev_buf; }
-void vqseg_debug_force_streaming_kernel(int on) { g_force_tc1 = on; }
-
-void vqseg_set_kernel_timing(int enable) {
-  g_timing = enable; g_ev_valid[0] = g_ev_valid[1] = 0;
-  if (enable)                               // created here, outside any stream capture
-    for (int i = 0; i < 4; ++i)
-      if (!g_ev[i] && cudaEventCreate(&g_ev[i]) != cudaSuccess) { (void)cudaGetLastError(); g_ev[i] = nullptr; }
-}
-
-float vqseg_get_kernel_timing_ms(int which) {
-  if (which < 0 || which > 1 || !g_ev_valid[which]) return -1.f;
-  float ms = -1.f;
-  if (!g_ev[2 * which] || !g_ev[2 * which + 1]) return -1.f;
-  if (cudaEventSynchronize(g_ev[2 * which + 1]) != cudaSuccess) { (void)cudaGetLastError(); return -1.f; }
-  if (cudaEventElapsedTime(&ms, g_ev[2 * which], g_ev[2 * which + 1]) != cudaSuccess) { (void)cudaGetLastError(); return -1.f; }
-  return ms;
-}
+#ifdef VQSEG_DEV
+void vqseg_debug_set_trace(void* dev_buf) { g_dev_trace = (long long*)dev_buf; }
+#endif
 
 const char* vqseg_error_string(int code) {
   switch (code) {
@@ -84,14 +122,16 @@ const char* vqseg_error_string(int code) {
 }
 
 static void blob_geometry(int64_t K, int64_t D, long long* K_pad, long long* D_pad, size_t* off_enorm, size_t* off_image,
-                          size_t* total, size_t* off_aug = nullptr) {
+                          size_t* total, size_t* off_aug = nullptr, size_t* off_hash = nullptr) {
   *K_pad = round_up(K, 256);
   *D_pad = round_up(D, kDChunk);
   *off_enorm = 1024;
   *off_image = *off_enorm + (size_t)round_up(2 * *K_pad * sizeof(float), 1024);
   size_t aug = *off_image + (size_t)(*K_pad / kCodeBlock) * (size_t)(*D_pad / kDChunk) * kTileBytes;
   if (off_aug) *off_aug = aug;
-  *total = aug + (size_t)(*K_pad / kCodeBlock) * 4096;
+  size_t hash = aug + (size_t)(*K_pad / kCodeBlock) * 4096;
+  if (off_hash) *off_hash = hash;
+  *total = hash + (size_t)round_up(*K_pad * sizeof(unsigned long long), 1024);
 }
 
 size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D) {
@@ -103,48 +143,32 @@ size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D) {
 
 int vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D, void* blob, size_t blob_bytes, void* stream) {
   if (!E || !blob || K <= 0 || D <= 0 || K >= (1ll << 30) || D >= (1ll << 20)) return VQSEG_EINVAL;
-  long long kp, dp; size_t oe, oi, tot, oa;
-  blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot, &oa);
+  long long kp, dp; size_t oe, oi, tot, oa, oh;
+  blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot, &oa, &oh);
   if (blob_bytes < tot) return VQSEG_EWORKSPACE;
   if ((reinterpret_cast<uintptr_t>(blob) & 1023) != 0) return VQSEG_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* b = (unsigned char*)blob;
-  blob_init_kernel<<<1, 1, 0, st>>>((BlobHeader*)b, (int)K, (int)D, (int)kp, (int)dp, oe, oi, oa);
+  blob_init_kernel<<<1, 1, 0, st>>>((BlobHeader*)b, (int)K, (int)D, (int)kp, (int)dp, oe, oi, oa, oh);
   VQSEG_LAUNCH_CHECK();
-  int rc = launch_enorm(E, (int)K, (int)D, (int)kp, (float*)(b + oe), (BlobHeader*)b, st);
+  int rc = launch_enorm(E, (int)K, (int)D, (int)kp, (float*)(b + oe), (BlobHeader*)b, (unsigned long long*)(b + oh), st);
   if (rc) return rc;
   return launch_pack(E, (int)K, (int)D, b, st);
 }
 
 size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int algo) {
   (void)D; (void)algo;
-  size_t b = 256;                                              // work counter
-  b += (size_t)round_up(n_rows * sizeof(int), 256);            // work_rows
-  b += (size_t)round_up(n_rows * sizeof(int), 256);            // cand_cnt
-  b += (size_t)round_up(n_rows * kCandCapHost * sizeof(int), 256);   // cand_idx
-  b += (size_t)round_up(round_up(K, 256) * sizeof(float), 256);      // enorm when no blob is given
+  size_t b = 256;                                                     // work counter + tickets
+  b += (size_t)round_up(n_rows * (long long)sizeof(WorkRec), 256);    // one record per undecided row (worst case: all)
+  b += (size_t)round_up(round_up(K, 256) * sizeof(float), 256);       // enorm when no blob is given
   return b;
 }
 
 static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
-                           const float* E, int64_t K, const void* blob,
+                           const float* E, int64_t K, void* blob,
                            int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
                            int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
-                           float* usage_out, float* zero_loss = nullptr, bool zero_outputs = false);
-
-int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
-                     const float* E, int64_t K, const void* blob,
-                     int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
-                     int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream) {
-  return assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, best_key_out, code_base, kblock, algo,
-                         ws, ws_bytes, stream, nullptr);
-}
-
-static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
-                           const float* E, int64_t K, const void* blob,
-                           int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
-                           int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
-                           float* usage_out, float* zero_loss, bool zero_outputs) {
+                           void* const* prof_events, float* zero_loss, bool zero_counts) {
   if (!x || !E || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
   if (!idx_out && !best_key_out) return VQSEG_EINVAL;
   const long long n_rows = B * P;
@@ -157,34 +181,35 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   if (kblock == 0) kblock = auto_kblock(D);
 
   char* p = (char*)ws;
-  int* work_count = (int*)p;   p += 256;
-  int* work_rows = (int*)p;    p += round_up(n_rows * sizeof(int), 256);
-  int* cand_cnt = (int*)p;     p += round_up(n_rows * sizeof(int), 256);
-  int* cand_idx = (int*)p;     p += round_up(n_rows * kCandCapHost * sizeof(int), 256);
+  int* work_count = (int*)p;   p += 256;                       // [0] undecided rows, [1] spare, [2] gather ticket, [3] spare
+  WorkRec* work = (WorkRec*)p; p += round_up(n_rows * (long long)sizeof(WorkRec), 256);
   float* enorm_ws = (float*)p;
 
-  const BlobHeader* hdr = (const BlobHeader*)blob;
+  bool use_tc = false;
+  if (algo == VQSEG_ALGO_AUTO) use_tc = blob != nullptr && n_rows >= 64 && K >= 32;
+  else if (algo == VQSEG_ALGO_EXACT) use_tc = false;
+  else if (algo >= VQSEG_ALGO_TC && algo <= VQSEG_ALGO_TC_TMA) { if (!blob) return VQSEG_EINVAL; use_tc = true; }
+  else return VQSEG_EINVAL;
+
+  // prologue: zeroing + (when a prepared codebook is used) the guard that rebuilds a stale blob in place
+  {
+    const int guard_blocks = use_tc ? (int)((K + 7) / 8 < 2 * num_sms() ? (K + 7) / 8 : 2 * num_sms()) : 1;
+    assign_prologue_kernel<<<guard_blocks, 256, 0, st>>>(zero_counts ? (unsigned long long*)counts_out : nullptr,
+                                                         zero_counts ? (int)K : 0, zero_loss, work_count, E, (int)K, (int)D,
+                                                         use_tc ? (unsigned char*)blob : nullptr);
+    VQSEG_LAUNCH_CHECK();
+  }
+
   const float* enorm = nullptr;
   long long kp = 0, dp = 0;
   size_t oe = 0, oi = 0, tot = 0, oa = 0;
-  if (blob) {
+  if (use_tc) {
     blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot, &oa);
     enorm = (const float*)((const char*)blob + oe);
   } else {
-    rc = launch_enorm(E, (int)K, (int)D, (int)K, enorm_ws, nullptr, st);
+    rc = launch_enorm(E, (int)K, (int)D, (int)K, enorm_ws, nullptr, nullptr, st);
     if (rc) return rc;
     enorm = enorm_ws;
-  }
-  (void)hdr;
-
-  bool use_tc = false;
-  if (algo == VQSEG_ALGO_TC) {
-    if (!blob) return VQSEG_EINVAL;
-    use_tc = true;
-  } else if (algo == VQSEG_ALGO_AUTO) {
-    use_tc = blob != nullptr && n_rows >= 64 && K >= 32;
-  } else if (algo != VQSEG_ALGO_EXACT) {
-    return VQSEG_EINVAL;
   }
 
   Rows xr{x, B, P, D, sB, sP, sD};
@@ -193,33 +218,40 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   ea.x = xr; ea.E = E; ea.K = (int)K; ea.enorm = enorm; ea.kblock = kblock;
   ea.idx_out = (long long*)idx_out; ea.counts_out = (unsigned long long*)counts_out;
   ea.key_out = (unsigned long long*)best_key_out; ea.code_base = code_base;
-  ea.done_blocks = work_count + 1;
-  ea.usage_out = counts_out ? usage_out : nullptr;
-  if (zero_outputs) {                                            // fused forward: counts + loss + work counter + ticket
-    forward_zero_kernel<<<1, 256, 0, st>>>((unsigned long long*)counts_out, (int)K, zero_loss, work_count);
-    VQSEG_LAUNCH_CHECK();
-  } else {
-    cudaError_t e0 = cudaMemsetAsync(work_count, 0, 2 * sizeof(int), st);      // work counter + block ticket
-    if (e0 != cudaSuccess) return (int)e0;
-  }
-
   if (!use_tc) return launch_exact(ea, n_rows, st);
 
-  const float tau = 0.00390625f * 1.015625f;   // 2^-8 (two fp16 roundings per operand pair, both sides) + margin
   const int n_cc = (int)(kp / 256), n_dc = (int)(dp / kDChunk);
   const bool force = (best_key_out != nullptr || idx_out == nullptr);
-  ev_record(0, st);
-  if (tc2_supported(n_cc, n_dc) && g_force_tc1 == 0) {
+  const bool can3 = tc3_supported(xr, n_cc, n_dc), can2 = tc2_supported(n_cc, n_dc);
+  int kernel = can3 ? 3 : (can2 ? 2 : 1);
+  if (algo == VQSEG_ALGO_TC_STREAM) kernel = 1;
+  if (algo == VQSEG_ALGO_TC_PAIR) { if (!can2) return VQSEG_EUNSUPPORTED; kernel = 2; }
+  if (algo == VQSEG_ALGO_TC_TMA) { if (!can3) return VQSEG_EUNSUPPORTED; kernel = 3; }
+  prof_record(prof_events, 0, st);
+  if (kernel == 3) {
+    Tc3Args t3;
+    memset(&t3, 0, sizeof(t3));
+    t3.B = B; t3.P = P; t3.D = D; t3.n_rows = n_rows; t3.blob = (const unsigned char*)blob;
+    t3.tiles_per_image = (int)((P + 127) / 128);
+    t3.n_tiles = (int)(B * t3.tiles_per_image);
+    t3.n_ptiles = (t3.n_tiles + 1) / 2; t3.n_cc = n_cc; t3.n_dc = n_dc;
+    t3.K = (int)K; t3.K_pad = (int)kp; t3.off_image = oi; t3.off_aug = oa; t3.off_enorm = oe;
+    t3.idx_out = (long long*)idx_out; t3.counts_out = (unsigned long long*)counts_out; t3.code_base = code_base;
+    t3.force_rescore = force ? 1 : 0;
+    t3.work = work; t3.work_count = work_count;
+    t3.trace = dev_trace();
+    rc = launch_assign_tc3(xr, t3, st);
+  } else if (kernel == 2) {
     Tc2Args t2;
     memset(&t2, 0, sizeof(t2));
     t2.x = xr; t2.blob = (const unsigned char*)blob; t2.n_rows = n_rows;
     t2.n_ptiles = (int)((n_rows + 255) / 256); t2.n_cc = n_cc; t2.n_dc = n_dc;
     t2.K = (int)K; t2.K_pad = (int)kp; t2.off_image = oi; t2.off_aug = oa; t2.off_enorm = oe;
-    t2.tau = tau;
+    t2.tau = 0.f;
     t2.idx_out = (long long*)idx_out; t2.counts_out = (unsigned long long*)counts_out; t2.code_base = code_base;
     t2.force_rescore = force ? 1 : 0;
-    t2.cand_idx = cand_idx; t2.cand_cnt = cand_cnt; t2.work_rows = work_rows; t2.work_count = work_count;
-    t2.trace = g_trace;
+    t2.work = work; t2.work_count = work_count;
+    t2.trace = dev_trace();
     rc = launch_assign_tc2(t2, st);
   } else {
     TcArgs ta;
@@ -227,24 +259,30 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     ta.x = xr; ta.blob = (const unsigned char*)blob; ta.n_rows = n_rows;
     ta.n_tiles = (int)((n_rows + 127) / 128); ta.n_cc = n_cc; ta.n_dc = n_dc;
     ta.K = (int)K;
-    ta.tau = tau;
+    ta.tau = 0.f;
     ta.idx_out = (long long*)idx_out; ta.counts_out = (unsigned long long*)counts_out; ta.code_base = code_base;
     ta.force_rescore = force ? 1 : 0;
-    ta.cand_idx = cand_idx; ta.cand_cnt = cand_cnt; ta.work_rows = work_rows; ta.work_count = work_count;
-    ta.trace = g_trace;
+    ta.work = work; ta.work_count = work_count;
+    ta.trace = dev_trace();
     rc = launch_assign_tc(ta, st);
   }
-  ev_record(1, st);
+  prof_record(prof_events, 1, st);
   if (rc) return rc;
-  if (g_timing) g_ev_valid[0] = 1;
-  ea.work_rows = work_rows; ea.work_count = work_count;
-  ea.cand_idx = cand_idx; ea.cand_cnt = cand_cnt; ea.cand_cap = kCandCapHost;
-  ea.trace = g_trace ? g_trace + 148 * 4 * 256 : nullptr;      // dev tool: 8 int64 after the filter's trace area
-  ev_record(2, st);
+  ea.work = work; ea.work_count = work_count;
+  ea.trace = dev_trace() ? dev_trace() + 148 * 4 * 256 : nullptr;      // dev tool: 8 int64 after the filter's trace area
+  prof_record(prof_events, 2, st);
   rc = launch_exact(ea, n_rows, st);
-  ev_record(3, st);
-  if (g_timing) g_ev_valid[1] = 1;
+  prof_record(prof_events, 3, st);
   return rc;
+}
+
+int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                     const float* E, int64_t K, void* blob,
+                     int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
+                     int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
+                     void* const* prof_events) {
+  return assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, best_key_out, code_base, kblock, algo,
+                         ws, ws_bytes, stream, prof_events, nullptr, false);
 }
 
 size_t vqseg_forward_workspace_bytes(int64_t n_rows, int64_t D, int64_t K) {
@@ -252,10 +290,11 @@ size_t vqseg_forward_workspace_bytes(int64_t n_rows, int64_t D, int64_t K) {
 }
 
 int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
-                         const float* E, int64_t K, const void* blob,
+                         const float* E, int64_t K, void* blob,
                          int64_t* idx_out, int64_t* counts_out, float* usage_out,
                          float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out,
-                         int mode, int algo, int kblock, void* ws, size_t ws_bytes, void* stream) {
+                         int mode, int algo, int kblock, void* ws, size_t ws_bytes, void* stream,
+                         void* const* prof_events) {
   if (!counts_out || K <= 0 || B < 0 || P < 0) return VQSEG_EINVAL;
   if (B * P != 0 && (!idx_out || !q_out)) return VQSEG_EINVAL;   // (empty tensors have null data pointers)
   const size_t wa = (size_t)round_up(vqseg_assign_workspace_bytes(B * P, D, K, algo), 256);
@@ -268,11 +307,12 @@ int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     return usage_out ? vqseg_code_usage(counts_out, K, usage_out, stream) : 0;     // no code is used: 100 %
   }
   int rc = assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, kblock, algo, ws, wa, stream,
-                           usage_out, loss_out, true);   // one zeroing launch; usage reduced by the exact pass's last block
+                           prof_events, loss_out, true);   // the prologue zeroes counts, loss, work counter and tickets
   if (rc) return rc;
-  // the first 256 bytes of the assignment workspace hold {work counter, block ticket, loss ticket}, all zeroed above
+  // the first 256 bytes of the assignment workspace hold {work counter, -, gather ticket, -}, all zeroed above; the
+  // gather's last block reduces the loss and turns the (final) counts into the code usage
   return vqseg_internal_gather_ticket(x, B, P, D, sB, sP, sD, E, K, idx_out, q_out, qB, qP, qD, loss_out, mode,
-                                      (char*)ws + wa, ws_bytes - wa, stream, (int*)ws + 2);
+                                      (char*)ws + wa, ws_bytes - wa, stream, (int*)ws + 2, counts_out, usage_out);
 }
 
 }  // extern "C"

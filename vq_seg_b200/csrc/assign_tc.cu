@@ -21,6 +21,7 @@
 // setmaxnreg moves the register budget to the producers (144 / 72 / 40).
 #include "tc_common.cuh"
 #include "kernels.cuh"
+#include "codebook_prep.cuh"
 
 namespace vqseg {
 
@@ -56,90 +57,15 @@ static_assert(TcSmem::total <= 232448, "smem budget");
 #define VQ_TRACE(role, slot) do { if (a.trace && lane == 0 && (slot) < 256) \
     a.trace[((long long)blockIdx.x * 4 + (role)) * 256 + (slot)] = clock64(); } while (0)
 
-// ---- codebook packing -----------------------------------------------------------------------------
-// image tile (cb, dc): 128 codes x 64 dims of fp16(-2 * s * e), SWIZZLE_128B K-major:
-//   byte = row*128 + ((col/8) ^ (row & 7))*16 + (col % 8)*2
+// ---- codebook packing (bodies in codebook_prep.cuh) ------------------------------------------------
 __global__ void __launch_bounds__(256) pack_codebook_kernel(const float* __restrict__ E, int K, int D,
                                                             unsigned char* __restrict__ blob) {
-  BlobHeader* hdr = reinterpret_cast<BlobHeader*>(blob);
-  const int K_pad = hdr->K_pad, D_pad = hdr->D_pad;
-  // power-of-two prescale: max |s e| in [8, 16)
-  const uint32_t mbits = hdr->max_abs_bits;
-  int ex = (int)((mbits >> 23) & 0xff) - 127;
-  if (mbits == 0) ex = 3;
-  int se = 3 - ex;
-  se = se < -100 ? -100 : (se > 100 ? 100 : se);
-  const float s = __uint_as_float((uint32_t)(127 + se) << 23);
-  float* enorm_s = reinterpret_cast<float*>(blob + hdr->off_enorm) + K_pad;      // scaled copy after the exact one
-  const float* enorm = reinterpret_cast<const float*>(blob + hdr->off_enorm);
-  __half* img = reinterpret_cast<__half*>(blob + hdr->off_image);
-  const int n_dc = D_pad / kDChunk;
-  const long long total = (long long)K_pad * (D_pad / 8);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i / (D_pad / 8)), d8 = (int)(i % (D_pad / 8)) * 8;
-    __align__(16) __half h[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = (k < K && d8 + j < D) ? E[(long long)k * D + d8 + j] : 0.f;
-      h[j] = __float2half_rn(-2.f * s * v);
-    }
-    const int cb = k / kCodeBlock, row = k % kCodeBlock, dc = d8 / kDChunk, c8 = (d8 % kDChunk) / 8;
-    unsigned char* tile = reinterpret_cast<unsigned char*>(img) + ((long long)cb * n_dc + dc) * kTileBytes;
-    *reinterpret_cast<uint4*>(tile + row * 128 + ((c8 ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h);
-  }
-  // |e|^2 limbs for the augmented K step: s|e_k|^2 = c * (h1 + h2 + h3), c a power of two putting the
-  // largest norm in [2^13, 2^14) so every limb is a normal/subnormal fp16 with residual <= 2^-24 c
-  const float men = __uint_as_float(hdr->max_enorm_bits) * s;
-  int ce = (int)((__float_as_uint(men) >> 23) & 0xff) - 127 - 13;
-  if (men == 0.f) ce = 0;
-  ce = ce < -14 ? -14 : (ce > 15 ? 15 : ce);
-  const float c = __uint_as_float((uint32_t)(127 + ce) << 23);
-  const float cinv = __uint_as_float((uint32_t)(127 - ce) << 23);
-  unsigned char* augbase = blob + hdr->off_aug;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K_pad; k += gridDim.x * blockDim.x) {
-    enorm_s[k] = k < K ? enorm[k] * s : 3.0e38f;
-    float v = k < K ? enorm[k] * s * cinv : 60000.f;
-    __half h1, h2, h3;
-    if (k < K) {
-      if (!(v <= 60000.f)) { atomicOr(&hdr->flags, 1u); v = 60000.f; }
-      h1 = __float2half_rn(v);
-      const float r1 = v - __half2float(h1);
-      h2 = __float2half_rn(r1);
-      h3 = __float2half_rn(r1 - __half2float(h2));
-    } else {
-      h1 = h2 = h3 = __float2half_rn(60000.f);          // pad codes can never come near the row minimum
-    }
-    const int cb = k / kCodeBlock, row = k % kCodeBlock;
-    // SWIZZLE_NONE K-major core matrices: 8 rows x 16 B; byte = (row/8)*256 + khalf*128 + (row%8)*16
-    unsigned char* t = augbase + (long long)cb * 4096 + (row >> 3) * 256 + (row & 7) * 16;
-    __align__(16) __half lo[8] = {h1, h2, h3, __float2half_rn(0.f), __float2half_rn(0.f), __float2half_rn(0.f),
-                                  __float2half_rn(0.f), __float2half_rn(0.f)};
-    *reinterpret_cast<uint4*>(t) = *reinterpret_cast<const uint4*>(lo);
-    *reinterpret_cast<uint4*>(t + 128) = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    hdr->scale = s;
-    hdr->max_enorm = __uint_as_float(hdr->max_enorm_bits);
-    hdr->aug_c = c;
-  }
+  prep_pack(E, K, D, blob, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
-
-// rounding error of the fp16 codebook operand, per code, exact: one warp per code -> header max
 __global__ void __launch_bounds__(256) codebook_rounding_error_kernel(const float* __restrict__ E, int K, int D,
                                                                       unsigned char* __restrict__ blob) {
-  BlobHeader* hdr = reinterpret_cast<BlobHeader*>(blob);
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (k >= K) return;
-  const float s = hdr->scale;
-  float acc = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    const float v = -2.f * s * E[(long long)k * D + d];
-    const float df = __half2float(__float2half_rn(v)) - v;
-    acc = fmaf(df, df, acc);
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) atomicMax(&hdr->max_de2_bits, __float_as_uint(acc * 1.0001f));
+  prep_rounding(E, K, D, blob, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), (int)((gridDim.x * blockDim.x) >> 5),
+                (int)(threadIdx.x & 31));
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -397,13 +323,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
           if (lane == 0) base = atomicAdd(a.work_count, __popc(fm));
           base = __shfl_sync(0xffffffffu, base, 0);
           if (flagged) {
+            // one 48-byte record per undecided row (cnt > cap => the exact pass scans all codes)
+            int* rec = reinterpret_cast<int*>(a.work + (base + __popc(fm & ((1u << lane) - 1))));
             int nc = 0;
             if (!overflow) {
-              for (int e = 0; e < cnt; ++e) { int k = cand[e]; if (k < a.K && nc < kCandCap) a.cand_idx[n * kCandCap + nc++] = k; else if (k < a.K) overflow = true; }
-              for (int e = 0; e < cnt1; ++e) { int k = cand_hi[e]; if (k < a.K && nc < kCandCap) a.cand_idx[n * kCandCap + nc++] = k; else if (k < a.K) overflow = true; }
+              for (int e = 0; e < cnt; ++e) { int k = cand[e]; if (k < a.K && nc < kCandCap) rec[4 + nc++] = k; else if (k < a.K) overflow = true; }
+              for (int e = 0; e < cnt1; ++e) { int k = cand_hi[e]; if (k < a.K && nc < kCandCap) rec[4 + nc++] = k; else if (k < a.K) overflow = true; }
             }
-            a.cand_cnt[n] = (overflow || nc == 0) ? kCandCap + 1 : nc;     // > cap => exact pass scans all codes
-            a.work_rows[base + __popc(fm & ((1u << lane) - 1))] = (int)n;
+            rec[0] = (int)n;
+            rec[1] = (overflow || nc == 0) ? kCandCap + 1 : nc;
           }
         }
       }
@@ -502,19 +430,17 @@ int launch_pack(const float* E, int K, int D, unsigned char* blob, cudaStream_t 
   int blocks = num_sms() * 2;
   pack_codebook_kernel<<<blocks, 256, 0, st>>>(E, K, D, blob);
   VQSEG_LAUNCH_CHECK();
-  codebook_rounding_error_kernel<<<(K * 32 + 255) / 256, 256, 0, st>>>(E, K, D, blob);
+  int rblocks = (K * 32 + 255) / 256;
+  if (rblocks > num_sms() * 8) rblocks = num_sms() * 8;
+  codebook_rounding_error_kernel<<<rblocks, 256, 0, st>>>(E, K, D, blob);
   VQSEG_LAUNCH_CHECK();
   return 0;
 }
 
 template <int MODE>
 static int launch_mode(const TcArgs& a, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(assign_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static size_t configured[kMaxDevices] = {0};
+  if (int rc = ensure_dynamic_smem(assign_tc_kernel<MODE>, TcSmem::total, configured)) return rc;
   assign_tc_kernel<MODE><<<grid, kTcThreads, TcSmem::total, st>>>(a);
   VQSEG_LAUNCH_CHECK();
   return 0;

@@ -304,13 +304,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
           if (lane == 0) base = atomicAdd(a.work_count, __popc(fm));
           base = __shfl_sync(0xffffffffu, base, 0);
           if (flagged) {
+            // one 48-byte record per undecided row (cnt > cap => the exact pass scans all codes)
+            int* rec = reinterpret_cast<int*>(a.work + (base + __popc(fm & ((1u << lane) - 1))));
             int nc = 0;
             if (!overflow) {
-              for (int e = 0; e < cnt; ++e) { int k = cand[e]; if (k < a.K && nc < k2CandCap) a.cand_idx[n * k2CandCap + nc++] = k; else if (k < a.K) overflow = true; }
-              for (int e = 0; e < cnt1; ++e) { int k = cand_hi[e]; if (k < a.K && nc < k2CandCap) a.cand_idx[n * k2CandCap + nc++] = k; else if (k < a.K) overflow = true; }
+              for (int e = 0; e < cnt; ++e) { int k = cand[e]; if (k < a.K && nc < k2CandCap) rec[4 + nc++] = k; else if (k < a.K) overflow = true; }
+              for (int e = 0; e < cnt1; ++e) { int k = cand_hi[e]; if (k < a.K && nc < k2CandCap) rec[4 + nc++] = k; else if (k < a.K) overflow = true; }
             }
-            a.cand_cnt[n] = (overflow || nc == 0) ? k2CandCap + 1 : nc;
-            a.work_rows[base + __popc(fm & ((1u << lane) - 1))] = (int)n;
+            rec[0] = (int)n;
+            rec[1] = (overflow || nc == 0) ? k2CandCap + 1 : nc;
           }
         }
       }
@@ -449,12 +451,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
 
 template <int MODE>
 static int launch_mode2(const Tc2Args& a, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(assign_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Smem::total);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static size_t configured[kMaxDevices] = {0};
+  if (int rc = ensure_dynamic_smem(assign_tc2_kernel<MODE>, Tc2Smem::total, configured)) return rc;
   assign_tc2_kernel<MODE><<<grid, k2Threads, Tc2Smem::total, st>>>(a);
   VQSEG_LAUNCH_CHECK();
   return 0;

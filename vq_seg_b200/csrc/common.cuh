@@ -45,6 +45,8 @@ struct RowsOut {
 // [..]   image  : fp16 (-2*s*E) as SWIZZLE_128B K-major tiles of 128 codes x 64 dims (16 KiB each),
 //                 ordered [code_block][d_chunk]
 // [..]   aug    : per code block a 4 KiB SWIZZLE_NONE tile (128 codes x 16 fp16): cols 0..2 = limbs of s|e|^2/aug_c
+// [..]   hash   : K_pad uint64 fingerprints of the fp32 code rows the blob was built from (the codebook guard of the
+//                 forward prologue compares them with the live weights, api.cu)
 struct BlobHeader {
   uint32_t magic;        // 'VQSB'
   int32_t  K, D, K_pad, D_pad;      // K_pad multiple of 256, D_pad multiple of 64
@@ -56,6 +58,10 @@ struct BlobHeader {
   float    aug_c;        // power of two: s|e_k|^2 = aug_c * (h1 + h2 + h3), three fp16 limbs per code
   uint32_t flags;        // bit 0: limbs not representable -> tensor-core filter must defer every row
   uint32_t max_de2_bits; // max_k |fp16(-2 s e_k) - (-2 s e_k)|^2 : the codebook operand's rounding error, exact
+  uint64_t off_hash;
+  uint32_t stale;        // guard scratch: set when a row fingerprint differs from the live weights
+  uint32_t ticket;       // guard scratch: blocks through the comparison
+  uint32_t rebuilds;     // how often the guard had to rebuild the blob (diagnostic)
 };
 constexpr uint32_t kBlobMagic = 0x42535156u;
 constexpr int kCodeBlock = 128;     // codes per packed tile
@@ -128,14 +134,35 @@ inline int check_arch() {
   return major == 10 ? 0 : VQSEG_EARCH;
 }
 
+// Per-device caches (a process may drive several GPUs: nn.DataParallel, one module per device): the SM count and the
+// opt-in dynamic shared-memory limit of a kernel are properties of the CURRENT device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
 inline int num_sms() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
+  static int cached[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (!cached[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
   }
-  return cached;
+  return cached[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device and per function: `state` is the caller's static
+// per-device table (one per kernel instantiation) of the size configured so far.
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&state)[kMaxDevices]) {
+  if (bytes <= 48 * 1024) return 0;
+  const int dev = current_device();
+  if (state[dev] >= bytes) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  state[dev] = bytes;
+  return 0;
 }
 
 #define VQSEG_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)

@@ -16,28 +16,15 @@
 // filter (assign_tc.cu).  Ties: the lowest code index wins, like torch.argmin.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "codebook_prep.cuh"
 
 namespace vqseg {
 
-// ---- |e_k|^2 in torch order, one warp per code -------------------------------------------------
+// ---- |e_k|^2 in torch order (+ max |e|, row fingerprints), one warp per code ---------------------------------
 __global__ void enorm_kernel(const float* __restrict__ E, int K, int D, int K_pad,
-                             float* __restrict__ enorm, BlobHeader* hdr) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= K_pad) return;
-  if (warp >= K) { if (lane == 0) enorm[warp] = 3.0e38f; return; }
-  const float* row = E + (long long)warp * D;
-  float s = torch_order_sumsq_warp([&](long long j) { float v = row[j]; return __fmul_rn(v, v); }, D, lane);
-  float amax = 0.f;
-  for (int j = lane; j < D; j += 32) amax = fmaxf(amax, fabsf(row[j]));
-#pragma unroll
-  for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-  if (lane == 0) {
-    enorm[warp] = s;
-    if (hdr) {
-      atomicMax(&hdr->max_enorm_bits, __float_as_uint(s));
-      atomicMax(&hdr->max_abs_bits, __float_as_uint(amax));
-    }
-  }
+                             float* __restrict__ enorm, BlobHeader* hdr, unsigned long long* __restrict__ hash) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  prep_enorm(E, K, D, K_pad, enorm, hdr, hash, warp, (int)((gridDim.x * blockDim.x) >> 5), lane);
 }
 
 // one augmented chain, generic block size. xs: shared x row, e: global code row
@@ -191,128 +178,38 @@ __device__ __forceinline__ void lexmin(float& d, int& k, float d2, int k2) {
 
 constexpr int kExactWarps = 8;
 
+// ---- brute force: every row against every code (VQSEG_ALGO_EXACT; the validator of the tensor-core path) ----------
 __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs a) {
   extern __shared__ __align__(16) float smem_x[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int D = (int)a.x.D;
   const int xs_stride = (D + 3) & ~3;
-  const bool stage_e = a.stage_e != 0;                   // smem also holds cand_cap code rows per warp
-  float* xs = smem_x + (size_t)wib * (xs_stride + (stage_e ? a.cand_cap * (xs_stride + 4) : 0));
+  float* xs = smem_x + (size_t)wib * xs_stride;
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.E) & 15) == 0);
-  auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
-  if (a.trace && threadIdx.x == 0) atomicMin((unsigned long long*)a.trace, (unsigned long long)gtime());
-  long long c0 = clock64(), c1 = c0, c2 = c0, c3 = c0, c4 = c0;
   const long long n_rows = a.x.n_rows();
-  const long long w_first = (long long)blockIdx.x * kExactWarps + wib;
-  // the work counter and this warp's first row id are independent loads (the list has n_rows slots)
-  int n_spec = (a.work_rows && w_first < n_rows) ? __ldg(a.work_rows + w_first) : 0;
-  long long n_work = a.work_rows ? (long long)__ldg(a.work_count) : n_rows;
-  if (a.work_rows && n_work > n_rows) n_work = n_rows;
-  for (long long w = w_first; w < n_work; w += (long long)gridDim.x * kExactWarps) {
-    const long long n = a.work_rows ? (w == w_first ? n_spec : a.work_rows[w]) : w;
+  for (long long n = (long long)blockIdx.x * kExactWarps + wib; n < n_rows; n += (long long)gridDim.x * kExactWarps) {
     const float* xr = a.x.row(n);
-    // wave 2 of dependent loads, all issued before the first use: candidate count, candidate ids (lane c
-    // holds candidate c) and the row itself (8 strided loads per lane)
-    c1 = clock64();
-    int cnt = a.cand_cnt ? __ldg(a.cand_cnt + n) : -1;
-    int my_k = 0;
-    if (a.cand_idx && lane < a.cand_cap) my_k = __ldg(a.cand_idx + n * a.cand_cap + lane);
     __syncwarp();
-    for (int j0 = 0; j0 < D; j0 += 256) {
-      float t[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {      // unconditional (clamped) loads: a predicated load gets fused with its predicated store and serialises
-        const int j = min(j0 + lane + 32 * u, D - 1);
-        t[u] = __ldg(xr + (long long)j * a.x.sD);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const int j = j0 + lane + 32 * u; if (j < D) xs[j] = t[u]; }
-    }
+    for (int j = lane; j < D; j += 32) xs[j] = __ldg(xr + (long long)j * a.x.sD);
+    __syncwarp();
+    const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
     float best = __int_as_float(0x7f800000);   // +inf
     int best_k = 0x7fffffff;
-    const bool listed = cnt >= 0 && cnt <= a.cand_cap;
-    __syncwarp(); c2 = clock64();
-    my_k = (listed && lane < cnt && my_k >= 0 && my_k < a.K) ? my_k : 0;
-    if (listed && stage_e) {
-      // wave 3: candidate code rows (coalesced, into smem; row stride es_stride = D rounded to 4, + 4:
-      // 16-byte aligned rows, and the <= 8 lanes chaining different rows read disjoint bank quads) and
-      // each candidate's |e|^2
-      float* es = xs + xs_stride;
-      const int es_stride = xs_stride + 4;
-      const float my_en = lane < cnt ? __ldg(a.enorm + my_k) : 0.f;
-      float xnorm;
-      if (vec4 && D <= 256 && cnt <= 4) {
-        // common case: <= 4 candidates of <= 256 dims: their rows travel in registers while |x|^2 is reduced
-        float4 ev[4][2];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float* er = a.E + (long long)__shfl_sync(0xffffffffu, my_k, c) * D;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int j = 4 * lane + 128 * h;
-            ev[c][h] = (c < cnt && j < D) ? __ldg(reinterpret_cast<const float4*>(er + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        __syncwarp();
-        c3 = clock64();
-        xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int j = 4 * lane + 128 * h;
-            if (c < cnt && j < D) *reinterpret_cast<float4*>(es + c * es_stride + j) = ev[c][h];
-          }
-        __syncwarp();
-        c4 = clock64();
+    for (int k0 = lane; k0 < a.K; k0 += 128) {
+      float c4[4];
+      if (vec4) {
+        chain_dist2_x4(xs, a.E, D, a.K, k0, xnorm, a.enorm, a.kblock, c4);
       } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (c < cnt) {
-            const float* er = a.E + (long long)__shfl_sync(0xffffffffu, my_k, c) * D;
-            if (vec4) {
-              for (int j = 4 * lane; j < D; j += 128)
-                *reinterpret_cast<float4*>(es + c * es_stride + j) = __ldg(reinterpret_cast<const float4*>(er + j));
-            } else {
-              for (int j = lane; j < D; j += 32) es[c * es_stride + j] = __ldg(er + j);
-            }
-          }
-        }
-        __syncwarp();
-        c3 = clock64();
-        xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
-        c4 = clock64();
-      }
-      if (lane < cnt) {
-        float c2 = chain_dist2_smem(xs, es + lane * es_stride, D, xnorm, my_en, a.kblock);
-        lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), my_k);
-      }
-    } else if (listed) {
-      __syncwarp();
-      const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
-      if (lane < cnt) {
-        float c2 = chain_dist2<true>(xs, a.E + (long long)my_k * D, D, xnorm, a.enorm[my_k], a.kblock, vec4);
-        lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), my_k);
-      }
-    } else {
-      __syncwarp();
-      const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
-      for (int k0 = lane; k0 < a.K; k0 += 128) {
-        float c4[4];
-        if (vec4) {
-          chain_dist2_x4(xs, a.E, D, a.K, k0, xnorm, a.enorm, a.kblock, c4);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            int k = k0 + 32 * q;
-            c4[q] = k < a.K ? chain_dist2<true>(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, false) : 0.f;
-          }
-        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           int k = k0 + 32 * q;
-          if (k < a.K) lexmin(best, best_k, __fsqrt_rn(fmaxf(c4[q], 0.f)), k);
+          c4[q] = k < a.K ? chain_dist2<true>(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, false) : 0.f;
         }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int k = k0 + 32 * q;
+        if (k < a.K) lexmin(best, best_k, __fsqrt_rn(fmaxf(c4[q], 0.f)), k);
       }
     }
     // NaN distances never win above; torch.argmin would return the first NaN -- documented divergence.
@@ -322,15 +219,6 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
       int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
       lexmin(best, best_k, d2, k2);
     }
-    if (a.trace && lane == 0) {
-      long long c5 = clock64();
-      atomicAdd((unsigned long long*)a.trace + 2, (unsigned long long)(c1 - c0));   // until row id known
-      atomicAdd((unsigned long long*)a.trace + 3, (unsigned long long)(c2 - c1));   // wave 2 (cnt, ids, x row)
-      atomicAdd((unsigned long long*)a.trace + 4, (unsigned long long)(c3 - c2));   // wave 3 (code rows)
-      atomicAdd((unsigned long long*)a.trace + 5, (unsigned long long)(c4 - c3));   // |x|^2
-      atomicAdd((unsigned long long*)a.trace + 6, (unsigned long long)(c5 - c4));   // chains + argmin
-      atomicAdd((unsigned long long*)a.trace + 7, 1ull);
-    }
     if (lane == 0) {
       if (best_k == 0x7fffffff) best_k = 0;
       if (a.idx_out) a.idx_out[n] = (long long)best_k + a.code_base;
@@ -339,59 +227,154 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
         a.key_out[n] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(uint32_t)(best_k + a.code_base);
     }
   }
-  if (a.trace && threadIdx.x == 0) atomicMax((unsigned long long*)a.trace + 1, (unsigned long long)gtime());
-  if (a.usage_out) {
-    // all counts are final once every block is through: the last one (ticket) reduces them -- saves a launch
-    __shared__ int s_last;
-    __shared__ int s_zero[kExactWarps];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(a.done_blocks, 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      int z = 0;
-      for (int k = threadIdx.x; k < a.K; k += blockDim.x) z += (__ldcg((const unsigned long long*)a.counts_out + k) == 0ull);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-      if (lane == 0) s_zero[wib] = z;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w2 = 0; w2 < kExactWarps; ++w2) t += s_zero[w2];
-        *a.usage_out = __fmul_rn(100.f, __fdiv_rn((float)t, (float)a.K));
-      }
-    }
-  }
 }
 
-int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st) {
+// ---- rescoring pass over the filter's work records ------------------------------------------------------------------
+// Two undecided rows per warp, one per half-warp: lane hl of a half runs the exact chain of candidate hl.  With one
+// row per warp only 2-5 lanes of 32 did chain work and six warps per scheduler made the 258-term dependent chains
+// issue-bound (3.9 k cycles instead of ~1.1 k, round-1 trace); with two rows per warp, 8 warps per SM cover 2368 rows
+// in one wave.  Dependent memory round trips per row: {work counter, record} -> {x row, candidate code rows, |e|^2}.
+constexpr int kRsStage = 4;          // candidates per row staged in shared memory (more: read straight from L2)
+
+__global__ void __launch_bounds__(kExactWarps * 32) rescore_kernel(ExactArgs a, int stage_cap, long long rec_cap) {
+  extern __shared__ __align__(16) float smem_x[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int hw = lane >> 4, hl = lane & 15;
+  const int D = (int)a.x.D;
+  const int xs_stride = (D + 3) & ~3, es_stride = xs_stride + 4;
+  const int row_floats = xs_stride + stage_cap * es_stride;
+  float* xs_w = smem_x + (size_t)(2 * wib) * row_floats;          // this warp's two rows
+  float* xs = xs_w + (size_t)hw * row_floats;                     // this half-warp's row
+  float* es = xs + xs_stride;
+  const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.E) & 15) == 0);
+  auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+  if (a.trace && threadIdx.x == 0) atomicMin((unsigned long long*)a.trace, (unsigned long long)gtime());
+  const long long w_first = ((long long)blockIdx.x * nwarps + wib) * 2;
+  // the work counter and this warp's first two records are independent loads (the list has rec_cap slots)
+  int rec_v = 0;
+  if (w_first + hw < rec_cap && hl < 12) rec_v = __ldg(reinterpret_cast<const int*>(a.work + w_first + hw) + hl);
+  long long n_work = (long long)__ldg(a.work_count);
+  if (n_work > rec_cap) n_work = rec_cap;
+  for (long long w = w_first; w < n_work; w += (long long)gridDim.x * nwarps * 2) {
+    if (w != w_first) {
+      rec_v = 0;
+      if (w + hw < n_work && hl < 12) rec_v = __ldg(reinterpret_cast<const int*>(a.work + w + hw) + hl);
+    }
+    const bool valid = w + hw < n_work;
+    const int row = __shfl_sync(0xffffffffu, rec_v, hw * 16);
+    int cnt = __shfl_sync(0xffffffffu, rec_v, hw * 16 + 1);
+    int my_k = __shfl_sync(0xffffffffu, rec_v, hw * 16 + 4 + (hl & 7));
+    if (!valid) cnt = 0;
+    const bool listed = cnt <= kWorkCandCap;
+    const bool mine = valid && listed && hl < cnt;
+    my_k = (mine && my_k >= 0 && my_k < a.K) ? my_k : 0;
+    // ---- second wave of loads, all in flight together: the row, the staged candidate rows, the candidates' |e|^2
+    const float* xr = a.x.row(valid ? row : 0);
+    const float my_en = mine ? __ldg(a.enorm + my_k) : 0.f;
+    __syncwarp();
+    if (valid) {
+      if (a.x.sD == 1 && vec4 && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0)) {
+        for (int j = 4 * hl; j < D; j += 64) *reinterpret_cast<float4*>(xs + j) = __ldg(reinterpret_cast<const float4*>(xr + j));
+      } else {
+        for (int j0 = 0; j0 < D; j0 += 128) {
+          float t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int j = min(j0 + hl + 16 * u, D - 1); t[u] = __ldg(xr + (long long)j * a.x.sD); }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int j = j0 + hl + 16 * u; if (j < D) xs[j] = t[u]; }
+        }
+      }
+    }
+    const int n_staged = listed ? min(cnt, stage_cap) : 0;
+    const int n_staged_w = max(n_staged, __shfl_xor_sync(0xffffffffu, n_staged, 16));      // warp-uniform trip count
+    for (int c = 0; c < n_staged_w; ++c) {
+      const float* er = a.E + (long long)__shfl_sync(0xffffffffu, my_k, hw * 16 + c, 32) * D;
+      if (c >= n_staged) continue;
+      if (vec4) {
+        for (int j = 4 * hl; j < D; j += 64) *reinterpret_cast<float4*>(es + c * es_stride + j) = __ldg(reinterpret_cast<const float4*>(er + j));
+      } else {
+        for (int j = hl; j < D; j += 16) es[c * es_stride + j] = __ldg(er + j);
+      }
+    }
+    __syncwarp();
+    // ---- |x|^2 in ATen's order: the reduction is warp-wide (lane t = accumulator t), one row after the other
+    const float xn0 = torch_order_sumsq_warp([&](long long j) { float v = xs_w[j]; return __fmul_rn(v, v); }, D, lane);
+    const float xn1 = torch_order_sumsq_warp([&](long long j) { float v = xs_w[row_floats + j]; return __fmul_rn(v, v); }, D, lane);
+    const float xnorm = hw ? xn1 : xn0;
+    float best = __int_as_float(0x7f800000);   // +inf
+    int best_k = 0x7fffffff;
+    if (mine) {
+      const float c2 = hl < n_staged ? chain_dist2_smem(xs, es + hl * es_stride, D, xnorm, my_en, a.kblock)
+                                     : chain_dist2<true>(xs, a.E + (long long)my_k * D, D, xnorm, my_en, a.kblock, vec4);
+      lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), my_k);
+    } else if (valid && !listed) {
+      // the short-list overflowed (or the filter deferred the row): every code, 16 lanes striding over K
+      for (int k = hl; k < a.K; k += 16) {
+        const float c2 = chain_dist2<true>(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, vec4);
+        lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), k);
+      }
+    }
+    // NaN distances never win above; torch.argmin would return the first NaN -- documented divergence.
+#pragma unroll
+    for (int o = 8; o; o >>= 1) {
+      float d2 = __shfl_xor_sync(0xffffffffu, best, o);
+      int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
+      lexmin(best, best_k, d2, k2);
+    }
+    if (hl == 0 && valid) {
+      if (best_k == 0x7fffffff) best_k = 0;
+      if (a.idx_out) a.idx_out[row] = (long long)best_k + a.code_base;
+      if (a.counts_out) atomicAdd(a.counts_out + best_k, 1ull);
+      if (a.key_out)
+        a.key_out[row] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(uint32_t)(best_k + a.code_base);
+    }
+    __syncwarp();
+  }
+  if (a.trace && threadIdx.x == 0) atomicMax((unsigned long long*)a.trace + 1, (unsigned long long)gtime());
+}
+
+int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, unsigned long long* hash,
+                 cudaStream_t st) {
   int warps = K_pad;
   int threads = 256, blocks = (warps * 32 + threads - 1) / threads;
-  enorm_kernel<<<blocks, threads, 0, st>>>(E, K, D, K_pad, enorm, hdr);
+  const int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  enorm_kernel<<<blocks, threads, 0, st>>>(E, K, D, K_pad, enorm, hdr, hash);
   VQSEG_LAUNCH_CHECK();
   return 0;
 }
 
-int launch_exact(const ExactArgs& a_in, long long max_work, cudaStream_t st) {
+int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st) {
   if (max_work <= 0) return 0;
-  ExactArgs a = a_in;
   const int D = (int)a.x.D;
   const size_t xs_bytes = (size_t)((D + 3) & ~3) * sizeof(float);
-  const size_t es_bytes = (size_t)a.cand_cap * (((D + 3) & ~3) + 4) * sizeof(float);
-  a.stage_e = (a.cand_idx != nullptr && kExactWarps * (xs_bytes + es_bytes) <= 100 * 1024) ? 1 : 0;
-  size_t smem = (size_t)kExactWarps * (xs_bytes + (a.stage_e ? es_bytes : 0));
-  if (smem > 200 * 1024) return VQSEG_EUNSUPPORTED;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(exact_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
+  if (!a.work) {                                             // brute force: one row per warp
+    const size_t smem = (size_t)kExactWarps * xs_bytes;
+    if (smem > 200 * 1024) return VQSEG_EUNSUPPORTED;
+    static size_t configured[kMaxDevices] = {0};
+    if (int rc = ensure_dynamic_smem(exact_score_kernel, smem, configured)) return rc;
+    long long blocks = (max_work + kExactWarps - 1) / kExactWarps;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    exact_score_kernel<<<(unsigned)blocks, kExactWarps * 32, smem, st>>>(a);
+    VQSEG_LAUNCH_CHECK();
+    return 0;
   }
-  long long blocks = (max_work + kExactWarps - 1) / kExactWarps;
-  long long cap = (long long)num_sms() * (a.stage_e ? 3 : 8);
+  // rescoring pass: rows of (x + staged candidates) per warp pair; as many warps per block as ~96 KB allow
+  const size_t es_bytes = xs_bytes + 16;
+  int stage_cap = kRsStage;
+  while (stage_cap > 0 && 2 * (xs_bytes + stage_cap * es_bytes) > 200 * 1024) --stage_cap;
+  const size_t row_bytes = xs_bytes + stage_cap * es_bytes;
+  if (2 * row_bytes > 200 * 1024) return VQSEG_EUNSUPPORTED;
+  int nwarps = (int)((96 * 1024) / (2 * row_bytes));
+  nwarps = nwarps < 1 ? 1 : (nwarps > kExactWarps ? kExactWarps : nwarps);
+  const size_t smem = (size_t)nwarps * 2 * row_bytes;
+  static size_t configured[kMaxDevices] = {0};
+  if (int rc = ensure_dynamic_smem(rescore_kernel, smem, configured)) return rc;
+  long long blocks = (max_work + 2 * nwarps - 1) / (2 * nwarps);
+  const long long cap = (long long)num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  exact_score_kernel<<<(unsigned)blocks, kExactWarps * 32, smem, st>>>(a);
+  rescore_kernel<<<(unsigned)blocks, nwarps * 32, smem, st>>>(a, stage_cap, max_work);
   VQSEG_LAUNCH_CHECK();
   return 0;
 }

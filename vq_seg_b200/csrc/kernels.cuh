@@ -5,6 +5,12 @@
 
 namespace vqseg {
 
+// One undecided row handed from a tensor-core filter to the rescoring pass: the row id and the short-list of codes
+// whose approximate score lies within the proven error bound of the row minimum.  cnt > kWorkCandCap means "the
+// short-list overflowed: score every code".  48 bytes, 16-byte aligned: one coalesced fetch per record.
+constexpr int kWorkCandCap = 8;
+struct alignas(16) WorkRec { int row; int cnt; int pad0; int pad1; int cand[kWorkCandCap]; };
+
 // ---- exact.cu: exact fp32 scorer (brute force over all codes, or the rescoring pass over the filter's short-lists)
 struct ExactArgs {
   Rows x;
@@ -12,15 +18,12 @@ struct ExactArgs {
   const float* enorm;
   int kblock;
   // candidate mode (null -> all rows x all codes)
-  const int* work_rows; const int* work_count;        // flagged row ids, device counter
-  const int* cand_idx; const int* cand_cnt; int cand_cap;   // per row: up to cand_cap codes; cnt > cap => all codes
+  const WorkRec* work; const int* work_count;         // undecided rows + device counter
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
-  int stage_e;
-  long long* trace;     // dev tool: [0] min start ns, [1] max end ns, [2..] per-phase clock sums
-  int* done_blocks;     // ticket counter (zeroed by the host) for the fused usage epilogue
-  float* usage_out;     // nullable: the last block to finish writes 100 * (#counts == 0) / K   (vq_img.py:174-175)
+  long long* trace;     // dev tool: [0] min start ns, [1] max end ns
 };
-int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, cudaStream_t st);
+int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, unsigned long long* hash,
+                 cudaStream_t st);
 int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st);
 
 // ---- assign_tc.cu: single-CTA streaming tcgen05 filter, and the codebook packer
@@ -34,7 +37,7 @@ struct TcArgs {
   // outputs
   long long* idx_out; unsigned long long* counts_out; long long code_base;
   int force_rescore;              // 1 -> every row goes to the exact pass (sharded mode needs exact distances)
-  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
+  WorkRec* work; int* work_count;
   long long* trace;               // optional (dev tool): [cta][role][256] clock64 stamps
 };
 int launch_pack(const float* E, int K, int D, unsigned char* blob, cudaStream_t st);
@@ -51,10 +54,27 @@ struct Tc2Args {
   float tau;
   long long* idx_out; unsigned long long* counts_out; long long code_base;
   int force_rescore;
-  int* cand_idx; int* cand_cnt; int* work_rows; int* work_count;
+  WorkRec* work; int* work_count;
   long long* trace;
 };
 bool tc2_supported(int n_cc, int n_dc);
 int launch_assign_tc2(const Tc2Args& a, cudaStream_t st);
+
+// ---- assign_tc3.cu: TMA-fed CTA-pair, codebook-resident tcgen05 filter (pixel-contiguous / NCHW inputs)
+struct Tc3Args {
+  long long B, P, D;              // logical (B, P, D) view; memory is pixel-contiguous (sP == 1)
+  long long n_rows;
+  const unsigned char* blob;
+  int n_tiles, tiles_per_image;   // tiles of 128 pixels, never straddling an image
+  int n_ptiles, n_cc, n_dc;       // pair tiles (two tiles), code chunks of 256, dim chunks of 64
+  int K, K_pad;
+  unsigned long long off_image, off_aug, off_enorm;
+  long long* idx_out; unsigned long long* counts_out; long long code_base;
+  int force_rescore;
+  WorkRec* work; int* work_count;
+  long long* trace;
+};
+bool tc3_supported(const Rows& x, int n_cc, int n_dc);
+int launch_assign_tc3(const Rows& x, const Tc3Args& a, cudaStream_t st);
 
 }  // namespace vqseg

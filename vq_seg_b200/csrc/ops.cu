@@ -22,7 +22,8 @@ __device__ __forceinline__ int gcol(int p) { return ((p & 3) << 5) | (p >> 2); }
 
 // Last-block loss reduction (fused forward): every block publishes its partial, takes a ticket, and the block that
 // draws the last one sums all partials in the same fixed order as loss_finalize_kernel -- one launch less.
-struct LossTail { int* ticket; float* loss_out; double inv_numel; };
+// The same block also turns the (by then final) per-code counts into the code usage of vq_img.py:173-175.
+struct LossTail { int* ticket; float* loss_out; double inv_numel; const unsigned long long* counts; int K; float* usage_out; };
 __device__ __forceinline__ void loss_tail(const LossTail& t, const float* partial, int n_partial, int n_blocks) {
   __shared__ double s_dred[256];
   __shared__ int s_last;
@@ -32,15 +33,29 @@ __device__ __forceinline__ void loss_tail(const LossTail& t, const float* partia
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n_partial; i += 256) s += (double)__ldcg(partial + i);
-  s_dred[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o; o >>= 1) {
-    if ((int)threadIdx.x < o) s_dred[threadIdx.x] += s_dred[threadIdx.x + o];
+  if (t.loss_out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += 256) s += (double)__ldcg(partial + i);
+    s_dred[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+      if ((int)threadIdx.x < o) s_dred[threadIdx.x] += s_dred[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) *t.loss_out = (float)(s_dred[0] * t.inv_numel);
     __syncthreads();
   }
-  if (threadIdx.x == 0) *t.loss_out = (float)(s_dred[0] * t.inv_numel);
+  if (t.usage_out) {
+    int z = 0;
+    for (int k = threadIdx.x; k < t.K; k += 256) z += (__ldcg(t.counts + k) == 0ull);
+    s_dred[threadIdx.x] = (double)z;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+      if ((int)threadIdx.x < o) s_dred[threadIdx.x] += s_dred[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) *t.usage_out = __fmul_rn(100.f, __fdiv_rn((float)s_dred[0], (float)t.K));
+  }
 }
 
 // VEC: pixel quads are 16-byte aligned and never straddle an image (P % 4 == 0, aligned bases)
@@ -162,8 +177,8 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
       for (int w = 0; w < 8; ++w) s += s_red[w];
       partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = s;
     }
-    if (tail.ticket) loss_tail(tail, partial, (int)(gridDim.x * gridDim.y), (int)(gridDim.x * gridDim.y));
   }
+  if (tail.ticket) loss_tail(tail, partial, (int)(gridDim.x * gridDim.y), (int)(gridDim.x * gridDim.y));
 }
 
 // Generic strides (row-major samples etc.): one warp per row, lanes along d.
@@ -207,8 +222,8 @@ __global__ void __launch_bounds__(256) gather_ste_generic_kernel(Rows x, const f
       for (int w = 0; w < 8; ++w) s += s_red[w];
       partial[blockIdx.x] = s;
     }
-    if (tail.ticket) loss_tail(tail, partial, (int)gridDim.x, (int)gridDim.x);
   }
+  if (tail.ticket) loss_tail(tail, partial, (int)gridDim.x, (int)gridDim.x);
 }
 
 // fixed-order final reduction of the per-block partials -> mean
@@ -228,12 +243,15 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restr
 
 template <int MODE>
 static int launch_gather(const Rows& x, const float* E, int K, const long long* idx, const RowsOut& q,
-                         float* loss_out, float* partial, size_t partial_cap, cudaStream_t st, int* ticket = nullptr) {
+                         float* loss_out, float* partial, size_t partial_cap, cudaStream_t st, int* ticket = nullptr,
+                         const unsigned long long* counts = nullptr, float* usage_out = nullptr) {
   const long long n_rows = x.n_rows();
   const bool train = (MODE == VQSEG_MODE_TRAIN || MODE == VQSEG_MODE_TRAIN_AMP);
   const bool want_loss = train && loss_out != nullptr;
-  // ticket (zeroed by the caller): the kernel's last block reduces the loss itself
-  LossTail tail{want_loss ? ticket : nullptr, loss_out, 1.0 / ((double)n_rows * (double)x.D)};
+  const bool want_usage = ticket && counts && usage_out;
+  // ticket (zeroed by the caller): the kernel's last block reduces the loss (and the code usage) itself
+  LossTail tail{(want_loss || want_usage) ? ticket : nullptr, want_loss ? loss_out : nullptr,
+                1.0 / ((double)n_rows * (double)x.D), counts, K, want_usage ? usage_out : nullptr};
   int n_partial = 0;
   if (x.sP == 1 && q.sP == 1 && (long long)K * x.D < (1ll << 31)) {
     dim3 grid((unsigned)((n_rows + kGPix - 1) / kGPix), (unsigned)((x.D + kGTile - 1) / kGTile));
@@ -697,12 +715,8 @@ static int stats_det_range(const float* x, long long B, long long P, long long D
   stats_scan_codes_kernel<<<1, 1024, 0, st>>>(code_total, (int)K, code_start);
   VQSEG_LAUNCH_CHECK();
   size_t smem = (size_t)K * sizeof(int);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    e = cudaFuncSetAttribute(stats_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
+  static size_t configured[kMaxDevices] = {0};
+  if (int rc = ensure_dynamic_smem(stats_scatter_kernel, smem, configured)) return rc;
   stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>((const long long*)idx, n_rows, (int)K, hist, code_start, perm);
   VQSEG_LAUNCH_CHECK();
   const bool packed = B == 1 && sD == 1 && D % 4 == 0 && sP % 4 == 0 &&
@@ -757,7 +771,8 @@ int vqseg_gather_ste_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
 int vqseg_internal_gather_ticket(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                                  const float* E, int64_t K, const int64_t* idx,
                                  float* q_out, int64_t qB, int64_t qP, int64_t qD, float* loss_out, int mode,
-                                 void* ws, size_t ws_bytes, void* stream, int* ticket) {
+                                 void* ws, size_t ws_bytes, void* stream, int* ticket,
+                                 const int64_t* counts, float* usage_out) {
   if (!E || !idx || !q_out || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
   const bool train = mode == VQSEG_MODE_TRAIN || mode == VQSEG_MODE_TRAIN_AMP;
   if (train && !x) return VQSEG_EINVAL;
@@ -769,11 +784,12 @@ int vqseg_internal_gather_ticket(const float* x, int64_t B, int64_t P, int64_t D
   float* partial = (float*)ws;
   size_t cap = ws ? ws_bytes / sizeof(float) : 0;
   const long long* ix = (const long long*)idx;
+  const unsigned long long* cu = (const unsigned long long*)counts;
   switch (mode) {
-    case VQSEG_MODE_EVAL:      return launch_gather<VQSEG_MODE_EVAL>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st, ticket);
-    case VQSEG_MODE_EVAL_AMP:  return launch_gather<VQSEG_MODE_EVAL_AMP>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st, ticket);
-    case VQSEG_MODE_TRAIN:     return launch_gather<VQSEG_MODE_TRAIN>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st, ticket);
-    case VQSEG_MODE_TRAIN_AMP: return launch_gather<VQSEG_MODE_TRAIN_AMP>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st, ticket);
+    case VQSEG_MODE_EVAL:      return launch_gather<VQSEG_MODE_EVAL>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st, ticket, cu, usage_out);
+    case VQSEG_MODE_EVAL_AMP:  return launch_gather<VQSEG_MODE_EVAL_AMP>(xr, E, (int)K, ix, qr, nullptr, partial, cap, st, ticket, cu, usage_out);
+    case VQSEG_MODE_TRAIN:     return launch_gather<VQSEG_MODE_TRAIN>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st, ticket, cu, usage_out);
+    case VQSEG_MODE_TRAIN_AMP: return launch_gather<VQSEG_MODE_TRAIN_AMP>(xr, E, (int)K, ix, qr, loss_out, partial, cap, st, ticket, cu, usage_out);
   }
   return VQSEG_EINVAL;
 }
@@ -954,12 +970,8 @@ int vqseg_assign_cosine_f32(const float* xn, int64_t N, int64_t D, const float* 
   if (N == 0) return 0;
   size_t smem = 8 * (size_t)D * sizeof(float);
   if (smem > 200 * 1024) return VQSEG_EUNSUPPORTED;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(assign_cosine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
+  static size_t configured[kMaxDevices] = {0};
+  if (int rc = ensure_dynamic_smem(assign_cosine_kernel, smem, configured)) return rc;
   assign_cosine_kernel<<<grid_for(N * 32, 256), 256, smem, (cudaStream_t)stream>>>(
       xn, N, (int)D, E, (int)K, (long long*)idx_out, (unsigned long long*)counts_out);
   VQSEG_LAUNCH_CHECK();

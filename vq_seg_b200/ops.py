@@ -10,7 +10,7 @@ import torch
 
 from . import _native
 
-ALGO_AUTO, ALGO_EXACT, ALGO_TC = 0, 1, 2
+ALGO_AUTO, ALGO_EXACT, ALGO_TC, ALGO_TC_STREAM, ALGO_TC_PAIR, ALGO_TC_TMA = 0, 1, 2, 3, 4, 5
 MODE_EVAL, MODE_TRAIN, MODE_TRAIN_AMP, MODE_EVAL_AMP = 0, 1, 2, 3
 _last_assign_ws = None
 
@@ -57,9 +57,20 @@ prepare_codebook = torch.library.custom_op("vqseg::prepare_codebook", mutates_ar
 @prepare_codebook.register_fake
 def _(codebook):
     k, d = codebook.shape
-    kp, dp = (k + 255) // 256 * 256, (d + 63) // 64 * 64
-    return codebook.new_empty(1024 + ((2 * kp * 4 + 1023) // 1024) * 1024 + kp * dp * 2 + (kp // 128) * 4096,
-                              dtype=torch.uint8)
+    return codebook.new_empty(_native.lib().vqseg_codebook_blob_bytes(k, d), dtype=torch.uint8)
+
+
+_profile = None      # a _native.ProfileEvents while bench.py / scripts time the kernels of a call, else None
+
+
+def set_profile_events(pe):
+    """bench.py: hand the next assign / fused-forward calls four caller-owned CUDA events (None switches it off)."""
+    global _profile
+    _profile = pe
+
+
+def _prof():
+    return _profile.array if _profile is not None else None
 
 
 def _assign_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], algo: int = 0,
@@ -82,7 +93,7 @@ def _assign_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.T
         _native.check(L.vqseg_assign_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
                                          blob.data_ptr() if blob is not None else None,
                                          idx.data_ptr(), counts.data_ptr(), None, 0, kblock, algo,
-                                         ws.data_ptr(), nws, _stream()), "assign")
+                                         ws.data_ptr(), nws, _stream(), _prof()), "assign")
     global _last_assign_ws
     _last_assign_ws = ws            # dev diagnostics: ws[0:4] = number of rows sent to the exact pass
     return idx, counts
@@ -114,7 +125,7 @@ def _assign_keys_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[to
         _native.check(L.vqseg_assign_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
                                          blob.data_ptr() if blob is not None else None,
                                          None, None, keys.data_ptr(), code_base, kblock, algo,
-                                         ws.data_ptr(), nws, _stream()), "assign_keys")
+                                         ws.data_ptr(), nws, _stream(), None), "assign_keys")
     return keys
 
 
@@ -559,7 +570,7 @@ def _vq_forward_raw(x, codebook, blob, mode, algo=0):
                                              blob.data_ptr() if blob is not None else None,
                                              idx.data_ptr(), counts.data_ptr(), usage.data_ptr(),
                                              q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), loss.data_ptr(),
-                                             mode, algo, 0, ws.data_ptr(), nws, _stream()), "vq_forward")
+                                             mode, algo, 0, ws.data_ptr(), nws, _stream(), _prof()), "vq_forward")
     return q, idx, loss, usage, counts
 
 
