@@ -422,12 +422,14 @@ def stage_trace():
     xd, ed = x.to(dev), e.to(dev)
     xv = view(xd)
     blob = ops.prepare_codebook(ed)
+    fused = "assign" not in sys.argv
+    run = (lambda: ops._vq_forward_raw(xv, ed, blob, ops.MODE_TRAIN if "train" in sys.argv else ops.MODE_EVAL)) if fused else (lambda: ops.assign(xv, ed, blob, ops.ALGO_TC))
     for _ in range(3):
-        ops.assign(xv, ed, blob, ops.ALGO_TC)
+        run()
     buf = torch.zeros(148 * 4 * 256 + 8, dtype=torch.int64, device=dev)
     buf[-8] = 2 ** 62
     L.vqseg_debug_set_trace(buf.data_ptr())
-    ops.assign(xv, ed, blob, ops.ALGO_TC)
+    run()
     torch.cuda.synchronize()
     L.vqseg_debug_set_trace(None)
     ex = buf[-8:].cpu()
