@@ -164,17 +164,11 @@ size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int al
   return b;
 }
 
-// what the fused forward hands down so that the TMA-fed pair kernel can also write the quantized rows, the loss and the
-// code usage (set `done` when it did: the caller then skips the gather launch)
-struct FusedGather {
-  float* q; int64_t qB, qP, qD; float* loss_out; float* usage_out; int mode; float* partial; size_t partial_cap; bool done;
-};
-
 static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
                            const float* E, int64_t K, void* blob,
                            int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
                            int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
-                           void* const* prof_events, float* zero_loss, bool zero_counts, FusedGather* fg = nullptr) {
+                           void* const* prof_events, float* zero_loss, bool zero_counts) {
   if (!x || !E || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
   if (!idx_out && !best_key_out) return VQSEG_EINVAL;
   const long long n_rows = B * P;
@@ -233,12 +227,10 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   if (algo == VQSEG_ALGO_TC_STREAM) kernel = 1;
   if (algo == VQSEG_ALGO_TC_PAIR) { if (!can2) return VQSEG_EUNSUPPORTED; kernel = 2; }
   if (algo == VQSEG_ALGO_TC_TMA) { if (!can3) return VQSEG_EUNSUPPORTED; kernel = 3; }
-  bool rescored = false;            // the filter kernel re-scored its undecided rows itself
   prof_record(prof_events, 0, st);
   if (kernel == 3) {
     Tc3Args t3;
     memset(&t3, 0, sizeof(t3));
-    t3.x = xr; t3.E = E; t3.enorm = enorm; t3.kblock = kblock;
     t3.B = B; t3.P = P; t3.D = D; t3.n_rows = n_rows; t3.blob = (const unsigned char*)blob;
     t3.tiles_per_image = (int)((P + 127) / 128);
     t3.n_tiles = (int)(B * t3.tiles_per_image);
@@ -248,18 +240,6 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     t3.force_rescore = force ? 1 : 0;
     t3.work = work; t3.work_count = work_count;
     t3.trace = dev_trace();
-    t3.local_rescore = tc3_rescores_locally(t3.n_ptiles, force) ? 1 : 0;
-    rescored = t3.local_rescore != 0;
-    if (fg && rescored && fg->qP == 1 && (fg->qD & 3) == 0 && (fg->qB & 3) == 0 && (reinterpret_cast<uintptr_t>(fg->q) & 15) == 0 &&
-        fg->partial && fg->partial_cap >= (size_t)num_sms() && counts_out && (D & 3) == 0 && (reinterpret_cast<uintptr_t>(E) & 15) == 0) {
-      const bool train = fg->mode == VQSEG_MODE_TRAIN || fg->mode == VQSEG_MODE_TRAIN_AMP;
-      t3.fuse_gather = 1; t3.mode = fg->mode; t3.q = fg->q; t3.qB = fg->qB; t3.qD = fg->qD;
-      t3.partial = fg->partial; t3.ticket = work_count + 2;
-      t3.loss_out = (train && fg->loss_out) ? fg->loss_out : nullptr;
-      t3.inv_numel = 1.0 / ((double)n_rows * (double)D);
-      t3.usage_out = fg->usage_out;
-      fg->done = true;
-    }
     rc = launch_assign_tc3(xr, t3, st);
   } else if (kernel == 2) {
     Tc2Args t2;
@@ -291,7 +271,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   ea.work = work; ea.work_count = work_count;
   ea.trace = dev_trace() ? dev_trace() + 148 * 4 * 256 : nullptr;      // dev tool: 8 int64 after the filter's trace area
   prof_record(prof_events, 2, st);
-  if (!rescored) rc = launch_exact(ea, n_rows, st);
+  rc = launch_exact(ea, n_rows, st);
   prof_record(prof_events, 3, st);
   return rc;
 }
@@ -326,10 +306,9 @@ int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     if (e != cudaSuccess) return (int)e;
     return usage_out ? vqseg_code_usage(counts_out, K, usage_out, stream) : 0;     // no code is used: 100 %
   }
-  FusedGather fg{q_out, qB, qP, qD, loss_out, usage_out, mode, (float*)((char*)ws + wa), (ws_bytes - wa) / sizeof(float), false};
   int rc = assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, kblock, algo, ws, wa, stream,
-                           prof_events, loss_out, true, &fg);   // the prologue zeroes counts, loss, work counter and tickets
-  if (rc || fg.done) return rc;   // the TMA-fed pair kernel wrote the quantized rows, the loss and the usage itself
+                           prof_events, loss_out, true);   // the prologue zeroes counts, loss, work counter and tickets
+  if (rc) return rc;
   // the first 256 bytes of the assignment workspace hold {work counter, -, gather ticket, -}, all zeroed above; the
   // gather's last block reduces the loss and turns the (final) counts into the code usage
   return vqseg_internal_gather_ticket(x, B, P, D, sB, sP, sD, E, K, idx_out, q_out, qB, qP, qD, loss_out, mode,

@@ -20,7 +20,6 @@
 #include <cuda.h>
 #include "tc_common.cuh"
 #include "kernels.cuh"
-#include "exact_chain.cuh"
 
 namespace vqseg {
 
@@ -47,13 +46,9 @@ struct Tc3Smem {
   static constexpr int off_xchg = off_cand + 2 * k3Rows * k3CandCap * 2;     // [128] {m_run, cnt|overflow} of the upper-half warp
   static constexpr int off_xsq = off_xchg + k3Rows * 8;                      // [2 tiles][2 groups][128] float2 {|x|^2, |fp16(x)-x|^2}
   static constexpr int off_bar = off_xsq + 2 * 2 * k3Rows * 8;
-  static constexpr int n_bars = 2 * k3Stages + 2 * k3ASlots + 4 + 2 * k3MaxCC + 2;
+  static constexpr int n_bars = 2 * k3Stages + 2 * k3ASlots + 4 + 2 * k3MaxCC;
   static constexpr int off_tmem = off_bar + 8 * n_bars;
-  static constexpr int kQueueBytes = 32 + k3Rows;                            // {int count; pad[3]; uint32 undecided_mask[4]; uint8 row[128]}
-  static constexpr int off_queue = off_tmem + 16;                            // [2 tiles] undecided rows of a tile
-  static constexpr int off_loss = off_queue + 2 * kQueueBytes;               // [16] per-warp commitment-loss partials
-  static constexpr int total = off_loss + 64 + 1024;
-  static constexpr int scratch_bytes = (k3ASlots * kTileBytes) + k3Stages * k3StageBytes;   // A ring + staging, contiguous
+  static constexpr int total = off_tmem + 16 + 1024;
 };
 static_assert(Tc3Smem::total <= 232448, "smem budget");
 static_assert(k3Issuers == k3Stages, "each stage barrier is waited on by exactly one issuing thread");
@@ -68,92 +63,6 @@ static_assert(k3Issuers == k3Stages, "each stage barrier is waited on by exactly
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
-}
-
-// ---- fused forward: gather + straight-through estimator + commitment-loss partial ---------------------------------
-__device__ __forceinline__ float round_fp16_3(float v) { return __half2float(__float2half_rn(v)); }
-// quantized value of one element and its loss term; e = the code's component (vq_img.py:170,236,239)
-__device__ __forceinline__ float ste_value(bool TRAIN, float e, float xv, float& acc) {
-  if (!TRAIN) return e;
-  const float o = __fadd_rn(xv, __fsub_rn(e, xv));          // x + (q - x): two fp32 roundings, like the reference
-  const float f = __fsub_rn(o, xv);
-  acc = __fmaf_rn(f, f, acc);
-  return o;
-}
-
-// The DECIDED rows of one tile (128 pixels of image `img` from pixel p0), written by 8 warps (wg = 0..7) in units of
-// 32 pixels x 32 dims through a 4 KiB shared-memory tile per warp:
-//   phase 1: cp.async of 16 bytes per lane -- 8 lanes cover the 128-byte segment of one code row, 4 pixels per
-//            instruction, 8 instructions per unit, all in flight before one wait; the 16-byte chunk c of pixel p lands
-//            in chunk slot c ^ (p & 7) of the pixel's 128-byte row;
-//   phase 2: lane = pixel: one conflict-free LDS.128 per 4 dims, four stores of 128 B per warp along the pixels.
-// ~2 instructions per element (the round-1 gather kernel needs 23: one LDG.32 / STS.32 per element in phase 1).
-// Undecided rows (mask bit set) are skipped: the rescoring warp that settles them writes their row.
-__device__ __forceinline__ float gather_tile_rows(const Tc3Args& a, bool TRAIN, bool AMP, int img, int p0, const uint32_t* undecided,
-                                                  float* tile, int wg, int lane) {
-  float acc = 0.f;
-  if (img >= (int)a.B) return acc;
-  const int D = (int)a.D;
-  const int n_db = (D + 31) >> 5;
-  const long long n_img = (long long)img * a.P;
-  const uint32_t tbase = smem_u32(tile);
-  for (int u = wg; u < 4 * n_db; u += 8) {
-    const int pq = u & 3, d0 = (u >> 2) * 32;
-    const int pb = p0 + 32 * pq;                             // first pixel of this unit
-    const uint32_t und = undecided[pq];
-    const bool mine = pb + lane < (int)a.P && !((und >> lane) & 1u);           // lane = pixel: decided and inside the image
-    const int k = mine ? (int)a.idx_out[n_img + pb + lane] - (int)a.code_base : -1;
-    __syncwarp();                                            // the previous unit's reads of the tile are done
-    {
-      const int c = lane & 7;
-      const bool dok = d0 + 4 * c < D;                       // D % 4 == 0 (checked by the launcher)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int p = 4 * i + (lane >> 3);
-        const int kp = __shfl_sync(0xffffffffu, k, p);
-        if (kp >= 0 && dok)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                       ::"r"(tbase + (uint32_t)(p * 128 + ((c ^ (p & 7)) << 4))), "l"(a.E + (long long)kp * D + d0 + 4 * c) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncwarp();
-    if (mine) {
-      float* qp = a.q + (long long)img * a.qB + (long long)d0 * a.qD + pb + lane;
-      const float* xp = a.x.ptr + (long long)img * a.x.sB + (long long)d0 * a.x.sD + pb + lane;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (d0 + 4 * c >= D) break;
-        float4 e = *reinterpret_cast<const float4*>(tile + lane * 32 + ((c ^ (lane & 7)) << 2));
-        if (AMP) { e.x = round_fp16_3(e.x); e.y = round_fp16_3(e.y); e.z = round_fp16_3(e.z); e.w = round_fp16_3(e.w); }
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-        if (TRAIN) {
-          x0 = __ldg(xp + (long long)(4 * c) * a.x.sD); x1 = __ldg(xp + (long long)(4 * c + 1) * a.x.sD);
-          x2 = __ldg(xp + (long long)(4 * c + 2) * a.x.sD); x3 = __ldg(xp + (long long)(4 * c + 3) * a.x.sD);
-        }
-        qp[(long long)(4 * c) * a.qD] = ste_value(TRAIN, e.x, x0, acc);
-        qp[(long long)(4 * c + 1) * a.qD] = ste_value(TRAIN, e.y, x1, acc);
-        qp[(long long)(4 * c + 2) * a.qD] = ste_value(TRAIN, e.z, x2, acc);
-        qp[(long long)(4 * c + 3) * a.qD] = ste_value(TRAIN, e.w, x3, acc);
-      }
-    }
-  }
-  return acc;
-}
-
-// one rescored row: its quantized values, lanes of the half-warp along d (xs = the row in shared memory)
-__device__ __forceinline__ float gather_one_row(const Tc3Args& a, bool TRAIN, bool AMP, int img, int p, int k, const float* xs, int hl) {
-  float acc = 0.f;
-  const int D = (int)a.D;
-  const float* er = a.E + (long long)k * D;
-  float* qp = a.q + (long long)img * a.qB + p;
-  for (int d = hl; d < D; d += 16) {
-    float e = __ldg(er + d);
-    if (AMP) e = round_fp16_3(e);
-    qp[(long long)d * a.qD] = ste_value(TRAIN, e, TRAIN ? xs[d] : 0.f, acc);
-  }
-  return acc;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k3Threads, 1)
@@ -185,7 +94,6 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
   const uint32_t bar_tempty = bar_tfull + 16;                          // [2]       leader: 16 epilogue-warp arrivals
   const uint32_t bar_bload = bar_tempty + 16;                          // [k3MaxCC] local bulk-copy completion per code chunk
   const uint32_t bar_bready = bar_bload + 8 * k3MaxCC;                 // [k3MaxCC] leader: 2 (chunk resident in both CTAs)
-  const uint32_t bar_resolved = bar_bready + 8 * k3MaxCC;              // [2 tiles] 4 epilogue warps: the tile's undecided rows are queued
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Tc3Smem::off_tmem);
   float2* xsq = reinterpret_cast<float2*>(smem + Tc3Smem::off_xsq);
 
@@ -201,15 +109,6 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
     if (t < a.n_tiles) { img = t / a.tiles_per_image; p0 = (t - img * a.tiles_per_image) * k3Rows; }
     else { img = (int)a.B; p0 = 0; }
   };
-  const bool f_train = a.mode == VQSEG_MODE_TRAIN || a.mode == VQSEG_MODE_TRAIN_AMP;
-  const bool f_amp = a.mode == VQSEG_MODE_TRAIN_AMP || a.mode == VQSEG_MODE_EVAL_AMP;
-  auto gather_tile = [&](int img, int p0, const uint32_t* undecided, float* tile, int wg) -> float {
-    return gather_tile_rows(a, f_train, f_amp, img, p0, undecided, tile, wg, lane);
-  };
-  auto gather_row = [&](int img, int p, int k, const float* xs, int hl) -> float {
-    return gather_one_row(a, f_train, f_amp, img, p, k, xs, hl);
-  };
-  float loss_acc = 0.f;                                       // this lane's share of sum((q_ste - x)^2)
   auto issue_box = [&](int q, int issuer) {                   // box q goes to the stage its issuer owns
     const int tt = q / ops_per_tile, h = q - tt * ops_per_tile;
     int img, p0;
@@ -223,10 +122,6 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
     for (int s = 0; s < k3ASlots; ++s) { mbar_init(bar_afull + 8 * s, 16); mbar_init(bar_aempty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 16); }
     for (int c = 0; c < k3MaxCC; ++c) { mbar_init(bar_bload + 8 * c, 1); mbar_init(bar_bready + 8 * c, 2); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_resolved + 8 * b, 4);
-      *reinterpret_cast<int*>(smem + Tc3Smem::off_queue + b * Tc3Smem::kQueueBytes) = 0;
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 16) {
@@ -300,66 +195,6 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
         mbar_arrive(bar_sempty + 8 * s);                                   // stage free for the next box
         if (hh == 1) mbar_arrive_cluster_relaxed(lead_afull + 8 * slot);   // chunk complete; leader's barrier (remote for rank 1)
       }
-    }
-    if (a.local_rescore) {
-      // ================= fused tail of the converter warps =================
-      // (1) fused forward: the decided rows of every tile but the last are written here (the epilogue warps are busy
-      //     with the next tile; they take the last one);
-      // (2) the undecided rows of ALL of this CTA's (<= 2) tiles are re-scored in combined passes of 16 rows, two per
-      //     warp, instead of by a separate kernel (7 us of kernel + a launch boundary for ~11 rows per CTA).
-      // Scratch: the A ring and the staging ring (80 KiB, contiguous) -- free once the last MMAs have released the
-      // A slots; it changes hands between gather tiles and rescoring rows at a named barrier.
-      const int n_chunks = my_tiles * a.n_dc;
-      for (int k = n_chunks > 2 ? n_chunks - 2 : 0; k < n_chunks; ++k) mbar_wait(bar_aempty + 8 * (k & 1), ((uint32_t)k >> 1) & 1);
-      if (a.fuse_gather) {
-        for (int tt = 0; tt + 1 < my_tiles; ++tt) {
-          if (warp == 0) VQ3_TRACE(0, 200 + 4 * tt);
-          mbar_wait(bar_resolved + 8 * (tt & 1), 0);
-          int img, p0;
-          tile_coords(tt, img, p0);
-          const unsigned char* qb = smem + Tc3Smem::off_queue + (tt & 1) * Tc3Smem::kQueueBytes;
-          loss_acc += gather_tile(img, p0, reinterpret_cast<const uint32_t*>(qb + 16),
-                                  reinterpret_cast<float*>(smem + Tc3Smem::off_a) + (size_t)warp * 1024, warp);
-          if (warp == 0) VQ3_TRACE(0, 201 + 4 * tt);
-        }
-        asm volatile("bar.sync 10, 256;" ::: "memory");
-      }
-      const int D = (int)a.D;
-      const int xs_stride = (D + 3) & ~3, es_stride = xs_stride + 4;
-      int stage_cap = (Tc3Smem::scratch_bytes / 64 - xs_stride) / es_stride;     // 16 half-warp rows share the scratch
-      stage_cap = stage_cap > kRsStage ? kRsStage : (stage_cap < 1 ? 1 : stage_cap);
-      const int row_floats = xs_stride + stage_cap * es_stride;
-      float* xs_w = reinterpret_cast<float*>(smem + Tc3Smem::off_a) + (size_t)(2 * warp) * row_floats;
-      const int hw = lane >> 4, hl = lane & 15;
-      int nq[2] = {0, 0};
-      for (int tt = 0; tt < my_tiles; ++tt) {
-        mbar_wait(bar_resolved + 8 * (tt & 1), 0);
-        nq[tt & 1] = *reinterpret_cast<const volatile int*>(smem + Tc3Smem::off_queue + (tt & 1) * Tc3Smem::kQueueBytes);
-      }
-      if (warp == 0) VQ3_TRACE(0, 210);
-      const int nq_all = nq[0] + nq[1];
-      for (int e0 = 0; e0 < nq_all; e0 += 16) {
-        const int e = e0 + 2 * warp + hw;
-        const bool valid = e < nq_all;
-        const int tt = (valid && e >= nq[0]) ? 1 : 0;              // entries of tile 0 first, then tile 1
-        const unsigned char* qb = smem + Tc3Smem::off_queue + tt * Tc3Smem::kQueueBytes;
-        int img, p0;
-        tile_coords(tt, img, p0);
-        const int pr = valid ? p0 + (int)qb[32 + (tt ? e - nq[0] : e)] : 0;
-        const long long n = valid ? (long long)img * a.P + pr : 0;
-        int rec_v = 0;
-        if (valid && hl < 12) rec_v = reinterpret_cast<const int*>(a.work + n)[hl];
-        float best; int best_k, row;
-        rescore_two_rows(a.x, a.E, a.K, a.enorm, a.kblock, rec_v, valid, xs_w, row_floats, stage_cap, lane, best, best_k, row);
-        if (hl == 0 && valid) {
-          a.idx_out[row] = (long long)best_k + a.code_base;
-          if (a.counts_out) atomicAdd(a.counts_out + best_k, 1ull);
-        }
-        if (a.fuse_gather && valid)                                // the settled row's quantized values, half-warp along d
-          loss_acc += gather_row(img, pr, best_k, xs_w + (size_t)hw * row_floats, hl);
-        __syncwarp();
-      }
-      if (warp == 0) VQ3_TRACE(0, 211);
     }
   } else if (warp < 16) {
     // ================= epilogue =================
@@ -465,17 +300,13 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
         }
         const bool flagged = in_range && !unique;
         const uint32_t fm = __ballot_sync(0xffffffffu, flagged);
-        unsigned char* qb = smem + Tc3Smem::off_queue + (tt & 1) * Tc3Smem::kQueueBytes;
         if (fm) {
           int base = 0;
-          if (lane == 0) base = a.local_rescore ? atomicAdd(reinterpret_cast<int*>(qb), __popc(fm)) : atomicAdd(a.work_count, __popc(fm));
+          if (lane == 0) base = atomicAdd(a.work_count, __popc(fm));
           base = __shfl_sync(0xffffffffu, base, 0);
           if (flagged) {
-            // one 48-byte record per undecided row (cnt > cap => the exact pass scans all codes): in the global list, or
-            // -- fused rescoring -- in the row's own slot with its tile-local index queued in shared memory
-            const int pos = base + __popc(fm & ((1u << lane) - 1));
-            int* rec = reinterpret_cast<int*>(a.work + (a.local_rescore ? n : (long long)pos));
-            if (a.local_rescore) qb[32 + pos] = (unsigned char)r;
+            // one 48-byte record per undecided row (cnt > cap => the exact pass scans all codes)
+            int* rec = reinterpret_cast<int*>(a.work + (base + __popc(fm & ((1u << lane) - 1))));
             int nc = 0;
             if (!overflow) {
               for (int e = 0; e < cnt; ++e) { int k = cand[e]; if (k < a.K && nc < k3CandCap) rec[4 + nc++] = k; else if (k < a.K) overflow = true; }
@@ -485,29 +316,8 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
             rec[1] = (overflow || nc == 0) ? k3CandCap + 1 : nc;
           }
         }
-        if (a.local_rescore) {
-          __syncwarp();
-          if (lane == 0) {
-            reinterpret_cast<uint32_t*>(qb + 16)[quarter] = fm;          // rows the gather must leave to the rescoring warps
-            mbar_arrive(bar_resolved + 8 * (tt & 1));                    // release: this warp's indices, records, queue entries
-          }
-        }
       }
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // lists / xchg free for the next tile
-    }
-    if (a.fuse_gather && my_tiles > 0) {
-      // the last tile's decided rows: every MMA has retired (both accumulators of the last tile were read), so the
-      // codebook operand's shared memory is free to stage the 64 x 32 gather tiles
-      const int tt = my_tiles - 1;
-      if (warp == 8) VQ3_TRACE(2, 200);
-      mbar_wait(bar_resolved + 8 * (tt & 1), 0);
-      if (warp == 8) VQ3_TRACE(2, 201);
-      int img, p0;
-      tile_coords(tt, img, p0);
-      const unsigned char* qb = smem + Tc3Smem::off_queue + (tt & 1) * Tc3Smem::kQueueBytes;
-      loss_acc += gather_tile(img, p0, reinterpret_cast<const uint32_t*>(qb + 16),
-                              reinterpret_cast<float*>(smem + Tc3Smem::off_b) + (size_t)(warp - 8) * 1024, warp - 8);
-      if (warp == 8) VQ3_TRACE(2, 202);
     }
   } else if (warp == 16) {
     if (rank == 0) {
@@ -610,47 +420,8 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
 
   // ---- teardown ----
   stamp(2);
-  if (a.fuse_gather) {
-    if (warp < 16) {
-#pragma unroll
-      for (int o = 16; o; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
-      if (lane == 0) reinterpret_cast<float*>(smem + Tc3Smem::off_loss)[warp] = loss_acc;
-    }
-    __threadfence();                       // this CTA's counts / indices / rows before its ticket
-  }
   tc_fence_before();
   __syncthreads();
-  if (a.fuse_gather && warp == 0) {
-    // fixed-order reductions: 16 warp partials -> one partial per CTA; the LAST CTA through (ticket) sums the CTA
-    // partials in index order (fp64) and turns the now final per-code counts into the code usage
-    int last = 0;
-    if (lane == 0) {
-      const float* wl = reinterpret_cast<const float*>(smem + Tc3Smem::off_loss);
-      float sum = 0.f;
-      for (int w = 0; w < 16; ++w) sum += wl[w];
-      if (a.partial) a.partial[blockIdx.x] = sum;
-      __threadfence();
-      last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence();
-      if (a.loss_out) {
-        double sl = 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) sl += (double)__ldcg(a.partial + i);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
-        if (lane == 0) *a.loss_out = (float)(sl * a.inv_numel);
-      }
-      if (a.usage_out) {
-        int z = 0;
-        for (int k = lane; k < a.K; k += 32) z += (__ldcg(a.counts_out + k) == 0ull);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-        if (lane == 0) *a.usage_out = __fmul_rn(100.f, __fdiv_rn((float)z, (float)a.K));
-      }
-    }
-  }
   cluster_sync_all();
   stamp(3);
   if (warp == 16) {
@@ -683,12 +454,6 @@ bool tc3_supported(const Rows& x, int n_cc, int n_dc) {
   if (x.B > 1 && ((x.sB & 3) != 0 || x.sB <= 0)) return false;
   if (x.P >= (1ll << 31) || x.D >= (1ll << 31) || x.B >= (1ll << 31)) return false;
   return encode_tiled_fn() != nullptr;
-}
-
-bool tc3_rescores_locally(int n_ptiles, bool force_rescore) {
-  int pairs = num_sms() / 2;
-  if (n_ptiles < pairs) pairs = n_ptiles;
-  return !force_rescore && pairs > 0 && n_ptiles <= 2 * pairs;
 }
 
 int launch_assign_tc3(const Rows& x, const Tc3Args& a, cudaStream_t st) {

@@ -62,15 +62,6 @@ int launch_assign_tc2(const Tc2Args& a, cudaStream_t st);
 
 // ---- assign_tc3.cu: TMA-fed CTA-pair, codebook-resident tcgen05 filter (pixel-contiguous / NCHW inputs)
 struct Tc3Args {
-  Rows x;                         // the same view as B, P, D below with its strides (row pointers for the fused rescoring)
-  const float* E; const float* enorm; int kblock;      // exact-scorer operands of the fused rescoring tail
-  int local_rescore;              // 1: every CTA has <= 2 tiles and rescoring its own undecided rows (no separate pass)
-  // fused forward (requires local_rescore): the CTA also writes the quantized rows of its tiles and the last CTA
-  // through reduces the commitment loss and the code usage -- vq_img.py:169-175,236-239 in the same launch
-  int fuse_gather; int mode;      // VQSEG_MODE_*
-  float* q; long long qB, qD;     // quantized output, pixel-contiguous like x
-  float* partial;                 // one loss partial per CTA
-  int* ticket; float* loss_out; double inv_numel; float* usage_out;
   long long B, P, D;              // logical (B, P, D) view; memory is pixel-contiguous (sP == 1)
   long long n_rows;
   const unsigned char* blob;
@@ -84,7 +75,6 @@ struct Tc3Args {
   long long* trace;
 };
 bool tc3_supported(const Rows& x, int n_cc, int n_dc);
-bool tc3_rescores_locally(int n_ptiles, bool force_rescore);   // true: launch_assign_tc3 leaves nothing for launch_exact
 int launch_assign_tc3(const Rows& x, const Tc3Args& a, cudaStream_t st);
 
 }  // namespace vqseg
