@@ -116,6 +116,196 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# =====================================================================================================================
+# extras: the other BASELINE.json configs, measured in the same run (the headline keys above stay config 2)
+# =====================================================================================================================
+def _ev_time(fn, iters, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def extras_c1(dev):
+    """configs[0] on the GPU: VectorQuantizer train-mode forward + backward at the three resnet50 latent shapes of a
+    2x3x512x512 batch (models/encoders/resnet.py:150-162), K=512, through the public module."""
+    import vq_seg_b200 as V
+    out = {}
+    for name, (b, c, h, w) in {"l3": (2, 512, 64, 64), "l4": (2, 1024, 32, 32), "l5": (2, 2048, 16, 16)}.items():
+        g = torch.Generator(device=dev).manual_seed(42)
+        m = V.VectorQuantizer(dim=c, num_embeddings=512).to(dev).train()
+        m.codebook.embedding.weight.data.normal_(generator=g)
+        x = torch.randn(b, c, h, w, generator=g, device=dev, requires_grad=True)
+        gq = torch.randn(b, c, h, w, generator=g, device=dev)
+        one = torch.ones(1, device=dev)
+
+        def step():
+            q, idx, loss, usage = m(x)
+            torch.autograd.backward((q, loss), (gq, one))
+            x.grad = None
+        us = _ev_time(step, 30, 5) * 1e3
+        with torch.no_grad():
+            m.eval()
+            us_eval = _ev_time(lambda: m(x), 30, 5) * 1e3
+        n = b * h * w
+        out[name] = {"shape": [b, c, h, w], "train_fwd_bwd_us": us, "eval_fwd_us": us_eval, "train_vectors_per_s": n / (us * 1e-6)}
+    return out
+
+
+def extras_c4(dev, rank, world, n_total=10_000_000, d=512, k=1024, iters=3):
+    """configs[3]: k-means codebook init (vq_img.py:29-63), N = 10 M latent vectors, K=1024, D=512, rows sharded over
+    the ranks; every iteration = assign (tcgen05 filter + rescoring) + per-code counts and sums + ONE all-reduce of
+    counts and sums (inside the timed region) + finalize."""
+    import torch.distributed as dist
+    from vq_seg_b200 import ops, distributed as D
+    n = n_total // world
+    # synthetic latents WITH cluster structure (a mixture of K Gaussians: centres randn, sigma 0.5) -- k-means on pure
+    # iid noise has no structure to find, and its near-zero centroids make every code a near-tie for every row
+    gc = torch.Generator(device=dev).manual_seed(99)
+    centres = torch.randn(k, d, generator=gc, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.empty(1, n, d, device=dev)
+    for i in range(0, n, 1 << 20):
+        m = min(1 << 20, n - i)
+        x[0, i:i + m].normal_(generator=g).mul_(0.5)
+        x[0, i:i + m] += centres[torch.randint(0, k, (m,), generator=g, device=dev)]
+    means = x[0, :k].clone()                                  # sample_vectors (vq_img.py:10-17): K rows of the data
+    if world > 1:
+        dist.broadcast(means, src=0)
+    rescored = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    t_assign, t_stats, t_ar, t_iter = [], [], [], []
+    for it in range(iters + 1):
+        ev[0].record()
+        blob = ops.prepare_codebook(means)
+        buckets, _ = ops.assign(x, means, blob, ops.ALGO_AUTO)
+        ev[1].record()
+        ws = ops._last_assign_ws
+        bins, sums = ops.code_stats(x, buckets, k, False)
+        ev[2].record()
+        D.allreduce_code_stats(bins, sums)
+        ev[3].record()
+        ops.kmeans_finalize(sums, bins, means, False)
+        ev[4].record()
+        torch.cuda.synchronize()
+        if it > 0:                                            # first iteration = warm-up
+            rescored.append(ws[:4].view(torch.int32).item() / n)
+            t_assign.append(ev[0].elapsed_time(ev[1])); t_stats.append(ev[1].elapsed_time(ev[2]))
+            t_ar.append(ev[2].elapsed_time(ev[3])); t_iter.append(ev[0].elapsed_time(ev[4]))
+    # the bit-exact ordered statistics (the reference's scatter_add_ order), once
+    det_ms = _ev_time(lambda: ops.code_stats(x, buckets, k, True), 1, 1)
+    vals = torch.tensor([statistics.median(t_assign), statistics.median(t_stats), statistics.median(t_ar),
+                         statistics.median(t_iter), det_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    a_ms, s_ms, ar_ms, it_ms, det_ms = [float(v) for v in vals.tolist()]
+    total = int(bins.sum().item())
+    return {"rows_total": n * world, "rows_per_gpu": n, "D": d, "K": k, "iter_ms": it_ms, "assign_ms": a_ms, "stats_atomic_ms": s_ms,
+            "allreduce_ms": ar_ms, "allreduce_bytes": k * 8 + k * d * 4, "stats_ordered_ms": det_ms,
+            "vector_iters_per_s": n * world / (it_ms * 1e-3), "assign_tflops_per_gpu": 2.0 * n * k * d / (a_ms * 1e-3) / 1e12,
+            "stats_atomic_GBps_per_gpu": (4.0 * n * d + 8.0 * n) / (s_ms * 1e-3) / 1e9,
+            "counts_sum_equals_rows": total == n * world, "rows_rescored_frac": max(rescored),
+            "data": "mixture of K Gaussians (centres randn, sigma 0.5), rank-seeded; start = K rows of rank 0", "collective": "all_reduce(SUM) of counts[K] int64 + sums[K,D] fp32, inside the timed iteration",
+            "scaling": "strong (10 M rows split over the ranks)"}
+
+
+def extras_c5(dev, rank, world, n=4 << 20, d=256, k=65536):
+    """configs[4]: large-codebook assignment, N = 4 Mi rows, K = 65536, D = 256.  (a) codebook-sharded: every rank
+    scores ALL rows against K / world codes and the ranks MIN-all-reduce 8-byte (distance, index) keys (inside the
+    timed region); (b) row-sharded: every rank scores N / world rows against the whole codebook, no exchange."""
+    import torch.distributed as dist
+    from vq_seg_b200 import ops, distributed as D
+    g = torch.Generator(device=dev).manual_seed(77)           # same rows and codebook on every rank
+    x = torch.empty(1, n, d, device=dev)
+    for i in range(0, n, 1 << 20):
+        x[0, i:i + (1 << 20)].normal_(generator=g)
+    e = torch.randn(k, d, generator=g, device=dev)
+    kl = k // world
+    shard = e[rank * kl:(rank + 1) * kl].contiguous()
+    blob_s = ops.prepare_codebook(shard)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_local, t_ar = [], []
+    idx = None
+    for it in range(2):
+        ev[0].record()
+        keys = ops.assign_keys(x, shard, blob_s, rank * kl, ops.ALGO_AUTO)
+        ev[1].record()
+        if world > 1:
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+        idx, dd, counts = ops.unpack_keys(keys, k)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if it > 0 or world == 1:
+            t_local.append(ev[0].elapsed_time(ev[1])); t_ar.append(ev[1].elapsed_time(ev[2]))
+    # (b) row-sharded over the whole codebook
+    nl = n // world
+    xs = x[:, rank * nl:(rank + 1) * nl]
+    blob = ops.prepare_codebook(e)
+    t_rows = _ev_time(lambda: ops.assign(xs, e, blob, ops.ALGO_AUTO), 1, 0 if world == 1 else 1)
+    idx_rows, _ = ops.assign(xs, e, blob, ops.ALGO_AUTO)
+    same = bool(torch.equal(idx_rows, idx[:, rank * nl:(rank + 1) * nl]))
+    vals = torch.tensor([min(t_local), min(t_ar), t_rows], device=dev)
+    flag = torch.tensor([int(same)], device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    l_ms, ar_ms, r_ms = [float(v) for v in vals.tolist()]
+    return {"rows": n, "D": d, "K": k, "codes_per_gpu": kl,
+            "sharded_local_assign_ms": l_ms, "sharded_min_allreduce_plus_unpack_ms": ar_ms, "allreduce_bytes": 8 * n,
+            "sharded_vectors_per_s": n / ((l_ms + ar_ms) * 1e-3), "sharded_assign_tflops_per_gpu": 2.0 * n * kl * d / (l_ms * 1e-3) / 1e12,
+            "row_split_ms": r_ms, "row_split_vectors_per_s": n / (r_ms * 1e-3),
+            "row_split_assign_tflops_per_gpu": 2.0 * nl * k * d / (r_ms * 1e-3) / 1e12,
+            "sharded_equals_row_split": bool(flag.item() == 1),
+            "collective": "all_reduce(MIN) of (float_bits(dist) << 32 | index) int64 keys, inside the timed region"}
+
+
+def extras_cpu_port(budget_s=25.0):
+    """The reference's CPU path (oracle port, or the live module when /root/reference exists) beside the extras, at the
+    largest sizes that finish in seconds: it cannot hold configs 4 and 5 at full size."""
+    from oracle import vq_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    out = {"cores": torch.get_num_threads(), "kind": "port"}
+    t_start = time.perf_counter()
+    g = torch.Generator().manual_seed(42)
+    for name, (b, c, h, w) in {"l3": (2, 512, 64, 64), "l4": (2, 1024, 32, 32), "l5": (2, 2048, 16, 16)}.items():
+        m = O.OracleVectorQuantizer(dim=c, num_embeddings=512)
+        m.faithful_ops = True
+        m.train()
+        x = torch.randn(b, c, h, w, generator=g, requires_grad=True)
+        gq = torch.randn(b, c, h, w, generator=g)
+        best = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            q, idx, loss, usage = m(x)
+            torch.autograd.backward((q, loss), (gq, torch.ones(1)))
+            x.grad = None
+            best = min(best, time.perf_counter() - t0)
+        out["c1_" + name + "_train_fwd_bwd_ms"] = best * 1e3
+    if time.perf_counter() - t_start < budget_s:
+        n, d, k = 100_000, 512, 1024
+        xs = torch.randn(1, n, d, generator=g)
+        t0 = time.perf_counter()
+        O.kmeans(xs, k, 1, init_indices=torch.arange(k))
+        dt = time.perf_counter() - t0
+        out["c4_sample"] = f"N={n}, K={k}, D={d}, 1 Lloyd iteration (the reference needs ~100 GB of temporaries at N=1e7)"
+        out["c4_vector_iters_per_s"] = n / dt
+    if time.perf_counter() - t_start < budget_s:
+        n, d, k = 2048, 256, 65536
+        xs, e = torch.randn(1, n, d, generator=g), torch.randn(k, d, generator=g)
+        t0 = time.perf_counter()
+        O.assign_euclidean(xs, e)
+        dt = time.perf_counter() - t0
+        out["c5_sample"] = f"N={n} rows against K={k}, D={d} (the full N x K distance matrix would be 1.1 TB)"
+        out["c5_vectors_per_s"] = n / dt
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -125,6 +315,7 @@ def main():
     ap.add_argument("--ring", type=int, default=8, help="input batches cycled so the working set exceeds L2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extras (configs 1, 4, 5, multi-GPU parity)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -316,6 +507,26 @@ def main():
         e2e_s = t.item()
     e2e_val = N_VEC * world * e2e_steps / e2e_s
 
+    # ---- extras: the other BASELINE configs (and, for N > 1, the multi-GPU parity check), same run
+    extras = None
+    if not args.no_extras:
+        extras = {}
+        try:
+            if world == 1:
+                extras["c1_vqreptunet_layers_train_fwd_bwd"] = extras_c1(dev)
+            torch.cuda.empty_cache()
+            extras["c4_kmeans_10M_K1024_D512"] = extras_c4(dev, rank, world)
+            torch.cuda.empty_cache()
+            extras["c5_K65536_D256_N4Mi"] = extras_c5(dev, rank, world)
+            torch.cuda.empty_cache()
+            if world > 1:
+                sys.path.insert(0, os.path.join(ROOT, "scripts"))
+                from multi_gpu_parity import run_parity
+                extras["parity"] = run_parity(rank, world, dev)
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                extras["cpu_port"] = extras_cpu_port()
+        except Exception as exc:                            # the headline line must still print
+            extras["error"] = f"{type(exc).__name__}: {exc}"
     if rank == 0:
         peaks = {}
         try:
@@ -358,7 +569,7 @@ def main():
                         "d2h_bytes_per_step": N_VEC * 8 + 4, "steps": e2e_steps,
                         "how": "VectorQuantizer.forward (eval) per step; H2D of step i+1 on a copy stream overlaps step i; best of 3 passes"},
                 "gpu_launches": 4 * args.steps,   # per step: zeroing, tcgen05 filter, exact pass, gather
-                 "clocks": sampler.summary()}
+                 "clocks": sampler.summary(), "extras": extras}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -349,7 +349,6 @@ def stage_big():
 def stage_shapes():
     """filter / rescoring kernel times (CUDA events inside the C ABI) over the BASELINE shapes"""
     from vq_seg_b200 import _native
-    L = _native.lib()
     shapes = {"C2": (8, 256, 64, 64, 512), "C1 l3": (2, 512, 64, 64, 512), "C1 l4": (2, 1024, 32, 32, 512),
               "C1 l5": (2, 2048, 16, 16, 512), "C3 l3": (4, 512, 64, 64, 512), "C3 l4": (4, 1024, 32, 32, 512),
               "C3 l5": (4, 2048, 16, 16, 512), "r448 l3": (4, 512, 56, 56, 512), "K4096": (8, 256, 64, 64, 4096),
@@ -366,12 +365,13 @@ def stage_shapes():
         blob = ops.prepare_codebook(e)
         for _ in range(3):
             ops.assign(xv, e, blob, ops.ALGO_TC)
-        L.vqseg_set_kernel_timing(1)
+        prof = _native.ProfileEvents()
+        ops.set_profile_events(prof)
         kt, rt = [], []
         for _ in range(10):
             ops.assign(xv, e, blob, ops.ALGO_TC); torch.cuda.synchronize()
-            kt.append(L.vqseg_get_kernel_timing_ms(0) * 1e3); rt.append(L.vqseg_get_kernel_timing_ms(1) * 1e3)
-        L.vqseg_set_kernel_timing(0)
+            kt.append(prof.filter_ms() * 1e3); rt.append(prof.rescore_ms() * 1e3)
+        ops.set_profile_events(None)
         kt.sort(); rt.sort()
         n = xv.shape[0] * xv.shape[1]
         flagged = ops._last_assign_ws[:4].view(torch.int32).item()
