@@ -42,6 +42,7 @@ extern "C" {
 #define VQSEG_ALGO_TC_STREAM 3       /*   ... the single-CTA streaming kernel (any K, D, strides)                  */
 #define VQSEG_ALGO_TC_PAIR   4       /*   ... the codebook-resident CTA-pair kernel, x through registers (any strides) */
 #define VQSEG_ALGO_TC_TMA    5       /*   ... the codebook-resident CTA-pair kernel, x by TMA tensor loads (NCHW maps) */
+#define VQSEG_ALGO_TC_STREAM_PAIR 6  /*   ... the streaming CTA-pair kernel, x by TMA (NCHW maps or packed rows, D <= 512) */
 /* 3-5 force one kernel (VQSEG_EUNSUPPORTED if the shape does not fit it): the tests cover all three on the same inputs */
 
 /* gather modes */

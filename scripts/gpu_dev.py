@@ -379,6 +379,45 @@ def stage_shapes():
         print(f"[shapes] {nm:16s} N={n:7d} D={c:5d} K={k:6d}: filter {kt[5]:8.1f} us ({fl / kt[5] / 1e6:7.1f} TFLOP/s)  rescoring {rt[5]:7.1f} us  rescored {100.0 * flagged / n:5.1f}%", flush=True)
 
 
+def stage_stream():
+    """the two streaming filters (single CTA / TMA-fed CTA pair) side by side on the k-means and large-codebook shapes"""
+    from vq_seg_b200 import _native
+    shapes = {"C4 rows 256k": ("rows", 262144, 512, 1024), "C4 rows 1M": ("rows", 1 << 20, 512, 1024),
+              "C5 rows 64k": ("rows", 65536, 256, 65536), "K4096 nchw": ("nchw", 32768, 256, 4096),
+              "K16384 nchw": ("nchw", 16384, 256, 16384), "D128 K2304 rows": ("rows", 262144, 128, 2304),
+              "D512 K512 nchw": ("nchw", 65536, 512, 512)}
+    sel = sys.argv[2:]
+    for nm, (lay, n, d, k) in shapes.items():
+        if sel and not any(s in nm for s in sel):
+            continue
+        g = torch.Generator(device="cuda").manual_seed(3)
+        if lay == "rows":
+            xv = torch.randn(1, n, d, generator=g, device=dev)
+        else:
+            xv = torch.relu(torch.randn(4, d, n // 4, generator=g, device=dev)).permute(0, 2, 1)
+        e = torch.randn(k, d, generator=g, device=dev)
+        blob = ops.prepare_codebook(e)
+        res = {}
+        for an, algo in (("single", ops.ALGO_TC_STREAM), ("pair", ops.ALGO_TC_STREAM_PAIR)):
+            for _ in range(2):
+                out = ops.assign(xv, e, blob, algo)
+            prof = _native.ProfileEvents()
+            ops.set_profile_events(prof)
+            kt, rt = [], []
+            for _ in range(5):
+                out = ops.assign(xv, e, blob, algo); torch.cuda.synchronize()
+                kt.append(prof.filter_ms() * 1e3); rt.append(prof.rescore_ms() * 1e3)
+            ops.set_profile_events(None)
+            kt.sort(); rt.sort()
+            flagged = ops._last_assign_ws[:4].view(torch.int32).item()
+            res[an] = (kt[2], rt[2], flagged, out)
+        fl = 2.0 * n * k * d
+        same = torch.equal(res["single"][3][0], res["pair"][3][0])
+        print(f"[stream] {nm:16s} N={n:8d} D={d:4d} K={k:6d}: single {res['single'][0]:9.1f} us ({fl / res['single'][0] / 1e6:6.1f} TF)  "
+              f"pair {res['pair'][0]:9.1f} us ({fl / res['pair'][0] / 1e6:6.1f} TF)  rescoring {res['pair'][1]:7.1f} us  "
+              f"rescored {100.0 * res['pair'][2] / n:4.1f}%  same idx {same}", flush=True)
+
+
 def stage_null():
     from vq_seg_b200 import _native
     L = _native.lib()
@@ -454,5 +493,5 @@ def stage_trace():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "seghead": stage_seghead, "big": stage_big, "shapes": stage_shapes, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "seghead": stage_seghead, "big": stage_big, "shapes": stage_shapes, "stream": stage_stream, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

@@ -56,18 +56,20 @@ def test_assign_matches_golden(dev, golden, name, algo):
     assert torch.equal(counts.cpu(), rec["counts"])
 
 
-@pytest.mark.parametrize("kernel", ["stream", "pair", "tma"])
+@pytest.mark.parametrize("kernel", ["stream", "pair", "tma", "stream_pair"])
 @pytest.mark.parametrize("name", ["c2_randn", "c2_relu", "d64", "odd_7x7", "k_not_tile", "dup_codes", "equidistant", "x_equals_code"])
 def test_every_tensor_core_kernel_on_resident_shapes(dev, golden, name, kernel):
-    """Shapes that fit the codebook-resident kernels, forced through each of the three tcgen05 filters in turn
-    (single-CTA streaming, CTA pair fed through registers, CTA pair fed by TMA): all must reproduce the reference."""
+    """Shapes that fit the codebook-resident kernels, forced through each of the four tcgen05 filters in turn
+    (single-CTA streaming, CTA pair fed through registers, CTA pair fed by TMA, streaming CTA pair fed by TMA): all
+    must reproduce the reference."""
     from vq_seg_b200 import ops
     x, e = cases.FORWARD_CASES[name]()
     rec = golden["forward"][name]
     xd, ed = x.to(dev), e.to(dev)
     blob = ops.prepare_codebook(ed)
-    algo = {"stream": ops.ALGO_TC_STREAM, "pair": ops.ALGO_TC_PAIR, "tma": ops.ALGO_TC_TMA}[kernel]
-    if kernel == "tma" and (x.shape[2] * x.shape[3]) % 4 != 0:
+    algo = {"stream": ops.ALGO_TC_STREAM, "pair": ops.ALGO_TC_PAIR, "tma": ops.ALGO_TC_TMA,
+            "stream_pair": ops.ALGO_TC_STREAM_PAIR}[kernel]
+    if kernel in ("tma", "stream_pair") and (x.shape[2] * x.shape[3]) % 4 != 0:
         # a tensor map needs 16-byte strides: such maps are refused when forced (ALGO_TC / AUTO take the register-fed kernel)
         with pytest.raises(RuntimeError, match="not supported"):
             ops.assign(view(xd), ed, blob, algo)
@@ -87,6 +89,33 @@ def test_kblock_override_changes_only_near_ties(dev):
     i_auto, _ = ops.assign(view(xd), ed, None, ops.ALGO_EXACT, 0)
     i_one, _ = ops.assign(view(xd), ed, None, ops.ALGO_EXACT, 1 << 20)       # one chain, no split
     assert near_tie_ok(x, e, i_one.cpu(), i_auto.cpu())
+
+
+@pytest.mark.parametrize("layout", ["nchw", "rows"])
+@pytest.mark.parametrize("shape", [
+    # (B, P, D, K): the k-means shapes of BASELINE configs 4 / 5 in small, ragged tiles, few and many dim chunks
+    (2, 4096, 512, 1024), (3, 1000, 512, 700), (1, 20000, 256, 4096), (2, 3000, 128, 2304), (4, 2500, 40, 3000),
+    (1, 131, 512, 1024), (5, 36, 320, 1500), (2, 8192, 64, 256),
+])
+def test_streaming_pair_kernel_equals_exact(dev, shape, layout):
+    """The TMA-fed streaming CTA-pair filter (assign_tc4.cu; k-means assignment, vq_img.py:39-41, and codebooks too
+    large to stay resident) forced on NCHW maps and on packed sample rows: indices and counts bit-equal to the
+    exact scorer (which the golden tests pin to the reference)."""
+    from vq_seg_b200 import ops
+    B, P, D, K = shape
+    if layout == "nchw" and P % 4 != 0:
+        P += 4 - P % 4                                   # tensor maps need 16-byte strides
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + D + K)
+    centres = torch.randn(K, D, generator=g, device=dev)
+    pick = torch.randint(0, K, (B, P), generator=g, device=dev)
+    rows = centres[pick] * 0.7 + 0.8 * torch.randn(B, P, D, generator=g, device=dev)
+    xv = rows.permute(0, 2, 1).contiguous().permute(0, 2, 1) if layout == "nchw" else rows
+    blob = ops.prepare_codebook(centres)
+    i1, c1 = ops.assign(xv, centres, None, ops.ALGO_EXACT)
+    i2, c2 = ops.assign(xv, centres, blob, ops.ALGO_TC_STREAM_PAIR)
+    torch.cuda.synchronize()
+    assert torch.equal(i1, i2), f"{(i1 != i2).sum().item()} of {i1.numel()} rows differ"
+    assert torch.equal(c1, c2)
 
 
 def test_large_codebook_streaming(dev):

@@ -188,7 +188,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   bool use_tc = false;
   if (algo == VQSEG_ALGO_AUTO) use_tc = blob != nullptr && n_rows >= 64 && K >= 32;
   else if (algo == VQSEG_ALGO_EXACT) use_tc = false;
-  else if (algo >= VQSEG_ALGO_TC && algo <= VQSEG_ALGO_TC_TMA) { if (!blob) return VQSEG_EINVAL; use_tc = true; }
+  else if (algo >= VQSEG_ALGO_TC && algo <= VQSEG_ALGO_TC_STREAM_PAIR) { if (!blob) return VQSEG_EINVAL; use_tc = true; }
   else return VQSEG_EINVAL;
 
   // prologue: zeroing + (when a prepared codebook is used) the guard that rebuilds a stale blob in place
@@ -223,8 +223,12 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   const int n_cc = (int)(kp / 256), n_dc = (int)(dp / kDChunk);
   const bool force = (best_key_out != nullptr || idx_out == nullptr);
   const bool can3 = tc3_supported(xr, n_cc, n_dc), can2 = tc2_supported(n_cc, n_dc);
-  int kernel = can3 ? 3 : (can2 ? 2 : 1);
+  const int lay4 = tc4_layout(xr, kp, n_dc);
+  // codebook-resident kernels when the codebook fits two SMs; else the streaming pair kernel when its TMA layouts
+  // apply and there is at least one pair tile per SM pair to amortise the A conversion; else the single-CTA kernel
+  int kernel = can3 ? 3 : (can2 ? 2 : ((lay4 && n_rows >= 256ll * (num_sms() / 2)) ? 4 : 1));
   if (algo == VQSEG_ALGO_TC_STREAM) kernel = 1;
+  if (algo == VQSEG_ALGO_TC_STREAM_PAIR) { if (!lay4) return VQSEG_EUNSUPPORTED; kernel = 4; }
   if (algo == VQSEG_ALGO_TC_PAIR) { if (!can2) return VQSEG_EUNSUPPORTED; kernel = 2; }
   if (algo == VQSEG_ALGO_TC_TMA) { if (!can3) return VQSEG_EUNSUPPORTED; kernel = 3; }
   prof_record(prof_events, 0, st);
@@ -241,6 +245,19 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     t3.work = work; t3.work_count = work_count;
     t3.trace = dev_trace();
     rc = launch_assign_tc3(xr, t3, st);
+  } else if (kernel == 4) {
+    Tc4Args t4;
+    memset(&t4, 0, sizeof(t4));
+    t4.B = B; t4.P = P; t4.D = D; t4.n_rows = n_rows; t4.blob = (const unsigned char*)blob;
+    if (lay4 == 1) { t4.tiles_per_image = (int)((P + 127) / 128); t4.n_tiles = (int)(B * t4.tiles_per_image); }
+    else { t4.tiles_per_image = 0; t4.n_tiles = (int)((n_rows + 127) / 128); }
+    t4.n_ptiles = (t4.n_tiles + 1) / 2; t4.n_cc = n_cc; t4.n_dc = n_dc;
+    t4.K = (int)K; t4.K_pad = (int)kp; t4.off_image = oi; t4.off_aug = oa; t4.off_enorm = oe;
+    t4.idx_out = (long long*)idx_out; t4.counts_out = (unsigned long long*)counts_out; t4.code_base = code_base;
+    t4.force_rescore = force ? 1 : 0;
+    t4.work = work; t4.work_count = work_count;
+    t4.trace = dev_trace();
+    rc = launch_assign_tc4(xr, t4, lay4, st);
   } else if (kernel == 2) {
     Tc2Args t2;
     memset(&t2, 0, sizeof(t2));

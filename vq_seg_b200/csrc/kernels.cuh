@@ -77,4 +77,21 @@ struct Tc3Args {
 bool tc3_supported(const Rows& x, int n_cc, int n_dc);
 int launch_assign_tc3(const Rows& x, const Tc3Args& a, cudaStream_t st);
 
+// ---- assign_tc4.cu: TMA-fed CTA-pair STREAMING tcgen05 filter (any K <= 65536, D_pad <= 512; NCHW maps or packed rows)
+struct Tc4Args {
+  long long B, P, D;              // logical (B, P, D) view
+  long long n_rows;
+  const unsigned char* blob;
+  int n_tiles, tiles_per_image;   // tiles of 128 rows (NCHW: 128 pixels of one image)
+  int n_ptiles, n_cc, n_dc;       // pair tiles (two tiles), code chunks of 256, dim chunks of 64
+  int K, K_pad;
+  unsigned long long off_image, off_aug, off_enorm;
+  long long* idx_out; unsigned long long* counts_out; long long code_base;
+  int force_rescore;
+  WorkRec* work; int* work_count;
+  long long* trace;
+};
+int tc4_layout(const Rows& x, long long K_pad, int n_dc);   // 0: unsupported, 1: NCHW maps, 2: packed rows
+int launch_assign_tc4(const Rows& x, const Tc4Args& a, int layout, cudaStream_t st);
+
 }  // namespace vqseg

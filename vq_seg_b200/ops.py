@@ -10,7 +10,7 @@ import torch
 
 from . import _native
 
-ALGO_AUTO, ALGO_EXACT, ALGO_TC, ALGO_TC_STREAM, ALGO_TC_PAIR, ALGO_TC_TMA = 0, 1, 2, 3, 4, 5
+ALGO_AUTO, ALGO_EXACT, ALGO_TC, ALGO_TC_STREAM, ALGO_TC_PAIR, ALGO_TC_TMA, ALGO_TC_STREAM_PAIR = 0, 1, 2, 3, 4, 5, 6
 MODE_EVAL, MODE_TRAIN, MODE_TRAIN_AMP, MODE_EVAL_AMP = 0, 1, 2, 3
 _last_assign_ws = None
 
