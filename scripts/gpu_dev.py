@@ -491,7 +491,61 @@ def stage_trace():
             print(f"  {names[role]}: " + " ".join(f"{i}:{v}" for i, v in ev))
 
 
+def stage_trace4():
+    """clock64 stamps of the streaming pair kernel's roles (developer build): where a unit's time goes"""
+    from vq_seg_b200 import _native, build
+    build.build(dev=True)
+    L = _native.use_dev_library()
+    which = sys.argv[2] if len(sys.argv) > 2 else "c5"
+    g = torch.Generator(device="cuda").manual_seed(3)
+    if which == "c5":
+        n, d, k = 148 * 128, 256, 8192          # one pair tile per CTA pair, 32 units
+    else:
+        n, d, k = 148 * 128 * 4, 512, 1024      # four pair tiles per CTA pair, 16 units
+    xv = torch.randn(1, n, d, generator=g, device=dev)
+    e = torch.randn(k, d, generator=g, device=dev)
+    blob = ops.prepare_codebook(e)
+    run = lambda: ops.assign(xv, e, blob, ops.ALGO_TC_STREAM_PAIR)
+    for _ in range(3):
+        run()
+    buf = torch.zeros(148 * 4 * 256 + 8, dtype=torch.int64, device=dev)
+    buf[-8] = 2 ** 62
+    L.vqseg_debug_set_trace(buf.data_ptr())
+    run()
+    torch.cuda.synchronize()
+    L.vqseg_debug_set_trace(None)
+    t = buf[:-8].cpu().reshape(148, 4, 256)
+    n_dc = d // 64
+    n_units = (k // 256) * (1 if which == "c5" else 4)
+    for cta in (0, 1, 100):
+        tt = t[cta]
+        ep = tt[2]
+        c0 = ep[0].item()
+        print(f"cta {cta}: epilogue(w8) per unit: [start-wait, waited, processed]")
+        line = []
+        for u in range(min(n_units, 60)):
+            line.append(f"{u}:{ep[4*u].item()-c0}/{ep[4*u+1].item()-ep[4*u].item()}/{ep[4*u+2].item()-ep[4*u+1].item()}")
+        print("   " + " ".join(line))
+        if cta % 2 == 0:
+            mm = tt[1]
+            line = []
+            for u in range(min(n_units, 56)):
+                line.append(f"{u}:{mm[128+2*u].item()-c0}/{mm[128+2*u+1].item()-mm[128+2*u].item()}")
+            print("  mma tempty [start, waited]: " + " ".join(line))
+            line = []
+            for bq in range(64):
+                if mm[2*bq] > 0:
+                    line.append(f"{bq}:{mm[2*bq].item()-c0}/{mm[2*bq+1].item()-mm[2*bq].item()}")
+            print("  mma bready (last 64 stages mod) [start, waited]: " + " ".join(line))
+        cv = tt[0]
+        line = []
+        for q in range(min(120, 2 * n_dc * 4)):
+            if cv[2*q] > 0:
+                line.append(f"{q}:{cv[2*q].item()-c0}/{cv[2*q+1].item()-cv[2*q].item()}")
+        print("  converter(w0) boxes [start, waited]: " + " ".join(line))
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "seghead": stage_seghead, "big": stage_big, "shapes": stage_shapes, "stream": stage_stream, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
+    {"exact": stage_exact, "tc": stage_tc, "ops": stage_ops, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "bw": stage_bw, "bwbulk": stage_bwbulk, "seghead": stage_seghead, "big": stage_big, "shapes": stage_shapes, "stream": stage_stream, "trace4": stage_trace4, "null": stage_null, "stats": stage_stats}[sys.argv[1]]()
     print(f"stage {sys.argv[1]} done in {time.time() - t0:.1f}s")

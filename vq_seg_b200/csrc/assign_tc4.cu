@@ -324,45 +324,50 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // lists / xchg free for the next tile
     }
   } else if (warp == 16) {
-    if (rank == 0) {
-      // ================= MMA issuer (leader CTA) =================
+    if (rank == 0 && elect_one()) {
+      // ================= MMA issuer (leader CTA): ONE thread, the leanest instruction stream we can give it ===========
+      // (tc_common.cuh "lean MMA issue": every instruction here is ~5 cycles of a 128-cycle MMA slot)
       const uint64_t aaug = make_desc_noswz(sbase + Tc4Smem::off_aaug, 128, 0);
-      int bq = 0;                                              // codebook stage sequence number
+      const uint32_t a_lo0 = desc_lo_sw128(sbase + Tc4Smem::off_a), b_lo0 = desc_lo_sw128(sbase + Tc4Smem::off_b);
+      const int n_dc = a.n_dc, n_cc = a.n_cc;
+      int slot0 = 0; uint32_t apar0 = 0;                       // first A slot of the current tile and its phase parity
+      int bs = 0; uint32_t bpar = 0;                           // codebook stage and its phase parity
+      uint32_t tpar = 0;                                       // bit b = parity of the next tempty phase of accumulator b
+      int u = 0;
       for (int tt = 0; tt < my_tiles; ++tt) {
-        for (int cc = 0; cc < a.n_cc; ++cc) {
-          const int u = tt * a.n_cc + cc, buf = u & 1;
+        int slot = slot0; uint32_t apar = apar0;
+        for (int cc = 0; cc < n_cc; ++cc, ++u) {
+          const int buf = u & 1;
+          const uint32_t acc = tmem_base + buf * 256;
           VQ4_TRACE(1, 128 + 2 * u);
-          mbar_wait(bar_tempty + 8 * buf, (((uint32_t)u >> 1) & 1) ^ 1);     // both CTAs' epilogues drained this accumulator
+          mbar_wait(bar_tempty + 8 * buf, ((tpar >> buf) & 1) ^ 1);          // both CTAs' epilogues drained this accumulator
+          tpar ^= 1u << buf;
           VQ4_TRACE(1, 128 + 2 * u + 1);
-          tc_fence_after();
-          const bool last_cc = cc == a.n_cc - 1;
-          for (int dc = 0; dc < a.n_dc; ++dc, ++bq) {
-            const int a_seq = tt * a.n_dc + dc, slot = a_seq % k4ASlots;
-            const int bs = bq % k4BStages;
-            if (cc == 0) mbar_wait(bar_afull + 8 * slot, ((uint32_t)(a_seq / k4ASlots)) & 1);   // both CTAs converted the chunk
-            VQ4_TRACE(1, (2 * bq) & 127);
-            mbar_wait(bar_bready + 8 * bs, ((uint32_t)(bq / k4BStages)) & 1);                   // both halves of the stage landed
-            VQ4_TRACE(1, (2 * bq + 1) & 127);
+          const bool last_cc = cc == n_cc - 1;
+          slot = slot0; apar = apar0;
+          for (int dc = 0; dc < n_dc; ++dc) {
+            if (cc == 0) mbar_wait(bar_afull + 8 * slot, apar);              // both CTAs converted the chunk
+            mbar_wait(bar_bready + 8 * bs, bpar);                            // both halves of the stage landed
             tc_fence_after();
-            if (lane == 0) {
-              const uint64_t ad = make_desc(sbase + Tc4Smem::off_a + slot * kTileBytes);
-              const uint64_t bd = make_desc(sbase + Tc4Smem::off_b + bs * kTileBytes);
-#pragma unroll
-              for (int k = 0; k < kDChunk / 16; ++k)
-                tc_mma_f16_2cta(tmem_base + buf * 256, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), k4Idesc, (dc | k) ? 1u : 0u);
-              if (dc == a.n_dc - 1) {
-                // the limb tile of this unit travelled with its first codebook stage (same barrier)
-                const uint64_t baug = make_desc_noswz(sbase + Tc4Smem::off_baug + buf * k4AugBytes, 128, 256);
-                tc_mma_f16_2cta(tmem_base + buf * 256, aaug, baug, k4Idesc, 1u);   // + s |e_k|^2
-                tc_commit_2cta(bar_gempty + 8 * buf);
-                tc_commit_2cta(bar_tfull + 8 * buf);
-              }
-              tc_commit_2cta(bar_bempty + 8 * bs);                           // codebook stage free in both CTAs
-              if (last_cc) tc_commit_2cta(bar_aempty + 8 * slot);            // A chunk free: the tile's last use of it
+            const uint32_t al = a_lo0 + (uint32_t)slot * (kTileBytes >> 4), bl = b_lo0 + (uint32_t)bs * (kTileBytes >> 4);
+            tc_mma_f16_2cta_lo(acc, al, bl, k4Idesc, dc ? 1u : 0u);
+            tc_mma_f16_2cta_lo(acc, al + 2, bl + 2, k4Idesc, 1u);
+            tc_mma_f16_2cta_lo(acc, al + 4, bl + 4, k4Idesc, 1u);
+            tc_mma_f16_2cta_lo(acc, al + 6, bl + 6, k4Idesc, 1u);
+            if (dc == n_dc - 1) {
+              // the limb tile of this unit travelled with its first codebook stage (same barrier)
+              const uint64_t baug = make_desc_noswz(sbase + Tc4Smem::off_baug + buf * k4AugBytes, 128, 256);
+              tc_mma_f16_2cta(acc, aaug, baug, k4Idesc, 1u);                 // + s |e_k|^2
+              tc_commit_2cta(bar_gempty + 8 * buf);
+              tc_commit_2cta(bar_tfull + 8 * buf);
             }
-            __syncwarp();
+            tc_commit_2cta(bar_bempty + 8 * bs);                             // codebook stage free in both CTAs
+            if (last_cc) tc_commit_2cta(bar_aempty + 8 * slot);              // A chunk free: the tile's last use of it
+            if (++bs == k4BStages) { bs = 0; bpar ^= 1u; }
+            if (++slot == k4ASlots) { slot = 0; apar ^= 1u; }
           }
         }
+        slot0 = slot; apar0 = apar;
       }
     }
   } else if (warp == 17) {

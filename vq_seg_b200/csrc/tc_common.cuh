@@ -154,4 +154,31 @@ __device__ __forceinline__ void tc_mma_f16_2cta(uint32_t d_tmem, uint64_t a_desc
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
 
+
+// ---- lean MMA issue (one elected thread) ----
+// The thread that issues the MMAs is a single instruction stream: every SASS instruction between two UTCHMMAs costs
+// ~5 cycles of dependent-issue latency, and an M=256 x N=256 x K=16 MMA lasts only 128 cycles (scripts/dev/mma_rate.cu:
+// a 50-instruction loop body issues one MMA per 321 cycles).  Two things keep the stream short: the issuer is chosen
+// with elect.sync (ptxas then knows the operands are uniform and drops the per-instruction ELECT / BRA.U.ANY
+// "waterfall" it wraps around tcgen05 instructions under `if (lane == 0)`), and descriptors are advanced as 32-bit
+// low words next to a constant high word.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);     // high word of make_desc()
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ void tc_mma_f16_2cta_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHiSw128), "r"(idesc), "r"(accum) : "memory");
+}
+
 }  // namespace vqseg
