@@ -27,7 +27,7 @@ constexpr int k4Threads = 21 * 32;
 constexpr int k4Rows = 128;                  // rows per CTA per tile (pair tile = 256)
 constexpr int k4ASlots = 8;                  // ring of 64-dim fp16 A chunks (16 KiB each)
 constexpr int k4BStages = 3;                 // ring of 128-code x 64-dim codebook stages (16 KiB each)
-constexpr int k4XStages = 2;                 // ring of fp32 x boxes (16 KiB each), one issuing thread per stage
+constexpr int k4XStages = 2;                 // ring of fp32 x boxes (16 KiB each), one issuing thread per stage (power of two)
 constexpr int k4BoxDims = 32;                // dims per x box
 constexpr int k4XBytes = k4BoxDims * k4Rows * 4;
 constexpr int k4CandCap = kWorkCandCap;
@@ -151,42 +151,47 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
     const int chh = warp >> 2;
     const int r = 32 * (warp & 3) + lane;
     float ss = 0.f, sd = 0.f;
-    for (int q = 0; q < total_boxes; ++q) {
-      const int tt = q / boxes_per_tile, h = q - tt * boxes_per_tile;
-      const int dc = h >> 1, hh = h & 1;
-      const int a_seq = tt * a.n_dc + dc, slot = a_seq % k4ASlots;
-      const int s = q % k4XStages;
+    // loop counters kept incrementally (a division by the runtime box count per box is 20+ dependent instructions)
+    int slot = 0; uint32_t apar = 1;                           // A slot of the current chunk, parity of its "empty" phase
+    int q = 0;
+    for (int tt = 0; tt < my_tiles; ++tt)
+    for (int h = 0; h < boxes_per_tile; ++h, ++q) {
+      const int hh = h & 1;
+      const int s = q & (k4XStages - 1);
       if (warp == 0) VQ4_TRACE(0, 2 * q);
       mbar_wait(bar_xfull + 8 * s, (uint32_t)(q / k4XStages) & 1);                   // the box has landed
-      if (hh == 0) mbar_wait(bar_aempty + 8 * slot, (((uint32_t)(a_seq / k4ASlots)) & 1) ^ 1);   // the slot's last MMAs retired
+      if (hh == 0) mbar_wait(bar_aempty + 8 * slot, apar);                          // the slot's last MMAs retired
       if (warp == 0) VQ4_TRACE(0, 2 * q + 1);
       const float* st = reinterpret_cast<const float*>(smem + Tc4Smem::off_x + s * k4XBytes);
       unsigned char* arow = smem + Tc4Smem::off_a + slot * kTileBytes + r * 128;
+      // all 16 values first (four LDS.128 / sixteen conflict-free LDS.32 in flight), then the arithmetic with
+      // independent accumulators: two warps per scheduler hide little latency, dependent chains would set the pace
+      float v[16];
+      if (ROWS) {
+        // [128 rows][32 dims], 128-byte rows, 16-byte chunk j of row r stored at j ^ (r & 7)
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[8];
-        if (ROWS) {
-          // [128 rows][32 dims], 128-byte rows, 16-byte chunk j of row r stored at j ^ (r & 7)
-          const int j0 = 4 * chh + 2 * c;
-          const float4 lo = *reinterpret_cast<const float4*>(st + r * 32 + (((j0) ^ (r & 7)) << 2));
-          const float4 hi = *reinterpret_cast<const float4*>(st + r * 32 + (((j0 + 1) ^ (r & 7)) << 2));
-          v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = st[(16 * chh + 8 * c + j) * k4Rows + r];
+        for (int j = 0; j < 4; ++j) {
+          const float4 q4 = *reinterpret_cast<const float4*>(st + r * 32 + (((4 * chh + j) ^ (r & 7)) << 2));
+          v[4 * j] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
         }
-        uint32_t pk[4];
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          __half2 hv = __floats2half2_rn(v[j], v[j + 1]);
-          const float2 hb = __half22float2(hv);
-          const float e0 = hb.x - v[j], e1 = hb.y - v[j + 1];
-          ss = fmaf(v[j], v[j], ss); ss = fmaf(v[j + 1], v[j + 1], ss);
-          sd = fmaf(e0, e0, sd); sd = fmaf(e1, e1, sd);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hv);
-        }
-        *reinterpret_cast<uint4*>(arow + (((4 * hh + 2 * chh + c) ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int j = 0; j < 16; ++j) v[j] = st[(16 * chh + j) * k4Rows + r];
       }
+      uint32_t pk[8];
+      float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        __half2 hv = __floats2half2_rn(v[j], v[j + 1]);
+        const float2 hb = __half22float2(hv);
+        const float e0 = hb.x - v[j], e1 = hb.y - v[j + 1];
+        s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[j + 1], v[j + 1], s1);
+        d0 = fmaf(e0, e0, d0); d1 = fmaf(e1, e1, d1);
+        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hv);
+      }
+      ss += s0 + s1; sd += d0 + d1;
+      *reinterpret_cast<uint4*>(arow + (((4 * hh + 2 * chh) ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(arow + (((4 * hh + 2 * chh + 1) ^ (r & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       if (h == boxes_per_tile - 1) {                           // this warp's share of the row norms is complete
         // with few dim chunks the A ring holds several tiles: never overwrite norms the epilogue has not read yet
         mbar_wait(bar_nempty + 8 * (tt & 1), (((uint32_t)tt >> 1) & 1) ^ 1);
@@ -199,6 +204,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
         mbar_arrive(bar_xempty + 8 * s);                                   // stage free for the next box
         if (hh == 1) mbar_arrive_cluster_relaxed(lead_afull + 8 * slot);   // chunk complete; leader's barrier (remote for rank 1)
       }
+      if (hh == 1 && ++slot == k4ASlots) { slot = 0; apar ^= 1u; }
     }
   } else if (warp < 16) {
     // ================= epilogue (8 warps: two per TMEM lane quarter, 128 columns each) =================
