@@ -320,8 +320,8 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // lists / xchg free for the next tile
     }
   } else if (warp == 16) {
-    if (rank == 0) {
-      // ================= MMA issuer (leader CTA) =================
+    if (rank == 0 && elect_one()) {
+      // ================= MMA issuer (leader CTA): one elected thread, lean instruction stream (tc_common.cuh) ==========
       // The tile's two accumulators (TMEM columns 0-255 / 256-511) ARE the whole tensor memory, so nothing can be
       // double-buffered across tiles.  What can overlap: the first two A chunks of a tile are multiplied against code
       // chunk 0 as soon as accumulator 0 is drained -- while the epilogue still reads accumulator 1 of the previous
@@ -329,53 +329,53 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
       // code chunks, slot released at once).  At the last chunk the accumulators are completed (|e|^2 step + commit)
       // one after the other, so the epilogue starts on the first while the second still computes.
       const uint64_t aaug = make_desc_noswz(sbase + Tc3Smem::off_aaug, 128, 0);
-      auto mma_chunk = [&](int cc, int dc, int slot) {               // lane 0 only
-        const uint64_t ad = make_desc(sbase + Tc3Smem::off_a + slot * kTileBytes);
-        const uint64_t bd = make_desc(sbase + Tc3Smem::off_b + (cc * a.n_dc + dc) * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kDChunk / 16; ++k)
-          tc_mma_f16_2cta(tmem_base + cc * 256, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), k3Idesc, (dc | k) ? 1u : 0u);
-        if (dc == a.n_dc - 1) {
+      const uint32_t a_lo0 = desc_lo_sw128(sbase + Tc3Smem::off_a), b_lo0 = desc_lo_sw128(sbase + Tc3Smem::off_b);
+      const int n_dc = a.n_dc, n_cc = a.n_cc;
+      auto mma_chunk = [&](int cc, int dc, int slot) {
+        const uint32_t al = a_lo0 + (uint32_t)slot * (kTileBytes >> 4);
+        const uint32_t bl = b_lo0 + (uint32_t)(cc * n_dc + dc) * (kTileBytes >> 4);
+        const uint32_t acc = tmem_base + cc * 256;
+        tc_mma_f16_2cta_lo(acc, al, bl, k3Idesc, dc ? 1u : 0u);
+        tc_mma_f16_2cta_lo(acc, al + 2, bl + 2, k3Idesc, 1u);
+        tc_mma_f16_2cta_lo(acc, al + 4, bl + 4, k3Idesc, 1u);
+        tc_mma_f16_2cta_lo(acc, al + 6, bl + 6, k3Idesc, 1u);
+        if (dc == n_dc - 1) {
           const uint64_t baug = make_desc_noswz(sbase + Tc3Smem::off_baug + cc * k3AugBytes, 128, 256);
-          tc_mma_f16_2cta(tmem_base + cc * 256, aaug, baug, k3Idesc, 1u);     // + s |e_k|^2
+          tc_mma_f16_2cta(acc, aaug, baug, k3Idesc, 1u);     // + s |e_k|^2
           tc_commit_2cta(bar_tfull + 8 * cc);
         }
       };
+      int a_seq = 0;                                            // running A chunk number: slot = a_seq & 1, phase = a_seq >> 1
       for (int tt = 0; tt < my_tiles; ++tt) {
-        const int n_first = a.n_dc < 2 ? a.n_dc : 2;
-        for (int cc = 0; cc < a.n_cc; ++cc) {
-          VQ3_TRACE(1, 128 + 2 * (tt * a.n_cc + cc));
+        const int n_first = n_dc < 2 ? n_dc : 2;
+        for (int cc = 0; cc < n_cc; ++cc) {
+          VQ3_TRACE(1, 128 + 2 * (tt * n_cc + cc));
           mbar_wait(bar_tempty + 8 * cc, ((uint32_t)tt & 1) ^ 1);          // both CTAs' epilogues drained it
-          VQ3_TRACE(1, 128 + 2 * (tt * a.n_cc + cc) + 1);
+          VQ3_TRACE(1, 128 + 2 * (tt * n_cc + cc) + 1);
           if (tt == 0) mbar_wait(bar_bready + 8 * cc, 0);                  // this code chunk is resident in both CTAs
           tc_fence_after();
           for (int dc = 0; dc < n_first; ++dc) {
-            const int a_seq = tt * a.n_dc + dc, slot = a_seq & 1;
+            const int sq = a_seq + dc, slot = sq & 1;
             if (cc == 0) {
-              VQ3_TRACE(1, 2 * a_seq);
-              mbar_wait(bar_afull + 8 * slot, ((uint32_t)a_seq >> 1) & 1); // both CTAs' halves of the A chunk are converted
-              VQ3_TRACE(1, 2 * a_seq + 1);
+              VQ3_TRACE(1, 2 * sq);
+              mbar_wait(bar_afull + 8 * slot, ((uint32_t)sq >> 1) & 1);    // both CTAs' halves of the A chunk are converted
+              VQ3_TRACE(1, 2 * sq + 1);
               tc_fence_after();
             }
-            if (lane == 0) {
-              mma_chunk(cc, dc, slot);
-              if (cc == a.n_cc - 1) tc_commit_2cta(bar_aempty + 8 * slot);  // A slot free in both CTAs
-            }
-            __syncwarp();
+            mma_chunk(cc, dc, slot);
+            if (cc == n_cc - 1) tc_commit_2cta(bar_aempty + 8 * slot);     // A slot free in both CTAs
           }
         }
-        for (int dc = n_first; dc < a.n_dc; ++dc) {
-          const int a_seq = tt * a.n_dc + dc, slot = a_seq & 1;
-          VQ3_TRACE(1, 2 * a_seq);
-          mbar_wait(bar_afull + 8 * slot, ((uint32_t)a_seq >> 1) & 1);
-          VQ3_TRACE(1, 2 * a_seq + 1);
+        for (int dc = n_first; dc < n_dc; ++dc) {
+          const int sq = a_seq + dc, slot = sq & 1;
+          VQ3_TRACE(1, 2 * sq);
+          mbar_wait(bar_afull + 8 * slot, ((uint32_t)sq >> 1) & 1);
+          VQ3_TRACE(1, 2 * sq + 1);
           tc_fence_after();
-          if (lane == 0) {
-            for (int cc = 0; cc < a.n_cc; ++cc) mma_chunk(cc, dc, slot);
-            tc_commit_2cta(bar_aempty + 8 * slot);
-          }
-          __syncwarp();
+          for (int cc = 0; cc < n_cc; ++cc) mma_chunk(cc, dc, slot);
+          tc_commit_2cta(bar_aempty + 8 * slot);
         }
+        a_seq += n_dc;
       }
     }
   } else {
