@@ -43,7 +43,11 @@ extern "C" {
 #define VQSEG_ALGO_TC_PAIR   4       /*   ... the codebook-resident CTA-pair kernel, x through registers (any strides) */
 #define VQSEG_ALGO_TC_TMA    5       /*   ... the codebook-resident CTA-pair kernel, x by TMA tensor loads (NCHW maps) */
 #define VQSEG_ALGO_TC_STREAM_PAIR 6  /*   ... the streaming CTA-pair kernel, x by TMA (NCHW maps or packed rows, D <= 512) */
-/* 3-5 force one kernel (VQSEG_EUNSUPPORTED if the shape does not fit it): the tests cover all three on the same inputs */
+#define VQSEG_METRIC_IP  0x100       /* OR into `algo`: inner-product metric -- idx = FIRST argmax_k <x_n, e_k> with the fp32 sum
+                                        evaluated as ATen's CPU matmul does (the cosine codebook, vq_img.py:104-107, and
+                                        `samples @ means^T` + argmax in kmeans, :37-41); x and E are used as given
+                                        (callers normalise them with vqseg_l2norm_f32); best_key_out is not supported */
+/* 3-6 force one kernel (VQSEG_EUNSUPPORTED if the shape does not fit it): the tests cover all three on the same inputs */
 
 /* gather modes */
 #define VQSEG_MODE_EVAL        0     /* quantize = E[idx]                          (vq_img.py:170)     */
@@ -67,6 +71,10 @@ const char* vqseg_error_string(int code);
 size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D);
 int    vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D,
                                   void* blob, size_t blob_bytes, void* stream);
+/* the same for VQSEG_METRIC_IP assignments (no |e_k|^2 term in the score).  A blob built for the other metric is
+ * detected and rebuilt by the assignment's prologue, like a stale one. */
+int    vqseg_codebook_prepare_ip_f32(const float* E, int64_t K, int64_t D,
+                                     void* blob, size_t blob_bytes, void* stream);
 
 /* ---- nearest-code assignment -----------------------------------------------------------------
  * Replaces `torch.cdist(flatten_x, weight, p=2)` + `torch.argmin(distance, -1)`
@@ -161,13 +169,16 @@ int    vqseg_gather_rows_f32(const float* x, int64_t B, int64_t P, int64_t D,
                              int64_t sB, int64_t sP, int64_t sD,
                              const int64_t* row_ids, int64_t n_ids, float* out, void* stream);
 
-/* ---- cosine codebook helpers (CosinesimCodebook, vq_img.py:93-107) ----------------------------
- * out[n,:] = x[n,:] / max(|x[n,:]|, 1e-12)  (F.normalize, vq_img.py:7-8,:97,:100), packed (N,D). */
-int    vqseg_l2norm_rows_f32(const float* x, int64_t B, int64_t P, int64_t D,
-                             int64_t sB, int64_t sP, int64_t sD, float* out, void* stream);
-/* idx = first argmax_k <x_n, e_k> over packed unit rows (einsum + argmax, vq_img.py:104-107)    */
-int    vqseg_assign_cosine_f32(const float* xn, int64_t N, int64_t D, const float* E, int64_t K,
-                               int64_t* idx_out, int64_t* counts_out, void* stream);
+/* ---- cosine codebook helper (CosinesimCodebook, vq_img.py:93-107) -----------------------------
+ * out[b,p,:] = x[b,p,:] / max(|x[b,p,:]|, 1e-12)  (F.normalize, vq_img.py:7-8,:97,:100,:54) in ATen's CPU
+ * arithmetic: a contiguous last dim (sD == 1: code rows, k-means means) is reduced in ATen's vectorised last-dim order,
+ * a strided one (the 'b c h w -> b (h w) c' view the cosine codebook normalises) as one sequential chain; IEEE sqrt
+ * and division.  `out` may have any strides (same layout as x keeps NCHW maps TMA-loadable) and may alias x when the
+ * strides are equal (in-place renormalisation of the codebook, vq_img.py:100).
+ * The lookup itself (einsum + argmax, vq_img.py:104-107) is vqseg_assign_f32 with VQSEG_METRIC_IP. */
+int    vqseg_l2norm_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                        int64_t sB, int64_t sP, int64_t sD,
+                        float* out, int64_t oB, int64_t oP, int64_t oD, void* stream);
 
 /* ---- EMA codebook update: OPT-IN EXTENSION, no reference counterpart (the reference stores `decay` and `eps`,
  * vq_img.py:150-151,199-200, and never reads them: there is no EMA, so parity is unpinned). Standard VQ-VAE

@@ -144,6 +144,29 @@ COSINE_CASES = {"cos_small": (lambda: _randn_case(70, 2, 64, 16, 16, 48)),
                 "cos_c2ish": (lambda: _relu_case(71, 2, 256, 32, 32, 512))}
 
 
+# Round-2 cosine goldens (golden_cosine_v2.pt, make_golden_cosine.py): bit-exact indices in train AND eval mode, the
+# normalised input and the renormalised weights pinned by SHA-256.  "cos2_dup" has duplicated codes (argmax ties ->
+# first index) and a zero pixel (norm clamped at 1e-12); "cos2_d512" / "cos2_d1024" cross MKL's K-blocking thresholds
+# (two half chains, 384-term blocks); "cos2_d100" has a channel count that is not a multiple of 8 (the tail rules of
+# ATen's last-dim norm); "cos2_c2" is BASELINE config 2's shape.
+def _cos_dup_case():
+    x, e = _relu_case(72, 2, 96, 24, 24, 200)
+    e[150:170] = e[20:40]
+    e[199] = e[0]
+    x[0, :, 3, 5] = 0.0
+    return x, e.contiguous()
+
+
+COSINE2_CASES = {"cos2_small": (lambda: _randn_case(73, 2, 64, 16, 16, 48)),
+                 "cos2_relu": (lambda: _relu_case(74, 2, 256, 32, 32, 512)),
+                 "cos2_dup": _cos_dup_case,
+                 "cos2_d100": (lambda: _randn_case(75, 3, 100, 20, 12, 130)),
+                 "cos2_d512": (lambda: _relu_case(76, 2, 512, 32, 32, 300)),
+                 "cos2_d1024": (lambda: _relu_case(77, 2, 1024, 32, 32, 512)),
+                 "cos2_b1": (lambda: _randn_case(78, 1, 128, 40, 40, 256)),
+                 "cos2_c2": (lambda: _relu_case(79, 8, 256, 64, 64, 512))}
+
+
 # VQ segmentation head: (seed, B, C=dim, H, W, K=classes, distance).  Decoder features are
 # post-ReLU (non-negative); prototypes are perturbed feature rows.  "sh_dup" has a pixel equal to a prototype
 # (distance ~0: catastrophic cancellation in the augmented form) and two identical prototypes (tie -> lower index).

@@ -4,6 +4,8 @@ vectors (produced by the live reference) and vs the CPU oracle on the same seede
 Bars (north_star): bit-exact indices and code counts; quantize / loss / gradients within 1e-5 relative
 (in fact quantize and the k-means means come out bit-exact, which the tests assert where it holds by
 construction)."""
+import os
+
 import pytest
 import torch
 
@@ -177,10 +179,7 @@ def test_kmeans_matches_golden(dev, golden, name):
     means, bins = V.kmeans(src, k, iters, use_cosine_sim=use_cos, init_indices=init_idx)
     assert means.shape == (1, k, x.shape[1]) and bins.shape == (1, k) and bins.dtype == torch.int64
     assert torch.equal(bins[0].cpu(), rec["bins"])                      # bit-exact counts after `iters` Lloyd steps
-    if use_cos:
-        torch.testing.assert_close(means[0].cpu(), rec["means"], rtol=1e-5, atol=1e-7)
-    else:
-        assert torch.equal(means[0].cpu(), rec["means"])                # ordered per-code sums -> bit-exact means
+    assert torch.equal(means[0].cpu(), rec["means"])    # ordered per-code sums (+ ATen-order l2norm for cosine) -> bit-exact means
 
 
 def test_kmeans_init_module_first_train_forward(dev):
@@ -211,6 +210,8 @@ def test_kmeans_init_module_first_train_forward(dev):
 
 @pytest.mark.parametrize("name", list(cases.COSINE_CASES))
 def test_cosine_codebook(dev, golden, name):
+    """round-1 goldens of the cosine codebook (vq_img.py:65-130), now bit-exact: indices, the straight-through output
+    and the in-place renormalised weights."""
     import vq_seg_b200 as V
     x, e = cases.COSINE_CASES[name]()
     rec = golden["cosine"][name]
@@ -218,13 +219,60 @@ def test_cosine_codebook(dev, golden, name):
     m.codebook.embedding.weight.data.copy_(e)
     m.train()
     q, idx, loss, usage = m(x.to(dev))
-    ref_idx = rec["idx"].to(torch.int64)
-    agree = (idx.cpu() == ref_idx).float().mean().item()
-    assert agree >= 0.999, agree                                        # norm rounding differs in the last ulp
+    assert torch.equal(idx.cpu(), rec["idx"].to(torch.int64))
+    assert cases.sha(q) == rec["q_train_sha"]
+    assert cases.sha(m.codebook.embedding.weight.data) == rec["weight_after_sha"]
     torch.testing.assert_close(usage.cpu(), rec["usage"])
-    torch.testing.assert_close(loss.detach().cpu(), rec["loss_train"], rtol=1e-4, atol=0)
-    w = m.codebook.embedding.weight.detach()
-    torch.testing.assert_close(w.norm(dim=-1), torch.ones(e.shape[0], device=dev), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(loss.detach().cpu(), rec["loss_train"], rtol=1e-6, atol=0)
+
+
+@pytest.fixture(scope="module")
+def golden_cosine():
+    return torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cosine_v2.pt"),
+                      weights_only=False)["cosine2"]
+
+
+@pytest.mark.parametrize("name", list(cases.COSINE2_CASES))
+def test_cosine_codebook_bit_exact_train_and_eval(dev, golden_cosine, name):
+    """The cosine codebook against the live reference's outputs (tests/golden/make_golden_cosine.py): l2norm of the
+    strided view and of the weights bit-equal (SHA-256), indices equal in TRAIN and in EVAL mode (first index on
+    ties, zero rows, D crossing MKL's K-blocking thresholds, D not a multiple of 8), the outputs and the twice
+    renormalised weights bit-equal; and the tcgen05 path equal to the exact scorer."""
+    import vq_seg_b200 as V
+    from vq_seg_b200 import ops
+    x, e = cases.COSINE2_CASES[name]()
+    rec = golden_cosine[name]
+    assert cases.sha(x) == rec["x_sha"] and cases.sha(e) == rec["e_sha"]
+    xd, ed = x.to(dev), e.to(dev)
+    xv = view(xd)
+    xn = ops.l2norm_rows(xv)
+    assert xn.stride() == xv.contiguous().permute(0, 2, 1).contiguous().permute(0, 2, 1).stride()    # layout kept
+    assert cases.sha(xn) == rec["xn_sha"], "l2norm of the (B, HW, C) view differs from F.normalize on CPU"
+    w1 = ed.clone()
+    ops.l2norm_rows_(w1)
+    assert cases.sha(w1) == rec["w1_sha"], "l2norm of the codebook rows differs from F.normalize on CPU"
+    i_ex, c_ex = ops.assign_cosine(xn, w1, None, ops.ALGO_EXACT)
+    i_tc, c_tc = ops.assign_cosine(xn, w1, None, ops.ALGO_TC)
+    assert torch.equal(i_ex, i_tc) and torch.equal(c_ex, c_tc)
+    assert torch.equal(i_ex.cpu().reshape(-1), rec["idx_train"].to(torch.int64).reshape(-1))
+
+    m = V.VectorQuantizer(dim=x.shape[1], num_embeddings=e.shape[0], distance="cosine").to(dev)
+    m.codebook.embedding.weight.data.copy_(ed)
+    m.train()
+    q, idx, loss, usage = m(xd)
+    assert torch.equal(idx.cpu(), rec["idx_train"].to(torch.int64))
+    assert cases.sha(q) == rec["q_train_sha"]
+    assert cases.sha(m.codebook.embedding.weight.data) == rec["w_after_train_sha"]
+    torch.testing.assert_close(usage.cpu(), rec["usage_train"])
+    torch.testing.assert_close(loss.detach().cpu(), rec["loss_train"], rtol=1e-6, atol=0)
+    m.eval()
+    with torch.no_grad():
+        q, idx, loss, usage = m(xd)
+    assert torch.equal(idx.cpu(), rec["idx_eval"].to(torch.int64))
+    assert cases.sha(q) == rec["q_eval_sha"]
+    assert cases.sha(m.codebook.embedding.weight.data) == rec["w_after_eval_sha"]
+    torch.testing.assert_close(usage.cpu(), rec["usage_eval"])
+    assert loss.shape == (1,) and loss.item() == 0.0 and not loss.requires_grad
 
 
 def test_row_major_samples_and_half_inputs(dev):

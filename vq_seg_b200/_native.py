@@ -19,6 +19,7 @@ SIGNATURES = {
     "vqseg_error_string": (ctypes.c_char_p, [ci]),
     "vqseg_codebook_blob_bytes": (sz, [i64, i64]),
     "vqseg_codebook_prepare_f32": (ci, [vp, i64, i64, vp, sz, vp]),
+    "vqseg_codebook_prepare_ip_f32": (ci, [vp, i64, i64, vp, sz, vp]),
     "vqseg_assign_workspace_bytes": (sz, [i64, i64, i64, ci]),
     "vqseg_assign_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp, vp]),
     "vqseg_unpack_keys": (ci, [vp, i64, vp, vp, vp, i64, vp]),
@@ -35,8 +36,7 @@ SIGNATURES = {
     "vqseg_kmeans_finalize_f32": (ci, [vp, vp, vp, i64, i64, ci, vp]),
     "vqseg_code_usage": (ci, [vp, i64, vp, vp]),
     "vqseg_gather_rows_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp]),
-    "vqseg_l2norm_rows_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, vp]),
-    "vqseg_assign_cosine_f32": (ci, [vp, i64, i64, vp, i64, vp, vp, vp]),
+    "vqseg_l2norm_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, i64, i64, vp]),
     "vqseg_ema_update_f32": (ci, [vp, vp, vp, vp, vp, i64, i64, f32, f32, vp, vp]),
     "vqseg_dist_map_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, ci, vp, i64, i64, i64, vp, vp, vp, vp]),
     "vqseg_dist_map_bwd_f32": (ci, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, vp, i64,

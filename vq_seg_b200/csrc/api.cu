@@ -7,8 +7,9 @@
 namespace vqseg {
 
 __global__ void blob_init_kernel(BlobHeader* h, int K, int D, int K_pad, int D_pad, unsigned long long off_enorm,
-                                 unsigned long long off_image, unsigned long long off_aug, unsigned long long off_hash) {
-  h->off_aug = off_aug; h->aug_c = 1.f; h->flags = 0u; h->max_de2_bits = 0u;
+                                 unsigned long long off_image, unsigned long long off_aug, unsigned long long off_hash,
+                                 int ip) {
+  h->off_aug = off_aug; h->aug_c = 1.f; h->flags = ip ? kBlobFlagIp : 0u; h->max_de2_bits = 0u;
   h->magic = kBlobMagic; h->K = K; h->D = D; h->K_pad = K_pad; h->D_pad = D_pad;
   h->scale = 1.f; h->max_enorm = 0.f; h->max_enorm_bits = 0u; h->max_abs_bits = 0u;
   h->off_enorm = off_enorm; h->off_image = off_image; h->off_hash = off_hash;
@@ -29,8 +30,11 @@ extern "C" int vqseg_internal_gather_ticket(const float* x, int64_t B, int64_t P
 //       on, so every warp re-hashes code rows and compares with the fingerprints the blob was built from; the last
 //       block through (ticket) rebuilds the blob in place if any row differs.  One block, because a grid-wide
 //       rebuild needs grid barriers; it is the rare path (a rebuild per weight change, ~50 us at K=512, D=256).
+//   (c) checks that the blob was built for the metric of this call (inner-product blobs carry no |e|^2 limbs) and
+//       rebuilds it for the other metric otherwise.
 __global__ void __launch_bounds__(256) assign_prologue_kernel(unsigned long long* counts, int n_counts, float* loss, int* work4,
-                                                              const float* __restrict__ E, int K, int D, unsigned char* blob) {
+                                                              const float* __restrict__ E, int K, int D, unsigned char* blob,
+                                                              int ip) {
   if (blockIdx.x == 0) {
     for (int k = threadIdx.x; k < n_counts; k += blockDim.x) counts[k] = 0ull;
     if (threadIdx.x == 0) { if (loss) *loss = 0.f; work4[0] = 0; work4[1] = 0; work4[2] = 0; work4[3] = 0; }
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(256) assign_prologue_kernel(unsigned long long
   BlobHeader* hdr = reinterpret_cast<BlobHeader*>(blob);
   const unsigned long long* hash = reinterpret_cast<const unsigned long long*>(blob + hdr->off_hash);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  bool differ = false;
+  bool differ = ((hdr->flags & kBlobFlagIp) != 0u) != (ip != 0);
   for (int k = blockIdx.x * 8 + wib; k < K; k += gridDim.x * 8) {
     const unsigned long long h = row_hash_warp(E + (long long)k * D, D, lane);
     differ |= (h != hash[k]);
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(256) assign_prologue_kernel(unsigned long long
   __threadfence();
   const bool stale = *reinterpret_cast<volatile uint32_t*>(&hdr->stale) != 0u;
   if (stale) {
-    if (threadIdx.x == 0) { hdr->flags = 0u; hdr->max_de2_bits = 0u; hdr->max_enorm_bits = 0u; hdr->max_abs_bits = 0u; }
+    if (threadIdx.x == 0) { hdr->flags = ip ? kBlobFlagIp : 0u; hdr->max_de2_bits = 0u; hdr->max_enorm_bits = 0u; hdr->max_abs_bits = 0u; }
     __threadfence(); __syncthreads();
     prep_enorm(E, K, D, hdr->K_pad, reinterpret_cast<float*>(blob + hdr->off_enorm), hdr,
                reinterpret_cast<unsigned long long*>(blob + hdr->off_hash), wib, 8, lane);
@@ -69,8 +73,7 @@ __global__ void __launch_bounds__(256) assign_prologue_kernel(unsigned long long
 
 // MKL's sgemm K-blocking as probed on the reference CPU path: one chain up to
 // 384 terms, two halves up to 768, 384-blocks beyond.
-static int auto_kblock(long long D) {
-  long long L = D + 2;
+static int auto_kblock(long long L) {
   if (L <= 384) return 0;
   if (L <= 768) return (int)((L + 1) / 2);
   return 384;
@@ -141,7 +144,17 @@ size_t vqseg_codebook_blob_bytes(int64_t K, int64_t D) {
   return tot;
 }
 
+static int codebook_prepare(const float* E, int64_t K, int64_t D, void* blob, size_t blob_bytes, void* stream, int ip);
+
 int vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D, void* blob, size_t blob_bytes, void* stream) {
+  return codebook_prepare(E, K, D, blob, blob_bytes, stream, 0);
+}
+
+int vqseg_codebook_prepare_ip_f32(const float* E, int64_t K, int64_t D, void* blob, size_t blob_bytes, void* stream) {
+  return codebook_prepare(E, K, D, blob, blob_bytes, stream, 1);
+}
+
+static int codebook_prepare(const float* E, int64_t K, int64_t D, void* blob, size_t blob_bytes, void* stream, int ip) {
   if (!E || !blob || K <= 0 || D <= 0 || K >= (1ll << 30) || D >= (1ll << 20)) return VQSEG_EINVAL;
   long long kp, dp; size_t oe, oi, tot, oa, oh;
   blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot, &oa, &oh);
@@ -149,7 +162,7 @@ int vqseg_codebook_prepare_f32(const float* E, int64_t K, int64_t D, void* blob,
   if ((reinterpret_cast<uintptr_t>(blob) & 1023) != 0) return VQSEG_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* b = (unsigned char*)blob;
-  blob_init_kernel<<<1, 1, 0, st>>>((BlobHeader*)b, (int)K, (int)D, (int)kp, (int)dp, oe, oi, oa, oh);
+  blob_init_kernel<<<1, 1, 0, st>>>((BlobHeader*)b, (int)K, (int)D, (int)kp, (int)dp, oe, oi, oa, oh, ip);
   VQSEG_LAUNCH_CHECK();
   int rc = launch_enorm(E, (int)K, (int)D, (int)kp, (float*)(b + oe), (BlobHeader*)b, (unsigned long long*)(b + oh), st);
   if (rc) return rc;
@@ -171,6 +184,9 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
                            void* const* prof_events, float* zero_loss, bool zero_counts) {
   if (!x || !E || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
   if (!idx_out && !best_key_out) return VQSEG_EINVAL;
+  const int ip = (algo & VQSEG_METRIC_IP) ? 1 : 0;
+  algo &= ~VQSEG_METRIC_IP;
+  if (ip && best_key_out) return VQSEG_EUNSUPPORTED;       // packed keys order distances, not signed inner products
   const long long n_rows = B * P;
   if (n_rows == 0) return 0;
   if (n_rows >= (1ll << 31) || K >= (1ll << 31) - 1 || D >= (1ll << 20)) return VQSEG_EUNSUPPORTED;
@@ -178,7 +194,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   int rc = check_arch();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (kblock == 0) kblock = auto_kblock(D);
+  if (kblock == 0) kblock = auto_kblock(ip ? D : D + 2);
 
   char* p = (char*)ws;
   int* work_count = (int*)p;   p += 256;                       // [0] undecided rows, [1] spare, [2] gather ticket, [3] spare
@@ -196,7 +212,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     const int guard_blocks = use_tc ? (int)((K + 7) / 8 < 2 * num_sms() ? (K + 7) / 8 : 2 * num_sms()) : 1;
     assign_prologue_kernel<<<guard_blocks, 256, 0, st>>>(zero_counts ? (unsigned long long*)counts_out : nullptr,
                                                          zero_counts ? (int)K : 0, zero_loss, work_count, E, (int)K, (int)D,
-                                                         use_tc ? (unsigned char*)blob : nullptr);
+                                                         use_tc ? (unsigned char*)blob : nullptr, ip);
     VQSEG_LAUNCH_CHECK();
   }
 
@@ -215,7 +231,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   Rows xr{x, B, P, D, sB, sP, sD};
   ExactArgs ea;
   memset(&ea, 0, sizeof(ea));
-  ea.x = xr; ea.E = E; ea.K = (int)K; ea.enorm = enorm; ea.kblock = kblock;
+  ea.x = xr; ea.E = E; ea.K = (int)K; ea.enorm = enorm; ea.kblock = kblock; ea.ip = ip;
   ea.idx_out = (long long*)idx_out; ea.counts_out = (unsigned long long*)counts_out;
   ea.key_out = (unsigned long long*)best_key_out; ea.code_base = code_base;
   if (!use_tc) return launch_exact(ea, n_rows, st);
@@ -314,6 +330,7 @@ int vqseg_vq_forward_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
                          void* const* prof_events) {
   if (!counts_out || K <= 0 || B < 0 || P < 0) return VQSEG_EINVAL;
   if (B * P != 0 && (!idx_out || !q_out)) return VQSEG_EINVAL;   // (empty tensors have null data pointers)
+  if (algo & VQSEG_METRIC_IP) return VQSEG_EINVAL;               // the cosine codebook looks up l2norm(x) but gathers against x
   const size_t wa = (size_t)round_up(vqseg_assign_workspace_bytes(B * P, D, K, algo), 256);
   if (B * P != 0 && (!ws || ws_bytes < wa + vqseg_gather_workspace_bytes(B * P, D))) return VQSEG_EWORKSPACE;
   if (B * P == 0) {                                              // nothing to launch: outputs of an empty batch

@@ -80,10 +80,11 @@ __device__ inline void prep_pack(const float* __restrict__ E, int K, int D, unsi
   const float c = __uint_as_float((uint32_t)(127 + ce) << 23);
   const float cinv = __uint_as_float((uint32_t)(127 - ce) << 23);
   unsigned char* augbase = blob + hdr->off_aug;
+  const bool ip = (hdr->flags & kBlobFlagIp) != 0u;       // inner-product blob: the score is -2 s <x, e> alone
   for (long long kk = tid; kk < K_pad; kk += n_threads) {
     const int k = (int)kk;
     enorm_s[k] = k < K ? enorm[k] * s : 3.0e38f;
-    float v = k < K ? enorm[k] * s * cinv : 60000.f;
+    float v = k < K ? (ip ? 0.f : enorm[k] * s * cinv) : 60000.f;
     __half h1, h2, h3;
     if (k < K) {
       if (!(v <= 60000.f)) { atomicOr(&hdr->flags, 1u); v = 60000.f; }

@@ -56,7 +56,7 @@ struct BlobHeader {
   uint32_t max_abs_bits;            // max |e_kd| bits
   uint64_t off_enorm, off_image, off_aug;
   float    aug_c;        // power of two: s|e_k|^2 = aug_c * (h1 + h2 + h3), three fp16 limbs per code
-  uint32_t flags;        // bit 0: limbs not representable -> tensor-core filter must defer every row
+  uint32_t flags;        // bit 0: limbs not representable -> tensor-core filter must defer every row; bit 1: kBlobFlagIp
   uint32_t max_de2_bits; // max_k |fp16(-2 s e_k) - (-2 s e_k)|^2 : the codebook operand's rounding error, exact
   uint64_t off_hash;
   uint32_t stale;        // guard scratch: set when a row fingerprint differs from the live weights
@@ -64,6 +64,7 @@ struct BlobHeader {
   uint32_t rebuilds;     // how often the guard had to rebuild the blob (diagnostic)
 };
 constexpr uint32_t kBlobMagic = 0x42535156u;
+constexpr uint32_t kBlobFlagIp = 2u;   // flags bit 1: inner-product blob (cosine codebook): no |e|^2 limbs in the score
 constexpr int kCodeBlock = 128;     // codes per packed tile
 constexpr int kDChunk = 64;         // dims per packed tile (64 fp16 = one 128-byte swizzle row)
 constexpr int kTileBytes = kCodeBlock * kDChunk * 2;
@@ -116,6 +117,24 @@ __device__ inline float torch_order_sumsq_warp(F sq, long long D, int lane) {
 #pragma unroll
   for (int l = 0; l < 8; ++l) f = __fadd_rn(f, __shfl_sync(0xffffffffu, p, l));
   return f;
+}
+
+// ||row|| of a contiguous row in ATen's vectorised last-dim order (see ops.cu, l2norm kernels); 8 lanes cooperate
+__device__ __forceinline__ float aten_norm_lastdim8(const float* __restrict__ row, int D, int l8) {
+  float a = 0.f;
+  const int d8 = D & ~7;
+  for (int d = l8; d < d8; d += 8) { const float v = row[d]; a = __fadd_rn(a, __fmul_rn(v, v)); }
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+  float b0 = __shfl_sync(gmask, a, 0, 8);
+#pragma unroll
+  for (int j = 1; j < 8; ++j) b0 = __fadd_rn(b0, __shfl_sync(gmask, a, j, 8));
+  int d = d8;
+  if (D - d >= 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j, ++d) { const float v = row[d]; b0 = __fadd_rn(b0, __fmul_rn(v, v)); }
+  }
+  for (; d < D; ++d) { const float v = row[d]; b0 = __fmaf_rn(v, v, b0); }
+  return __fsqrt_rn(b0);
 }
 
 __device__ inline float warp_min_f(float v) {

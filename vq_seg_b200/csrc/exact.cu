@@ -44,24 +44,25 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
     __syncwarp();
     for (int j = lane; j < D; j += 32) xs[j] = __ldg(xr + (long long)j * a.x.sD);
     __syncwarp();
-    const float xnorm = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
+    const bool ip = a.ip != 0;
+    const float xnorm = ip ? 0.f : torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
     float best = __int_as_float(0x7f800000);   // +inf
     int best_k = 0x7fffffff;
     for (int k0 = lane; k0 < a.K; k0 += 128) {
       float c4[4];
       if (vec4) {
-        chain_dist2_x4(xs, a.E, D, a.K, k0, xnorm, a.enorm, a.kblock, c4);
+        chain_dist2_x4(xs, a.E, D, a.K, k0, xnorm, a.enorm, a.kblock, c4, ip);
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           int k = k0 + 32 * q;
-          c4[q] = k < a.K ? chain_dist2<true>(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, false) : 0.f;
+          c4[q] = k < a.K ? chain_dist2<true>(xs, a.E + (long long)k * D, D, xnorm, a.enorm[k], a.kblock, false, ip) : 0.f;
         }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         int k = k0 + 32 * q;
-        if (k < a.K) lexmin(best, best_k, __fsqrt_rn(fmaxf(c4[q], 0.f)), k);
+        if (k < a.K) lexmin(best, best_k, score_key(c4[q], ip), k);
       }
     }
     // NaN distances never win above; torch.argmin would return the first NaN -- documented divergence.
@@ -105,7 +106,8 @@ __global__ void __launch_bounds__(kExactWarps * 32) rescore_kernel(ExactArgs a, 
     }
     const bool valid = w + hw < n_work;
     float best; int best_k, row;
-    rescore_two_rows(a.x, a.E, a.K, a.enorm, a.kblock, rec_v, valid, xs_w, row_floats, stage_cap, lane, best, best_k, row);
+    rescore_two_rows(a.x, a.E, a.K, a.enorm, a.kblock, rec_v, valid, xs_w, row_floats, stage_cap, lane, best, best_k, row,
+                     a.ip != 0);
     if (hl == 0 && valid) {
       if (a.idx_out) a.idx_out[row] = (long long)best_k + a.code_base;
       if (a.counts_out) atomicAdd(a.counts_out + best_k, 1ull);

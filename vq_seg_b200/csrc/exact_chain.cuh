@@ -1,5 +1,10 @@
 // The exact fp32 scorer's arithmetic as device functions: ATen's CPU `_euclidean_dist` chain (see exact.cu) and the
-// rescoring of two undecided rows by one warp.  Shared by exact.cu (brute force + standalone rescoring kernel) and by
+// rescoring of two undecided rows by one warp.
+//
+// Inner-product mode (`ip`, the cosine codebook: einsum('n d, e d -> n e') + argmax, vq_img.py:104-107, and
+// `samples @ means^T` in kmeans, :37): the same MKL sgemm chain over the D plain terms (no augmentation), returned
+// NEGATED -- negation commutes with fp32 rounding, so "lowest index among the minimal -<x, e>" is torch.argmax's
+// "first index among the maximal <x, e>".  Shared by exact.cu (brute force + standalone rescoring kernel) and by
 // the fused tail of assign_tc3.cu.
 #pragma once
 #include "common.cuh"
@@ -10,9 +15,9 @@ namespace vqseg {
 // one augmented chain, generic block size. xs: shared x row, e: global code row
 template <bool LDG>
 static __device__ __noinline__ float chain_dist2(const float* __restrict__ xs, const float* __restrict__ e,
-                                             int D, float xnorm, float enorm, int kb, bool vec4) {
+                                             int D, float xnorm, float enorm, int kb, bool vec4, bool ip = false) {
   auto ld = [](const float* p) { return LDG ? __ldg(p) : *p; };
-  const int L = D + 2;
+  const int L = ip ? D : D + 2;
   if (kb <= 0 || kb > L) kb = L;
   float c = 0.f;
   bool first = true;
@@ -31,7 +36,7 @@ static __device__ __noinline__ float chain_dist2(const float* __restrict__ xs, c
       }
     }
     for (; j < dend; ++j) t = __fmaf_rn(xs[j], ld(e + j), t);
-    float s = -2.f * t;                                   // exact
+    float s = ip ? -t : -2.f * t;                         // exact
     if (end > D) {
       if (blk <= D) s = __fadd_rn(s, xnorm);              // term D   : |x|^2 * 1
       if (end > D + 1) s = __fadd_rn(s, enorm);           // term D+1 : 1 * |e|^2
@@ -44,8 +49,8 @@ static __device__ __noinline__ float chain_dist2(const float* __restrict__ xs, c
 
 // chain over smem-staged operands (both 16-byte aligned): loads are hoisted 8 terms ahead of the FMA chain
 static __device__ __noinline__ float chain_dist2_smem(const float* __restrict__ xs, const float* __restrict__ es,
-                                                  int D, float xnorm, float enorm, int kb) {
-  const int L = D + 2;
+                                                  int D, float xnorm, float enorm, int kb, bool ip = false) {
+  const int L = ip ? D : D + 2;
   if (kb <= 0 || kb > L) kb = L;
   float c = 0.f;
   bool first = true;
@@ -87,7 +92,7 @@ static __device__ __noinline__ float chain_dist2_smem(const float* __restrict__ 
 #undef VQSEG_FMA8
     }
     for (; j < dend; ++j) t = __fmaf_rn(xs[j], es[j], t);
-    float s = -2.f * t;
+    float s = ip ? -t : -2.f * t;
     if (end > D) {
       if (blk <= D) s = __fadd_rn(s, xnorm);
       if (end > D + 1) s = __fadd_rn(s, enorm);
@@ -101,8 +106,8 @@ static __device__ __noinline__ float chain_dist2_smem(const float* __restrict__ 
 // four independent chains per lane (codes k0 + 32*q), used by the all-codes path for ILP
 __device__ __forceinline__ void chain_dist2_x4(const float* __restrict__ xs, const float* __restrict__ E,
                                                int D, int K, int k0, float xnorm,
-                                               const float* __restrict__ enorm, int kb, float out[4]) {
-  const int L = D + 2;
+                                               const float* __restrict__ enorm, int kb, float out[4], bool ip = false) {
+  const int L = ip ? D : D + 2;
   if (kb <= 0 || kb > L) kb = L;
   const float* e[4];
   bool ok[4];
@@ -138,7 +143,7 @@ __device__ __forceinline__ void chain_dist2_x4(const float* __restrict__ xs, con
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float s = -2.f * t[q];
+      float s = ip ? -t[q] : -2.f * t[q];
       if (end > D) {
         if (blk <= D) s = __fadd_rn(s, xnorm);
         if (end > D + 1) s = __fadd_rn(s, enorm[ok[q] ? k0 + 32 * q : 0]);
@@ -150,6 +155,9 @@ __device__ __forceinline__ void chain_dist2_x4(const float* __restrict__ xs, con
 #pragma unroll
   for (int q = 0; q < 4; ++q) out[q] = c[q];
 }
+
+// what the argmin runs over: the distance sqrt(max(c, 0)) (cdist), or the negated inner product itself
+__device__ __forceinline__ float score_key(float c, bool ip) { return ip ? c : __fsqrt_rn(fmaxf(c, 0.f)); }
 
 __device__ __forceinline__ void lexmin(float& d, int& k, float d2, int k2) {
   if (d2 < d || (d2 == d && k2 < k)) { d = d2; k = k2; }
@@ -176,7 +184,7 @@ constexpr int kRsStage = 4;          // candidates per row staged in shared memo
 __device__ __forceinline__ void rescore_two_rows(const Rows& x, const float* __restrict__ E, int K,
                                                  const float* __restrict__ enorm, int kblock, int rec_v, bool valid,
                                                  float* xs_w, int row_floats, int stage_cap, int lane,
-                                                 float& best, int& best_k, int& row) {
+                                                 float& best, int& best_k, int& row, bool ip = false) {
   const int hw = lane >> 4, hl = lane & 15;
   const int D = (int)x.D;
   const int xs_stride = (D + 3) & ~3, es_stride = xs_stride + 4;
@@ -269,23 +277,23 @@ __device__ __forceinline__ void rescore_two_rows(const Rows& x, const float* __r
       }
     }
     __syncwarp();
-    if (g0 == 0) {
+    if (g0 == 0 && !ip) {
       // |x|^2 in ATen's order: the reduction is warp-wide (lane t = accumulator t), one row after the other
       const float xn0 = torch_sumsq_smem(xs_w, D, lane);
       const float xn1 = torch_sumsq_smem(xs_w + row_floats, D, lane);
       xnorm = hw ? xn1 : xn0;
     }
     if (mine && hl >= g0 && hl < g0 + stage_cap) {
-      const float c2 = chain_dist2_smem(xs, es + (hl - g0) * es_stride, D, xnorm, my_en, kblock);
-      lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), my_k);
+      const float c2 = chain_dist2_smem(xs, es + (hl - g0) * es_stride, D, xnorm, my_en, kblock, ip);
+      lexmin(best, best_k, score_key(c2, ip), my_k);
     }
     __syncwarp();
   }
   if (valid && !listed) {
     // the short-list overflowed (or the filter deferred the row): every code, 16 lanes striding over K
     for (int k = hl; k < K; k += 16) {
-      const float c2 = chain_dist2<true>(xs, E + (long long)k * D, D, xnorm, enorm[k], kblock, vec4);
-      lexmin(best, best_k, __fsqrt_rn(fmaxf(c2, 0.f)), k);
+      const float c2 = chain_dist2<true>(xs, E + (long long)k * D, D, xnorm, enorm[k], kblock, vec4, ip);
+      lexmin(best, best_k, score_key(c2, ip), k);
     }
   }
   // NaN distances never win above; torch.argmin would return the first NaN -- documented divergence.

@@ -17,6 +17,7 @@ struct ExactArgs {
   const float* E; int K;
   const float* enorm;
   int kblock;
+  int ip;               // 1: inner-product mode (cosine codebook): argmax <x, e>, plain D-term chain (exact_chain.cuh)
   // candidate mode (null -> all rows x all codes)
   const WorkRec* work; const int* work_count;         // undecided rows + device counter
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;

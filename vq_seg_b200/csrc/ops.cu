@@ -547,16 +547,13 @@ __global__ void __launch_bounds__(256) kmeans_finalize_kernel(const float* __res
   const long long c = counts[k];
   if (c == 0) return;                                   // empty cluster keeps its old mean
   const float cf = __ll2float_rn(c);
-  float ss = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float m = __fdiv_rn(sums[k * D + d], cf);
-    means[k * D + d] = m;
-    ss = __fmaf_rn(m, m, ss);
-  }
+  for (int d = lane; d < D; d += 32) means[k * D + d] = __fdiv_rn(sums[k * D + d], cf);
   if (cosine) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    float nrm = fmaxf(__fsqrt_rn(ss), 1e-12f);
+    // l2norm(new_means) on the contiguous (1, K, D) tensor (vq_img.py:53-54): ATen's last-dim order, lanes 0-7
+    __syncwarp();
+    float nrm = 0.f;
+    if (lane < 8) nrm = fmaxf(aten_norm_lastdim8(means + k * D, D, lane), 1e-12f);
+    nrm = __shfl_sync(0xffffffffu, nrm, 0);
     for (int d = lane; d < D; d += 32) means[k * D + d] = __fdiv_rn(means[k * D + d], nrm);
   }
 }
@@ -594,53 +591,38 @@ __global__ void __launch_bounds__(256) unpack_keys_kernel(const unsigned long lo
   }
 }
 
-// F.normalize(x, p=2, dim=-1): x / max(|x|_2, 1e-12), packed (N, D) output    (vq_img.py:7-8)
-__global__ void __launch_bounds__(256) l2norm_rows_kernel(Rows x, float* __restrict__ out) {
-  const int D = (int)x.D;
-  const int lane = threadIdx.x & 31;
-  const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (n >= x.n_rows()) return;
-  const float* xr = x.row(n);
-  float ss = 0.f;
-  for (int d = lane; d < D; d += 32) { float v = xr[(long long)d * x.sD]; ss = __fmaf_rn(v, v, ss); }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  float nrm = fmaxf(__fsqrt_rn(ss), 1e-12f);
-  for (int d = lane; d < D; d += 32) out[n * D + d] = __fdiv_rn(xr[(long long)d * x.sD], nrm);
+// ---- F.normalize(t, p=2, dim=-1) = t / max(||t||, 1e-12) in ATen's CPU arithmetic (vq_img.py:7-8) --------------------
+// Probed on the reference's CPU path (torch 2.11, tests/golden/make_golden_cosine.py pins it):
+//  * the norm of a CONTIGUOUS last dim (code rows, k-means means) is ATen's vectorised last-dim reduction: eight lane
+//    accumulators a_l += fl(v * v) over elements l, l + 8, ..., summed a_0 + a_1 + ... + a_7 in order, then the
+//    D % 8 tail: four separately rounded fl(v * v) adds if at least four remain, fused multiply-adds for the last <= 3;
+//  * the norm over a STRIDED dim (the 'b c h w -> b (h w) c' view of vq_img.py:232, which is what the cosine codebook
+//    normalises, :97) is one sequential chain acc = fl(acc + fl(v * v)) in channel order;
+//  * sqrt and the division are IEEE round-to-nearest.
+// Eight lanes own a contiguous row (lane l = accumulator l); one thread owns a strided row (pixel-contiguous maps:
+// a warp reads 32 neighbouring pixels of one channel).
+__global__ void __launch_bounds__(256) l2norm_lastdim_kernel(const float* __restrict__ x, long long n_rows, int D,
+                                                             long long row_stride, float* __restrict__ out, long long out_stride) {
+  const int l8 = threadIdx.x & 7;
+  const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool on = n < n_rows;                            // (whole groups of 8 lanes are on or off together)
+  const float* row = x + (on ? n : 0) * row_stride;
+  const float nrm = fmaxf(aten_norm_lastdim8(row, on ? D : 0, l8), 1e-12f);
+  if (!on) return;
+  float* o = out + n * out_stride;
+  for (int d = l8; d < D; d += 8) o[d] = __fdiv_rn(row[d], nrm);       // in place is fine: each element is read by its writer
 }
 
-// first argmax_k <x_n, e_k>: one warp per row, lanes over codes, sequential FMA chain over d
-__global__ void __launch_bounds__(256) assign_cosine_kernel(const float* __restrict__ xn, long long N, int D,
-                                                            const float* __restrict__ E, int K,
-                                                            long long* __restrict__ idx_out,
-                                                            unsigned long long* __restrict__ counts) {
-  extern __shared__ __align__(16) float s_x[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* xs = s_x + (size_t)warp * D;
-  for (long long n = (long long)blockIdx.x * 8 + warp; n < N; n += (long long)gridDim.x * 8) {
-    __syncwarp();
-    for (int d = lane; d < D; d += 32) xs[d] = xn[n * D + d];
-    __syncwarp();
-    float best = -__int_as_float(0x7f800000);
-    int best_k = 0x7fffffff;
-    for (int k = lane; k < K; k += 32) {
-      const float* er = E + (long long)k * D;
-      float t = 0.f;
-      for (int d = 0; d < D; ++d) t = __fmaf_rn(xs[d], __ldg(er + d), t);
-      if (t > best || (t == best && k < best_k)) { best = t; best_k = k; }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      float b2 = __shfl_xor_sync(0xffffffffu, best, o);
-      int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
-      if (b2 > best || (b2 == best && k2 < best_k)) { best = b2; best_k = k2; }
-    }
-    if (lane == 0) {
-      if (best_k == 0x7fffffff) best_k = 0;
-      idx_out[n] = best_k;
-      if (counts) atomicAdd(counts + best_k, 1ull);
-    }
-  }
+__global__ void __launch_bounds__(256) l2norm_strided_kernel(Rows x, RowsOut out) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= x.n_rows()) return;
+  const float* xr = x.row(n);
+  const int D = (int)x.D;
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) { const float v = xr[(long long)d * x.sD]; acc = __fadd_rn(acc, __fmul_rn(v, v)); }
+  const float nrm = fmaxf(__fsqrt_rn(acc), 1e-12f);
+  float* o = out.row(n);
+  for (int d = 0; d < D; ++d) o[(long long)d * out.sD] = __fdiv_rn(xr[(long long)d * x.sD], nrm);
 }
 
 static inline unsigned grid_for(long long total, int threads, int waves = 8) {
@@ -954,26 +936,20 @@ int vqseg_unpack_keys(const uint64_t* keys, int64_t n, int64_t* idx_out, float* 
   return 0;
 }
 
-int vqseg_l2norm_rows_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
-                          float* out, void* stream) {
-  if (!x || !out || D <= 0) return VQSEG_EINVAL;
+int vqseg_l2norm_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                     float* out, int64_t oB, int64_t oP, int64_t oD, void* stream) {
+  if (!x || !out || D <= 0 || B < 0 || P < 0 || D >= (1ll << 31)) return VQSEG_EINVAL;
   if (B * P == 0) return 0;
-  Rows xr{x, B, P, D, sB, sP, sD};
-  l2norm_rows_kernel<<<(unsigned)((B * P * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xr, out);
-  VQSEG_LAUNCH_CHECK();
-  return 0;
-}
-
-int vqseg_assign_cosine_f32(const float* xn, int64_t N, int64_t D, const float* E, int64_t K,
-                            int64_t* idx_out, int64_t* counts_out, void* stream) {
-  if (!xn || !E || !idx_out || D <= 0 || K <= 0) return VQSEG_EINVAL;
-  if (N == 0) return 0;
-  size_t smem = 8 * (size_t)D * sizeof(float);
-  if (smem > 200 * 1024) return VQSEG_EUNSUPPORTED;
-  static size_t configured[kMaxDevices] = {0};
-  if (int rc = ensure_dynamic_smem(assign_cosine_kernel, smem, configured)) return rc;
-  assign_cosine_kernel<<<grid_for(N * 32, 256), 256, smem, (cudaStream_t)stream>>>(
-      xn, N, (int)D, E, (int)K, (long long*)idx_out, (unsigned long long*)counts_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sD == 1 && oD == 1 && (B == 1 || (sB == P * sP && oB == P * oP))) {
+    // contiguous last dim, one flat row range: ATen's vectorised last-dim reduction
+    const long long n = B * P;
+    l2norm_lastdim_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(x, n, (int)D, sP, out, oP);
+  } else {
+    Rows xr{x, B, P, D, sB, sP, sD};
+    RowsOut orow{out, B, P, D, oB, oP, oD};
+    l2norm_strided_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(xr, orow);
+  }
   VQSEG_LAUNCH_CHECK();
   return 0;
 }

@@ -11,6 +11,7 @@ import torch
 from . import _native
 
 ALGO_AUTO, ALGO_EXACT, ALGO_TC, ALGO_TC_STREAM, ALGO_TC_PAIR, ALGO_TC_TMA, ALGO_TC_STREAM_PAIR = 0, 1, 2, 3, 4, 5, 6
+METRIC_IP = 0x100        # OR into an algo: first argmax of the fp32 inner product (cosine codebook) instead of cdist + argmin
 MODE_EVAL, MODE_TRAIN, MODE_TRAIN_AMP, MODE_EVAL_AMP = 0, 1, 2, 3
 _last_assign_ws = None
 
@@ -38,8 +39,9 @@ def _aligned_bytes(nbytes: int, device) -> torch.Tensor:
 
 
 # -------------------------------------------------------------------------------------------------
-def _prepare_codebook_impl(codebook: torch.Tensor) -> torch.Tensor:
-    """fp32 |e|^2 (torch CPU summation order) + fp16 tcgen05 operand image; see vqseg.h."""
+def _prepare_codebook_impl(codebook: torch.Tensor, ip: bool = False) -> torch.Tensor:
+    """fp32 |e|^2 (torch CPU summation order) + fp16 tcgen05 operand image; see vqseg.h.
+    ip=True: the blob of an inner-product (cosine) lookup, whose score carries no |e|^2 term."""
     _require_cuda(codebook)
     L = _native.lib()
     cb = codebook.detach().contiguous().float()
@@ -47,7 +49,8 @@ def _prepare_codebook_impl(codebook: torch.Tensor) -> torch.Tensor:
     n = L.vqseg_codebook_blob_bytes(k, d)
     blob = _aligned_bytes(n, cb.device)
     with torch.cuda.device(cb.device):
-        _native.check(L.vqseg_codebook_prepare_f32(cb.data_ptr(), k, d, blob.data_ptr(), n, _stream()), "codebook_prepare")
+        fn = L.vqseg_codebook_prepare_ip_f32 if ip else L.vqseg_codebook_prepare_f32
+        _native.check(fn(cb.data_ptr(), k, d, blob.data_ptr(), n, _stream()), "codebook_prepare")
     return blob
 
 
@@ -55,7 +58,7 @@ prepare_codebook = torch.library.custom_op("vqseg::prepare_codebook", mutates_ar
 
 
 @prepare_codebook.register_fake
-def _(codebook):
+def _(codebook, ip=False):
     k, d = codebook.shape
     return codebook.new_empty(_native.lib().vqseg_codebook_blob_bytes(k, d), dtype=torch.uint8)
 
@@ -322,16 +325,29 @@ def _(x, row_ids):
     return x.new_empty((row_ids.numel(), x.shape[2]), dtype=torch.float32)
 
 
+def _dense_like(x: torch.Tensor) -> torch.Tensor:
+    """an uninitialised dense tensor of x's shape whose dims are ordered like x's strides (what TensorIterator
+    allocates for an elementwise result: NCHW maps viewed as (B, P, D) stay pixel-contiguous)"""
+    order = sorted(range(x.dim()), key=lambda i: (x.stride(i), -i), reverse=True)
+    strides, acc = [0] * x.dim(), 1
+    for i in reversed(order):
+        strides[i] = acc
+        acc *= max(x.shape[i], 1)
+    return torch.empty_strided(tuple(x.shape), tuple(strides), dtype=torch.float32, device=x.device)
+
+
 def _l2norm_rows_impl(x: torch.Tensor) -> torch.Tensor:
-    """F.normalize(x, dim=-1) packed as (B, P, D) contiguous."""
+    """F.normalize(x, p=2, dim=-1) of a (B, P, D) view in ATen's CPU arithmetic (bit-equal: the summation order
+    follows the layout, see vqseg.h); the result keeps x's dim order like torch's."""
     _require_cuda(x)
     L = _native.lib()
     if x.dtype != torch.float32:
         x = x.float()
     b, p, d, sb, sp, sd = _bpd(x)
-    out = torch.empty((b, p, d), dtype=torch.float32, device=x.device)
+    out = _dense_like(x)
     with torch.cuda.device(x.device):
-        _native.check(L.vqseg_l2norm_rows_f32(x.data_ptr(), b, p, d, sb, sp, sd, out.data_ptr(), _stream()), "l2norm_rows")
+        _native.check(L.vqseg_l2norm_f32(x.data_ptr(), b, p, d, sb, sp, sd, out.data_ptr(), out.stride(0), out.stride(1),
+                                         out.stride(2), _stream()), "l2norm")
     return out
 
 
@@ -340,30 +356,35 @@ l2norm_rows = torch.library.custom_op("vqseg::l2norm_rows", mutates_args=())(_l2
 
 @l2norm_rows.register_fake
 def _(x):
-    return x.new_empty(x.shape, dtype=torch.float32)
+    return _dense_like(x)
 
 
-def _assign_cosine_impl(xn: torch.Tensor, codebook: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    _require_cuda(xn, codebook)
+def _l2norm_rows_inplace_impl(w: torch.Tensor) -> None:
+    """w[k, :] /= max(|w[k, :]|, 1e-12) for a contiguous (K, D) codebook: `weight.data.copy_(l2norm(weight.data))`
+    (vq_img.py:100) without the temporary."""
+    _require_cuda(w)
+    if w.dtype != torch.float32 or not w.is_contiguous() or w.dim() != 2:
+        raise RuntimeError("l2norm_rows_ expects a contiguous fp32 (K, D) tensor")
     L = _native.lib()
-    xn = xn.contiguous().float()
-    cb = codebook.detach().contiguous().float()
-    b, p, d = xn.shape
-    k = cb.shape[0]
-    idx = torch.empty((b, p), dtype=torch.int64, device=xn.device)
-    counts = torch.zeros(k, dtype=torch.int64, device=xn.device)
-    with torch.cuda.device(xn.device):
-        _native.check(L.vqseg_assign_cosine_f32(xn.data_ptr(), b * p, d, cb.data_ptr(), k, idx.data_ptr(),
-                                                counts.data_ptr(), _stream()), "assign_cosine")
-    return idx, counts
+    k, d = w.shape
+    with torch.cuda.device(w.device):
+        _native.check(L.vqseg_l2norm_f32(w.data_ptr(), 1, k, d, k * d, d, 1, w.data_ptr(), k * d, d, 1, _stream()), "l2norm_")
 
 
-assign_cosine = torch.library.custom_op("vqseg::assign_cosine", mutates_args=())(_assign_cosine_impl)
+l2norm_rows_ = torch.library.custom_op("vqseg::l2norm_rows_", mutates_args=("w",))(_l2norm_rows_inplace_impl)
 
 
-@assign_cosine.register_fake
-def _(xn, codebook):
-    return xn.new_empty(xn.shape[:2], dtype=torch.int64), xn.new_empty((codebook.shape[0],), dtype=torch.int64)
+@l2norm_rows_.register_fake
+def _(w):
+    return None
+
+
+def assign_cosine(xn: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor] = None, algo: int = ALGO_AUTO):
+    """(idx, counts): first argmax_k <xn, e_k> as the reference's einsum + argmax computes it (vq_img.py:104-107):
+    the tcgen05 filter + exact rescoring of `assign` in inner-product mode.  `blob` = prepare_codebook(e, ip=True)."""
+    if blob is None and algo != ALGO_EXACT:
+        blob = fast_prepare_codebook(codebook, True)
+    return fast_assign(xn, codebook, blob, algo | METRIC_IP)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -700,5 +721,5 @@ def fast_code_usage(counts):
     return (_code_usage_impl if _fast() else code_usage)(counts)
 
 
-def fast_prepare_codebook(codebook):
-    return (_prepare_codebook_impl if _fast() else prepare_codebook)(codebook)
+def fast_prepare_codebook(codebook, ip=False):
+    return (_prepare_codebook_impl if _fast() else prepare_codebook)(codebook, ip)

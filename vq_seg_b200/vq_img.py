@@ -73,7 +73,7 @@ def kmeans(flatten_x: torch.Tensor, num_clusters: int, num_iters: int, use_cosin
     bins = torch.zeros(num_clusters, dtype=torch.int64, device=x.device)
     for _ in range(num_iters):
         if use_cosine_sim:
-            buckets, _ = ops.assign_cosine(x, means)
+            buckets, _ = ops.assign_cosine(x, means, None, algo)
         else:
             blob = ops.prepare_codebook(means) if algo != ops.ALGO_EXACT else None
             buckets, _ = ops.assign(x, means, blob, algo)
@@ -108,11 +108,13 @@ class _CodebookBase(nn.Module):
         self._blob = None
         self._blob_key = None
 
-    def _prepared(self):
+    def _prepared(self, ip=False):
+        """The prepared-codebook blob (a cache: every assignment re-checks it against the live weights on the device
+        and rebuilds it in place when they changed, so `weight.data.copy_()` needs no invalidate())."""
         w = self.embedding.weight
-        key = (w.data_ptr(), w._version, w.device)
+        key = (w.data_ptr(), w._version, w.device, ip)
         if self._blob is None or self._blob_key != key:
-            self._blob = ops.fast_prepare_codebook(w.detach())
+            self._blob = ops.fast_prepare_codebook(w.detach(), ip)
             self._blob_key = key
         return self._blob
 
@@ -178,28 +180,28 @@ class EuclideanCodebook(_CodebookBase):
 
 
 class CosinesimCodebook(_CodebookBase):
+    def lookup(self, x: torch.Tensor):
+        """(idx (B,P) int64, counts (K,) int64) of vq_img.py:97-107: l2norm(x) (ATen's arithmetic, layout kept), the
+        in-place renormalisation of the weights EVERY forward (:100), einsum + argmax as the tcgen05 filter + exact
+        rescoring in inner-product mode."""
+        if x.shape[-1] != self.embedding_dim:
+            raise RuntimeError(f"einsum(): operands do not broadcast with remapped shapes: {x.shape[-1]} vs {self.embedding_dim}")
+        xn = ops.l2norm_rows(x)
+        w = self.embedding.weight
+        ops.l2norm_rows_(w.data)
+        blob = self._prepared(ip=True) if self.algo != ops.ALGO_EXACT else None
+        return ops.fast_assign(xn, w.detach(), blob, self.algo | ops.METRIC_IP)
+
     def forward(self, x):
-        """vq_img.py:93-113: l2norm(x); in-place renormalise the weights EVERY forward (:100); argmax of
-        the cosine similarity; gather."""
+        """x: (B, HxW, C) -> (quantized, embed_idx, code_usage)   [vq_img.py:93-113]"""
         x = x.float()
         if x.dim() != 3:
             x = x.reshape(x.shape[0], -1, x.shape[-1])
-        xn = ops.l2norm_rows(x)
         if self.kmeans_init and self.training:
-            self._kmeans_init(xn, cosine=True)
-        w = self.embedding.weight
-        w.data.copy_(ops.l2norm_rows(w.data.unsqueeze(0))[0])
-        self.invalidate()
-        idx, counts = ops.assign_cosine(xn, w.detach())
-        quantized = ops.eval_gather(w, x, idx)
+            self._kmeans_init(ops.l2norm_rows(x), cosine=True)
+        idx, counts = self.lookup(x)
+        quantized = ops.eval_gather(self.embedding.weight, x, idx)
         return quantized, idx, ops.code_usage(counts)
-
-    def lookup(self, x):
-        xn = ops.l2norm_rows(x)
-        w = self.embedding.weight
-        w.data.copy_(ops.l2norm_rows(w.data.unsqueeze(0))[0])
-        self.invalidate()
-        return ops.assign_cosine(xn, w.detach())
 
 
 class VectorQuantizer(nn.Module):

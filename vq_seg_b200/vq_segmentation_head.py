@@ -104,7 +104,7 @@ class CosinesimSegHead(_SegHeadBase):
         if self.kmeans_init and self.training:
             self._kmeans_init(ops.l2norm_rows(x), cosine=True)
         w = self.embedding.weight
-        w.data.copy_(ops.l2norm_rows(w.data.unsqueeze(0))[0])                   # in-place renormalisation (:100)
+        ops.l2norm_rows_(w.data)                                                # in-place renormalisation (:100)
         return _CosineMap.apply(x, w)
 
 
