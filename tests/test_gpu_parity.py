@@ -275,6 +275,84 @@ def test_cosine_codebook_bit_exact_train_and_eval(dev, golden_cosine, name):
     assert loss.shape == (1,) and loss.item() == 0.0 and not loss.requires_grad
 
 
+def test_kmeans_helpers_match_reference_semantics(dev):
+    """batched_bincount (vq_img.py:22-27), sample_vectors both branches (:10-17) and batched_sample_vectors (:19-20)
+    called directly, against the oracle / the reference's definitions."""
+    import vq_seg_b200 as V
+    g = torch.Generator().manual_seed(123)
+    # batched_bincount == zeros.scatter_add_(-1, x, ones) == bincount with minlength, including empty bins
+    for n, k in ((1000, 37), (5, 64), (100000, 512)):
+        b = torch.randint(0, k, (1, n), generator=g)
+        b[0, : n // 2] = b[0, : n // 2] % max(1, k // 3)                 # leave high bins sparse / empty
+        got = V.batched_bincount(b.to(dev), k)
+        want = torch.zeros(1, k, dtype=torch.int64).scatter_add_(-1, b, torch.ones_like(b))
+        assert got.dtype == torch.int64 and got.shape == (1, k) and torch.equal(got.cpu(), want)
+    # sample_vectors: injected indices reproduce sample[indices] bit for bit (both branches of :12-15)
+    sample = torch.randn(300, 24, generator=g)
+    for num in (64, 300, 1000):                                          # N > num, N == num, N < num (with replacement)
+        ids = O.sample_indices(sample.shape[0], num, torch.Generator().manual_seed(num))
+        assert ids.shape == (num,) and (len(set(ids.tolist())) == num) == (num <= 300)
+        got = V.sample_vectors(sample.to(dev), num, ids.to(dev))
+        assert torch.equal(got.cpu(), sample[ids])
+    # ... and with the device RNG: rows of the sample, distinct when N >= num, any valid rows otherwise
+    rows = {tuple(r.tolist()): i for i, r in enumerate(sample)}
+    for num in (64, 1000):
+        got = V.sample_vectors(sample.to(dev), num).cpu()
+        assert got.shape == (num, 24)
+        picked = [rows[tuple(r.tolist())] for r in got]                   # KeyError = not a row of the sample
+        assert (len(set(picked)) == num) == (num <= 300)
+    bs = V.batched_sample_vectors(sample.to(dev).unsqueeze(0), 50).cpu()
+    assert bs.shape == (1, 50, 24) and all(tuple(r.tolist()) in rows for r in bs[0])
+    # a strided NCHW view is sampled in place: the same rows as the contiguous copy
+    x = torch.randn(2, 24, 6, 7, generator=g).to(dev)
+    xv = view(x)
+    ids = torch.tensor([0, 41, 42, 83, 7], device=dev)
+    assert torch.equal(V.vq_img._sample_rows(xv, 5, ids), xv.reshape(-1, 24)[ids])
+
+
+def test_module_cuda_graph_mode_and_weight_updates(dev, golden):
+    """enable_cuda_graphs(): the no-grad eval forward replayed as one CUDA graph per input buffer gives the golden
+    outputs, follows `weight.data` updates made behind the cache (the on-device codebook guard, ADVICE r1: the
+    prepared blob is keyed on a version counter that .data writes do not bump), and leaves training forwards alone."""
+    import vq_seg_b200 as V
+    x, e = cases.FORWARD_CASES["c2_relu"]()
+    rec = golden["forward"]["c2_relu"]
+    m = V.VectorQuantizer(dim=x.shape[1], num_embeddings=e.shape[0]).to(dev)
+    m.codebook.embedding.weight.data.copy_(e.to(dev))
+    m.eval().enable_cuda_graphs()
+    xd = x.to(dev)
+    with torch.no_grad():
+        for _ in range(3):                                   # capture, then two replays
+            q, idx, loss, usage = m(xd)
+    assert torch.equal(idx.cpu().to(torch.int32), rec["idx"]) and cases.sha(q) == rec["q_eval_sha"]
+    assert loss.shape == (1,) and loss.item() == 0.0 and usage.item() == rec["usage"].item()
+    assert len(m._graphs) == 1
+    # the weights change through .data (k-means init, mean-teacher update): the replayed graph must see it
+    g = torch.Generator().manual_seed(5)
+    e2 = e + 0.5 * torch.randn(e.shape, generator=g)
+    m.codebook.embedding.weight.data.copy_(e2.to(dev))
+    with torch.no_grad():
+        q2, idx2, _, _ = m(xd)
+    want = O.assign_euclidean(view(x), e2)
+    assert torch.equal(idx2.cpu().reshape(-1), want.reshape(-1)) or near_tie_ok(x, e2, idx2.cpu().reshape(want.shape), want)
+    assert torch.equal(q2.permute(0, 2, 3, 1).reshape(-1, x.shape[1]).cpu(), e2[idx2.cpu().reshape(-1)])
+    # the same without graphs (plain forward after a .data write, no invalidate())
+    m2 = V.VectorQuantizer(dim=x.shape[1], num_embeddings=e.shape[0]).to(dev).eval()
+    m2.codebook.embedding.weight.data.copy_(e.to(dev))
+    with torch.no_grad():
+        m2(xd)
+        m2.codebook.embedding.weight.data.copy_(e2.to(dev))
+        _, idx3, _, _ = m2(xd)
+    assert torch.equal(idx3, idx2)
+    # a different buffer is a second entry; a training forward does not go through the cache
+    with torch.no_grad():
+        m(xd.clone())
+    assert len(m._graphs) == 2
+    m.train()
+    q, idx, loss, usage = m(xd.clone().requires_grad_(True))
+    assert loss.requires_grad and len(m._graphs) == 2
+
+
 def test_row_major_samples_and_half_inputs(dev):
     from vq_seg_b200 import ops
     g = torch.Generator().manual_seed(5)

@@ -51,9 +51,22 @@ def test_seghead_matches_golden(dev, golden_seghead, name):
     assert rel_to_max(score.detach().cpu(), rec["score"]) <= 1e-5
     assert abs(loss.item() - rec["loss"].item()) <= 1e-5 * abs(rec["loss"].item())
     assert rel_to_max(xg.grad.cpu(), rec["gx"]) <= 1e-5, rel_to_max(xg.grad.cpu(), rec["gx"])
-    # sh_dup holds a pixel that coincides with a prototype: d ~ 1e-3 from catastrophic cancellation, g / d is huge and
-    # the reference's own composite backward (cat / matmul / clamp / sqrt) loses digits there
-    assert rel_to_max(m.codebook.embedding.weight.grad.cpu(), rec["gw"]) <= (1e-3 if name == "sh_dup" else 1e-5)
+    # prototype gradient: within 1e-5 of the reference, except where the REFERENCE's float32 value is itself further
+    # than that from the float64 value of the same mathematics (sh_dup: a pixel coincides with a prototype, d ~ 1e-3
+    # is cancellation noise, g / d is huge and two such terms cancel; the reference is 1.1e-4 off, see
+    # tests/golden/make_golden_seghead_f64.py).  There the bar is the reference's own loss of digits: the kernel must
+    # be no further from float64 than 1.5 x the reference is.
+    f64 = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_seghead_f64_v2.pt"),
+                     weights_only=False)["seghead_f64"][name]
+    gw = m.codebook.embedding.weight.grad.cpu()
+    gw_err64 = ((gw.double() - f64["gw_f64"]).abs().max() / f64["gw_f64"].abs().max()).item()
+    gx_err64 = ((xg.grad.cpu().double() - f64["gx_f64"]).abs().max() / f64["gx_f64"].abs().max()).item()
+    assert gx_err64 <= max(1e-5, 1.5 * f64["ref_gx_err"]), (gx_err64, f64["ref_gx_err"])
+    assert gw_err64 <= max(1e-5, 1.5 * f64["ref_gw_err"]), (gw_err64, f64["ref_gw_err"])
+    if f64["ref_gw_err"] <= 1e-6:
+        assert rel_to_max(gw, rec["gw"]) <= 1e-5, rel_to_max(gw, rec["gw"])
+    else:
+        assert rel_to_max(gw, rec["gw"]) <= 2.5 * f64["ref_gw_err"], (rel_to_max(gw, rec["gw"]), f64["ref_gw_err"])
     assert torch.equal(m.codebook.embedding.weight.detach().cpu(), rec["w_after"]) or distance == "cosine"
     if distance == "cosine":
         assert rel_to_max(m.codebook.embedding.weight.detach().cpu(), rec["w_after"]) <= 1e-6

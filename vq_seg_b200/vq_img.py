@@ -29,16 +29,22 @@ def l2norm(t: torch.Tensor) -> torch.Tensor:
     return ops.l2norm_rows(t.reshape(1, -1, t.shape[-1]) if t.dim() != 3 else t).reshape(*lead, t.shape[-1])
 
 
-def sample_vectors(sample: torch.Tensor, num: int, indices: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """vq_img.py:10-17: randperm(N)[:num] rows if N >= num, else randint with replacement.
-    `indices` injects the choice (the device RNG stream differs from the CPU one)."""
-    num_samples, device = sample.shape[0], sample.device
+def _sample_rows(x_bpd: torch.Tensor, num: int, indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`num` rows of the flattened (B*P, D) view of x_bpd WITHOUT flattening it (strided NCHW views stay in place):
+    randperm(N)[:num] if N >= num, else randint with replacement (vq_img.py:11-15)."""
+    num_samples, device = x_bpd.shape[0] * x_bpd.shape[1], x_bpd.device
     if indices is None:
         if num_samples >= num:
             indices = torch.randperm(num_samples, device=device)[:num]
         else:
             indices = torch.randint(0, num_samples, (num,), device=device)
-    return ops.gather_rows(sample.unsqueeze(0), indices.to(device))
+    return ops.gather_rows(x_bpd, indices.to(device))
+
+
+def sample_vectors(sample: torch.Tensor, num: int, indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """vq_img.py:10-17 for an (N, D) sample.  `indices` injects the choice (the device RNG stream differs from the
+    CPU one)."""
+    return _sample_rows(sample.unsqueeze(0), num, indices)
 
 
 def batched_sample_vectors(samples: torch.Tensor, num: int) -> torch.Tensor:
@@ -63,13 +69,7 @@ def kmeans(flatten_x: torch.Tensor, num_clusters: int, num_iters: int, use_cosin
     reference; bins belong to the LAST assignment."""
     x = flatten_x if flatten_x.dim() == 3 else flatten_x.reshape(1, -1, flatten_x.shape[-1])
     x = x.detach()
-    n = x.shape[0] * x.shape[1]
-    if init_indices is None:
-        if n >= num_clusters:
-            init_indices = torch.randperm(n, device=x.device)[:num_clusters]
-        else:
-            init_indices = torch.randint(0, n, (num_clusters,), device=x.device)
-    means = ops.gather_rows(x, init_indices.to(x.device))
+    means = _sample_rows(x, num_clusters, init_indices)            # batched_sample_vectors of vq_img.py:33, one codebook
     bins = torch.zeros(num_clusters, dtype=torch.int64, device=x.device)
     for _ in range(num_iters):
         if use_cosine_sim:
@@ -218,6 +218,46 @@ class VectorQuantizer(nn.Module):
                                        kmeans_init=kmeans_init, kmeans_iters=kmeans_iters, decay=decay,
                                        eps=eps, num_codebook=num_codebook)
         self.amp_compat = True    # under fp16 autocast round the gathered code through fp16 like the reference's matmul
+        self._graphs = None       # opt-in CUDA-graph cache of the no-grad forward (enable_cuda_graphs)
+
+    def enable_cuda_graphs(self, max_entries: int = 16):
+        """Opt-in: replay the no-grad forward as ONE CUDA graph per (input address, shape, strides) instead of
+        enqueueing its kernels from Python -- the host cost of a forward drops from ~120 us to one graph launch, so a
+        model calling `self.codebook[i](x)` per layer gets the kernels' speed without capturing graphs itself.
+        Contract of a captured forward (the usual one for CUDA graphs): the four returned tensors are buffers owned by
+        the cache entry and are overwritten by the next call with the same input address; the input must stay at that
+        address (a reused activation buffer / a static input).  Weight updates are picked up: the kernels re-check the
+        prepared codebook against the live weights on the device.  Training-mode and grad-enabled calls, the k-means
+        init and the EMA update take the ordinary path."""
+        self._graphs = {}
+        self._graphs_max = max_entries
+        return self
+
+    def disable_cuda_graphs(self):
+        self._graphs = None
+        return self
+
+    def _graph_forward(self, x):
+        amp16 = bool(self.amp_compat and torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.float16)
+        w = self.codebook.embedding.weight
+        key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, amp16, w.data_ptr(), torch.cuda.current_device())
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self._graphs_max:
+                self._graphs.pop(next(iter(self._graphs)))        # oldest entry
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                         # warm-up outside the capture (lazy init, allocations)
+                self._forward_impl(x)
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = self._forward_impl(x)
+            ent = (g, outs, self.codebook._blob)                  # the blob the graph reads must outlive the cache's view of it
+            self._graphs[key] = ent
+        ent[0].replay()
+        return ent[1]
 
     def enable_ema(self, **kw):
         """Opt-in EMA codebook update with the stored `decay` and `eps` (extension; see the codebook's enable_ema)."""
@@ -231,6 +271,12 @@ class VectorQuantizer(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("vq_seg_b200.VectorQuantizer runs on a B200 GPU only (no CPU fallback); "
                                "move the module and its input to cuda")
+        if (self._graphs is not None and not self.training and not torch.is_grad_enabled() and x.numel() > 0
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._graph_forward(x)
+        return self._forward_impl(x)
+
+    def _forward_impl(self, x):
         x = x.to(torch.float32)
         b, c, h, w = x.shape
         device = x.device
@@ -241,7 +287,6 @@ class VectorQuantizer(nn.Module):
         cosine = isinstance(cb, CosinesimCodebook)
         if cb.kmeans_init and self.training and not cb.initted:
             cb._kmeans_init(ops.l2norm_rows(xv) if cosine else xv, cosine=cosine)
-        loss = torch.zeros(1, device=device, dtype=torch.float32, requires_grad=self.training)   # no H2D copy
         if cosine:
             idx, counts = cb.lookup(xv)
             code_usage = ops.fast_code_usage(counts)
@@ -255,8 +300,17 @@ class VectorQuantizer(nn.Module):
                 raise RuntimeError(f"X1 and X2 must have the same number of columns. X1: {xv.shape[-1]} X2: {cb.embedding_dim}")
             blob = cb._prepared() if cb.algo != ops.ALGO_EXACT else None
             quantize, idx, mse, code_usage = ops.fused_forward(xv, cb.embedding.weight, blob, self.training, amp16, cb.algo)
-        if self.training and self.commitment_weight > 0:
-            loss = loss + mse * self.commitment_weight
+        # loss (vq_img.py:230,239-241): [0.] + mse * w.  0 + v and v * 1 are exact in fp32, so for the default weight
+        # the kernel's (1,) mse IS the loss (no fill / mul / add launches); eval: the kernel's zeroed (1,) output
+        if self.training and self.commitment_weight > 0 and (mse.requires_grad or not torch.is_grad_enabled()):
+            loss = mse if self.commitment_weight == 1 else mse * self.commitment_weight
+        elif self.training and self.commitment_weight > 0:
+            # x carries no gradient: the reference's requires_grad leaf still makes the loss require grad
+            loss = torch.zeros(1, device=device, dtype=torch.float32, requires_grad=True) + mse * self.commitment_weight
+        elif mse is not None and not self.training and not mse.requires_grad:
+            loss = mse
+        else:
+            loss = torch.zeros(1, device=device, dtype=torch.float32, requires_grad=self.training)
         if self.training and cb.ema_enabled:
             if cb.embed_avg.device != device:    # enable_ema() ran before .to(device)
                 cb.enable_ema(eps=cb.ema_eps, reduce_fn=cb.ema_reduce_fn, deterministic=cb.ema_deterministic)
