@@ -59,7 +59,19 @@ def run_parity(rank, world, dev, rows=1 << 20, dim=128, k_kmeans=256, k_sharded=
     sub = xv[:1, :4096]                                       # the single-GPU assignment itself against brute force
     ex_idx, _ = ops.assign(sub, e, None, ops.ALGO_EXACT)
     out["single_gpu_matches_brute_force"] = bool(torch.equal(ex_idx, ref_idx[:1, :4096]))
-    flags = torch.tensor([int(out["dp_kmeans_bins_equal"]), int(out["sharded_idx_equal"]), int(out["sharded_counts_equal"]),
+    # ---- the module's own k-means hook (kmeans_init=True + codebook.kmeans_reduce_fn): every rank sees different
+    # images and draws its own start rows; rank 0's start is broadcast and the statistics are all-reduced, so the
+    # replicated codebooks must come out identical on all ranks after the first training forward
+    torch.manual_seed(100 + rank)                                                  # ranks DISAGREE on the RNG on purpose
+    m = V.VectorQuantizer(dim=dim, num_embeddings=64, kmeans_init=True, kmeans_iters=3).to(dev)
+    m.codebook.kmeans_reduce_fn = D.allreduce_code_stats
+    m.train()
+    m(x[rank * per:(rank + 1) * per].reshape(per, dim, 64, pix // 64)[:, :, :, :64].contiguous())
+    w = m.codebook.embedding.weight.detach()
+    w0 = w.clone()
+    dist.broadcast(w0, src=0)
+    out["module_kmeans_hook_same_codebook"] = bool(torch.equal(w, w0))
+    flags = torch.tensor([int(out["module_kmeans_hook_same_codebook"]), int(out["dp_kmeans_bins_equal"]), int(out["sharded_idx_equal"]), int(out["sharded_counts_equal"]),
                           int(out["single_gpu_matches_brute_force"]), int(out["dp_kmeans_means_rel_err"] < 1e-5),
                           int(out["dp_kmeans_bins_moved_after_%d_iters" % iters] <= max(2, out["rows"] // 1000))], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)

@@ -48,4 +48,5 @@ def test_two_gpu_modes(rows):
         assert out["sharded_idx_equal"] and out["sharded_counts_equal"], "sharded (min,index) reduction differs from the single-GPU argmin"
         assert out["dp_kmeans_bins_equal"], "data-parallel k-means counts differ from single-GPU"
         assert out["dp_kmeans_means_rel_err"] < 1e-5, out
+        assert out["module_kmeans_hook_same_codebook"], "kmeans_reduce_fn: the ranks' codebooks differ after the k-means init"
         assert out["single_gpu_matches_brute_force"] and out["all_ranks_ok"]

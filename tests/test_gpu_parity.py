@@ -82,6 +82,37 @@ def test_every_tensor_core_kernel_on_resident_shapes(dev, golden, name, kernel):
     assert torch.equal(counts.cpu(), rec["counts"])
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 32, 32, 512), (2, 1024, 16, 16, 512), (1, 520, 12, 12, 300), (2, 64, 24, 24, 4096)])
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_short_list_overflow_rows(dev, shape, metric):
+    """More than 8 codes within the filter's error bound of a row's minimum (clusters of near-duplicate codes; a
+    zero feature vector against a symmetric codebook): the rows are deferred to the block-per-row brute-force kernel.
+    Indices and counts must equal the exact scorer's, including the first-index rule among exact duplicates."""
+    from vq_seg_b200 import ops
+    b, c, h, w, k = shape
+    g = torch.Generator(device="cuda").manual_seed(c + k)
+    x = torch.relu(torch.randn(b, c, h * w, generator=g, device=dev))
+    xv = x.permute(0, 2, 1)
+    base = xv.reshape(-1, c)[torch.randperm(b * h * w, generator=g, device=dev)[:k // 16]]
+    e = base.repeat_interleave(16, dim=0)[:k].clone()                  # 16 copies of each centre ...
+    e[1::2] += 1e-6 * torch.randn(e[1::2].shape, generator=g, device=dev)     # ... half of them perturbed in the last bits
+    if e.shape[0] < k:
+        e = torch.cat([e, torch.randn(k - e.shape[0], c, generator=g, device=dev)])
+    e = e.contiguous()
+    x[0, :, 5] = 0.0                                                   # a zero pixel
+    ip = metric == "cosine"
+    if ip:
+        xv = ops.l2norm_rows(xv)
+        ops.l2norm_rows_(e)
+    flag = ops.METRIC_IP if ip else 0
+    i_ex, c_ex = ops.assign(xv, e, None, ops.ALGO_EXACT | flag)
+    i_tc, c_tc = ops.assign(xv, e, ops.prepare_codebook(e, ip), ops.ALGO_TC | flag)
+    n_ovf = ops._last_assign_ws[4:8].view(torch.int32).item()
+    assert n_ovf > 0, "the case is meant to overflow the short-list"
+    assert torch.equal(i_ex, i_tc), f"{(i_ex != i_tc).sum().item()} rows differ ({n_ovf} overflow rows)"
+    assert torch.equal(c_ex, c_tc)
+
+
 def test_kblock_override_changes_only_near_ties(dev):
     """kblock is the fp32 chain split of the exact scorer; a different split may only move rows
     whose two best reference distances are within 2 ulp."""

@@ -173,6 +173,7 @@ size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int al
   (void)D; (void)algo;
   size_t b = 256;                                                     // work counter + tickets
   b += (size_t)round_up(n_rows * (long long)sizeof(WorkRec), 256);    // one record per undecided row (worst case: all)
+  b += (size_t)round_up(n_rows * (long long)sizeof(int), 256);        // rows whose short-list overflowed (worst case: all)
   b += (size_t)round_up(round_up(K, 256) * sizeof(float), 256);       // enorm when no blob is given
   return b;
 }
@@ -197,8 +198,9 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   if (kblock == 0) kblock = auto_kblock(ip ? D : D + 2);
 
   char* p = (char*)ws;
-  int* work_count = (int*)p;   p += 256;                       // [0] undecided rows, [1] spare, [2] gather ticket, [3] spare
+  int* work_count = (int*)p;   p += 256;                       // [0] undecided rows, [1] overflow rows, [2] gather ticket, [3] spare
   WorkRec* work = (WorkRec*)p; p += round_up(n_rows * (long long)sizeof(WorkRec), 256);
+  int* ovf_rows = (int*)p;     p += round_up(n_rows * (long long)sizeof(int), 256);
   float* enorm_ws = (float*)p;
 
   bool use_tc = false;
@@ -302,6 +304,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   prof_record(prof_events, 1, st);
   if (rc) return rc;
   ea.work = work; ea.work_count = work_count;
+  ea.ovf_rows = ovf_rows; ea.ovf_count = work_count + 1;               // ([1] is zeroed by the prologue with the counter)
   ea.trace = dev_trace() ? dev_trace() + 148 * 4 * 256 : nullptr;      // dev tool: 8 int64 after the filter's trace area
   prof_record(prof_events, 2, st);
   rc = launch_exact(ea, n_rows, st);

@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(kExactWarps * 32) rescore_kernel(ExactArgs a, 
     const bool valid = w + hw < n_work;
     float best; int best_k, row;
     rescore_two_rows(a.x, a.E, a.K, a.enorm, a.kblock, rec_v, valid, xs_w, row_floats, stage_cap, lane, best, best_k, row,
-                     a.ip != 0);
-    if (hl == 0 && valid) {
+                     a.ip != 0, a.ovf_rows, a.ovf_count);
+    if (hl == 0 && valid && row >= 0) {
       if (a.idx_out) a.idx_out[row] = (long long)best_k + a.code_base;
       if (a.counts_out) atomicAdd(a.counts_out + best_k, 1ull);
       if (a.key_out)
@@ -117,6 +117,102 @@ __global__ void __launch_bounds__(kExactWarps * 32) rescore_kernel(ExactArgs a, 
     __syncwarp();
   }
   if (a.trace && threadIdx.x == 0) atomicMax((unsigned long long*)a.trace + 1, (unsigned long long)gtime());
+}
+
+// ---- rows the rescoring pass deferred (short-list overflow: more than kWorkCandCap codes within the filter's error
+// bound of the row minimum, or the filter could not bound the row at all): every code is scored, one BLOCK per row.
+// Warp w owns the 32-code slices w, w + 8, ...: lane = code; the slice's code rows arrive as coalesced
+// [32 codes][32 dims] tiles through a padded shared-memory transpose (the next tile is in registers while the current
+// one feeds the chains), so each lane runs its code's chain -- the same terms in the same order and the same K-blocking
+// as chain_dist2 -- from conflict-free shared memory.
+constexpr int kOvfWarps = 8;
+__global__ void __launch_bounds__(kOvfWarps * 32) overflow_rows_kernel(ExactArgs a) {
+  extern __shared__ __align__(16) float smem_x[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int D = (int)a.x.D, K = a.K;
+  const bool ip = a.ip != 0;
+  float* xs = smem_x;                                                   // [D rounded to 4]
+  float* tile = smem_x + ((D + 3) & ~3) + (size_t)wib * (32 * 33);      // this warp's [32 codes][33]
+  __shared__ float s_best[kOvfWarps];
+  __shared__ int s_bestk[kOvfWarps];
+  __shared__ float s_xnorm;
+  const int n_ovf = *reinterpret_cast<volatile const int*>(a.ovf_count);
+  const int L = ip ? D : D + 2;
+  int kb = a.kblock;
+  if (kb <= 0 || kb > L) kb = L;
+  const int n_slices = (K + 31) / 32;
+  for (int r = blockIdx.x; r < n_ovf; r += gridDim.x) {
+    const int row = a.ovf_rows[r];
+    const float* xr = a.x.row(row);
+    __syncthreads();                                                    // the previous row's xs / s_best are done with
+    for (int j = threadIdx.x; j < D; j += blockDim.x) xs[j] = __ldg(xr + (long long)j * a.x.sD);
+    __syncthreads();
+    if (wib == 0 && !ip) {
+      const float xn = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
+      if (lane == 0) s_xnorm = xn;
+    }
+    __syncthreads();
+    const float xnorm = ip ? 0.f : s_xnorm;
+    float best = __int_as_float(0x7f800000);
+    int best_k = 0x7fffffff;
+    for (int s = wib; s < n_slices; s += kOvfWarps) {
+      const int k = s * 32 + lane;
+      float c = 0.f;
+      bool first = true;
+      for (int blk = 0; blk < L; blk += kb) {
+        const int end = min(blk + kb, L), dend = min(end, D);
+        float t = 0.f;
+        float nxt[32];
+        auto fetch = [&](int d0) {                                      // tile rows = codes, lane = dim d0 + lane
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) {
+            const int kc = s * 32 + cc;
+            nxt[cc] = (kc < K && d0 + lane < dend) ? __ldg(a.E + (long long)kc * D + d0 + lane) : 0.f;
+          }
+        };
+        if (blk < dend) fetch(blk);
+        for (int d0 = blk; d0 < dend; d0 += 32) {
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) tile[cc * 33 + lane] = nxt[cc];
+          __syncwarp();
+          if (d0 + 32 < dend) fetch(d0 + 32);
+          const int w = min(32, dend - d0);
+          const float* tr = tile + lane * 33;
+          if (w == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t = __fmaf_rn(xs[d0 + j], tr[j], t);
+          } else {
+            for (int j = 0; j < w; ++j) t = __fmaf_rn(xs[d0 + j], tr[j], t);
+          }
+        }
+        float sc = ip ? -t : -2.f * t;                                   // exact
+        if (end > D) {
+          if (blk <= D) sc = __fadd_rn(sc, xnorm);                       // term D   : |x|^2 * 1
+          if (end > D + 1) sc = __fadd_rn(sc, k < K ? a.enorm[k] : 0.f); // term D+1 : 1 * |e|^2
+        }
+        c = first ? sc : __fadd_rn(c, sc);
+        first = false;
+      }
+      if (k < K) lexmin(best, best_k, score_key(c, ip), k);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float d2 = __shfl_xor_sync(0xffffffffu, best, o);
+      const int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
+      lexmin(best, best_k, d2, k2);
+    }
+    if (lane == 0) { s_best[wib] = best; s_bestk[wib] = best_k; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kOvfWarps; ++w) lexmin(best, best_k, s_best[w], s_bestk[w]);
+      if (best_k == 0x7fffffff) best_k = 0;
+      if (a.idx_out) a.idx_out[row] = (long long)best_k + a.code_base;
+      if (a.counts_out) atomicAdd(a.counts_out + best_k, 1ull);
+      if (a.key_out)
+        a.key_out[row] = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(uint32_t)(best_k + a.code_base);
+    }
+  }
 }
 
 int launch_enorm(const float* E, int K, int D, int K_pad, float* enorm, BlobHeader* hdr, unsigned long long* hash,
@@ -162,6 +258,15 @@ int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st) {
   if (blocks > cap) blocks = cap;
   rescore_kernel<<<(unsigned)blocks, nwarps * 32, smem, st>>>(a, stage_cap, max_work);
   VQSEG_LAUNCH_CHECK();
+  if (a.ovf_rows) {
+    const size_t osmem = xs_bytes + (size_t)kOvfWarps * 32 * 33 * sizeof(float);
+    if (osmem > 200 * 1024) return VQSEG_EUNSUPPORTED;
+    static size_t oconf[kMaxDevices] = {0};
+    if (int rc = ensure_dynamic_smem(overflow_rows_kernel, osmem, oconf)) return rc;
+    long long ob = max_work < 2ll * num_sms() ? max_work : 2ll * num_sms();
+    overflow_rows_kernel<<<(unsigned)ob, kOvfWarps * 32, osmem, st>>>(a);
+    VQSEG_LAUNCH_CHECK();
+  }
   return 0;
 }
 

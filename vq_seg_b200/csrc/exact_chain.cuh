@@ -184,7 +184,8 @@ constexpr int kRsStage = 4;          // candidates per row staged in shared memo
 __device__ __forceinline__ void rescore_two_rows(const Rows& x, const float* __restrict__ E, int K,
                                                  const float* __restrict__ enorm, int kblock, int rec_v, bool valid,
                                                  float* xs_w, int row_floats, int stage_cap, int lane,
-                                                 float& best, int& best_k, int& row, bool ip = false) {
+                                                 float& best, int& best_k, int& row, bool ip = false,
+                                                 int* ovf_rows = nullptr, int* ovf_count = nullptr) {
   const int hw = lane >> 4, hl = lane & 15;
   const int D = (int)x.D;
   const int xs_stride = (D + 3) & ~3, es_stride = xs_stride + 4;
@@ -289,8 +290,13 @@ __device__ __forceinline__ void rescore_two_rows(const Rows& x, const float* __r
     }
     __syncwarp();
   }
-  if (valid && !listed) {
-    // the short-list overflowed (or the filter deferred the row): every code, 16 lanes striding over K
+  if (valid && !listed && ovf_rows) {
+    // the short-list overflowed (or the filter deferred the row): every code must be scored.  One half-warp doing
+    // that alone is a 250-500 us latency chain (K = 512, D = 512-1024: a single such row on a real feature map made
+    // the whole kernel 20x slower), so the row goes to overflow_rows_kernel, which spreads it over a block
+    if (hl == 0) ovf_rows[atomicAdd(ovf_count, 1)] = row;
+    row = -1;                                              // (no early return: the shuffles below are warp-wide)
+  } else if (valid && !listed) {
     for (int k = hl; k < K; k += 16) {
       const float c2 = chain_dist2<true>(xs, E + (long long)k * D, D, xnorm, enorm[k], kblock, vec4, ip);
       lexmin(best, best_k, score_key(c2, ip), k);

@@ -20,6 +20,7 @@ struct ExactArgs {
   int ip;               // 1: inner-product mode (cosine codebook): argmax <x, e>, plain D-term chain (exact_chain.cuh)
   // candidate mode (null -> all rows x all codes)
   const WorkRec* work; const int* work_count;         // undecided rows + device counter
+  int* ovf_rows; int* ovf_count;                      // rows whose short-list overflowed: deferred to overflow_rows_kernel
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
   long long* trace;     // dev tool: [0] min start ns, [1] max end ns
 };

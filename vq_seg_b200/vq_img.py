@@ -70,6 +70,12 @@ def kmeans(flatten_x: torch.Tensor, num_clusters: int, num_iters: int, use_cosin
     x = flatten_x if flatten_x.dim() == 3 else flatten_x.reshape(1, -1, flatten_x.shape[-1])
     x = x.detach()
     means = _sample_rows(x, num_clusters, init_indices)            # batched_sample_vectors of vq_img.py:33, one codebook
+    if reduce_fn is not None and init_indices is None:
+        # data-parallel: every rank drew its own rows; all must iterate from ONE start (rank 0's), or the first
+        # all-reduce would sum statistics of unrelated clusters under one index and the replicas would diverge
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(means, src=0)
     bins = torch.zeros(num_clusters, dtype=torch.int64, device=x.device)
     for _ in range(num_iters):
         if use_cosine_sim:
