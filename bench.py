@@ -484,10 +484,14 @@ def main():
             torch.cuda.empty_cache()
             extras["c5_K65536_D256_N4Mi"] = extras_c5(dev, rank, world)
             torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
             if world > 1:
-                sys.path.insert(0, os.path.join(ROOT, "scripts"))
                 from multi_gpu_parity import run_parity
                 extras["parity"] = run_parity(rank, world, dev)
+            torch.cuda.empty_cache()
+            from train_step_c3 import run_c3                  # BASELINE configs[2]: the training step, "train img/s"
+            extras["c3_train_step"] = run_c3(dev, rank, world, steps=6, warmup=5)
+            torch.cuda.empty_cache()
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 extras["cpu_port"] = extras_cpu_port()
         except Exception as exc:                            # the headline line must still print

@@ -11,14 +11,22 @@ from vq_seg_b200 import ops, _native
 
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
-torch.manual_seed(1234)
-model = T.VQUnet(T.make_codebooks("b200_noema", dev, 1)).to(dev)
+n_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+arm = sys.argv[2] if len(sys.argv) > 2 else "b200_noema"
+args = argparse.Namespace(steps=1, warmup=1, per_gpu_batch=4, size=512)
+models, opts, step = T.build(arm, args, dev, 0, 1)
+model = models[0]
 model.train()
 g = torch.Generator(device=dev).manual_seed(100)
 x = torch.rand(4, 3, 512, 512, device=dev, generator=g)
-with torch.autocast("cuda", dtype=torch.float16):
-    out = model(x)                      # k-means init happens here
-feats = model.encoder(x)[1:]
+if n_steps == 0:
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = model(x)                      # k-means init happens here
+for i in range(n_steps):
+    loss = step()
+print(f"after {n_steps} training steps of arm {arm}")
+with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+    feats = model.encoder(x)[1:]
 for i, m in enumerate(model.codebook):
     if not isinstance(m, V.VectorQuantizer):
         continue

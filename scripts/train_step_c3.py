@@ -177,17 +177,20 @@ def dice_loss(pred, target, num_classes=3, eps=1e-6):
     return 1 - ((2 * inter + eps) / (p.sum(dim=(0, 2, 3)) + t.sum(dim=(0, 2, 3)) + eps)).mean()
 
 
-def run_arm(arm, args, dev, rank, world):
-    import torch.distributed as dist
+def build(arm, args, dev, rank, world):
+    """(models, step): the two CPS models of one arm and the closure that runs one training step"""
     torch.manual_seed(1234)                                   # same initial weights in every arm and on every rank
     models = [VQUnet(make_codebooks(arm, dev, world)).to(dev) for _ in range(2)]
     if world > 1:
         models = [nn.parallel.DistributedDataParallel(m, device_ids=[dev.index]) for m in models]
     opts = [torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4) for m in models]
-    scaler = torch.amp.GradScaler("cuda")
+    # (the default initial scale 2^16 overflows fp16 on this untrained net for the first ~6 steps: skipped optimizer
+    # steps would make the short timed window incomparable between arms)
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 10)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     nb, s = args.per_gpu_batch, args.size
     ce = nn.CrossEntropyLoss(ignore_index=255)
+    nb_ = nb
 
     def step():
         l_input = torch.rand(nb, 3, s, s, device=dev, generator=g)
@@ -222,6 +225,13 @@ def run_arm(arm, args, dev, rank, world):
         scaler.update()
         return loss
 
+    step.scaler = scaler
+    return models, opts, step
+
+
+def run_arm(arm, args, dev, rank, world):
+    import torch.distributed as dist
+    models, opts, step = build(arm, args, dev, rank, world)
     for _ in range(args.warmup):
         loss = step()
     torch.cuda.synchronize()
@@ -238,13 +248,15 @@ def run_arm(arm, args, dev, rank, world):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
-    out = {"ms_per_step": ms, "train_img_per_s": nb * world / (ms * 1e-3), "final_loss": float(loss.detach().float().item())}
+    nb = args.per_gpu_batch
+    out = {"ms_per_step": ms, "train_img_per_s": nb * world / (ms * 1e-3), "final_loss": float(loss.detach().float().item()),
+           "grad_scale_at_end": float(step.scaler.get_scale())}
     del models, opts
     torch.cuda.empty_cache()
     return out
 
 
-def run_c3(dev, rank, world, steps=8, warmup=3, per_gpu_batch=4, size=512, arms=("b200", "torch", "identity")):
+def run_c3(dev, rank, world, steps=10, warmup=6, per_gpu_batch=4, size=512, arms=("b200", "torch", "identity")):
     args = argparse.Namespace(steps=steps, warmup=warmup, per_gpu_batch=per_gpu_batch, size=size)
     res = {"images_per_step": f"{per_gpu_batch * world} labelled + {per_gpu_batch * world} unlabelled at {size}x{size}, "
                               f"two models: 4 train-mode + 2 eval-mode forwards, 1 backward, 2 Adam steps, fp16 autocast",
@@ -262,8 +274,8 @@ def run_c3(dev, rank, world, steps=8, warmup=3, per_gpu_batch=4, size=512, arms=
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--per-gpu-batch", type=int, default=4)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--arms", default="b200,torch,identity")
