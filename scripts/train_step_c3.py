@@ -182,7 +182,9 @@ def build(arm, args, dev, rank, world):
     torch.manual_seed(1234)                                   # same initial weights in every arm and on every rank
     models = [VQUnet(make_codebooks(arm, dev, world)).to(dev) for _ in range(2)]
     if world > 1:
-        models = [nn.parallel.DistributedDataParallel(m, device_ids=[dev.index]) for m in models]
+        # (two forwards of each model precede the backward: DDP's per-forward buffer broadcast would rewrite BatchNorm
+        # statistics the first forward's graph still needs; the EMA buffers stay equal through the all-reduced statistics)
+        models = [nn.parallel.DistributedDataParallel(m, device_ids=[dev.index], broadcast_buffers=False) for m in models]
     opts = [torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4) for m in models]
     # (the default initial scale 2^16 overflows fp16 on this untrained net for the first ~6 steps: skipped optimizer
     # steps would make the short timed window incomparable between arms)
