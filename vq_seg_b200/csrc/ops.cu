@@ -613,6 +613,38 @@ __global__ void __launch_bounds__(256) l2norm_lastdim_kernel(const float* __rest
   for (int d = l8; d < D; d += 8) o[d] = __fdiv_rn(row[d], nrm);       // in place is fine: each element is read by its writer
 }
 
+// pixel-contiguous maps (sP == 1): a block owns 32 neighbouring pixels of one image.  All eight warps stage 256
+// channels x 32 pixels (coalesced 128-byte lines) in shared memory, warp 0 runs the 32 sequential chains over them
+// (lane = pixel), chunk after chunk; then all warps divide (second read of x: L2).  The thread-per-pixel kernel below
+// had 32768 threads on the config-2 map, each waiting on 2 x 256 dependent strided loads: 99 us.
+__global__ void __launch_bounds__(256) l2norm_px_kernel(Rows x, RowsOut out) {
+  __shared__ float tile[256 * 32];
+  __shared__ float s_nrm[32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int D = (int)x.D;
+  const long long groups_per_image = (x.P + 31) / 32;
+  for (long long gidx = blockIdx.x; gidx < x.B * groups_per_image; gidx += gridDim.x) {
+    const long long b = gidx / groups_per_image, p = (gidx % groups_per_image) * 32 + lane;
+    const bool on = p < x.P;
+    const float* xp = x.ptr + b * x.sB + (on ? p : 0);
+    float acc = 0.f;
+    for (int d0 = 0; d0 < D; d0 += 256) {
+      const int dn = min(256, D - d0);
+      __syncthreads();
+      for (int j = wib; j < dn; j += 8) tile[j * 32 + lane] = on ? __ldg(xp + (long long)(d0 + j) * x.sD) : 0.f;
+      __syncthreads();
+      if (wib == 0)
+        for (int j = 0; j < dn; ++j) { const float v = tile[j * 32 + lane]; acc = __fadd_rn(acc, __fmul_rn(v, v)); }
+    }
+    if (wib == 0) s_nrm[lane] = fmaxf(__fsqrt_rn(acc), 1e-12f);
+    __syncthreads();
+    const float nrm = s_nrm[lane];
+    float* op = out.ptr + b * out.sB + (on ? p : 0) * out.sP;
+    if (on)
+      for (int d = wib; d < D; d += 8) op[(long long)d * out.sD] = __fdiv_rn(__ldg(xp + (long long)d * x.sD), nrm);
+  }
+}
+
 __global__ void __launch_bounds__(256) l2norm_strided_kernel(Rows x, RowsOut out) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= x.n_rows()) return;
@@ -677,6 +709,34 @@ __global__ void __launch_bounds__(256) ema_embed_kernel(const float* __restrict_
 using namespace vqseg;
 
 // one pass of the deterministic statistics over a row range (accumulates on top of counts / sums)
+// Rows [row0, row0 + n) of a strided (B, P, D) view copied into packed (n, D) rows: 32 x 32 tiles through a padded
+// shared-memory transpose (pixel-contiguous NCHW maps: reads coalesced along pixels, writes along dims).  The per-code
+// statistics of such maps run on the packed copy: scattering them from the strided layout costs one 32-byte sector per
+// 4-byte element (ncu, config-2 map: 765 us atomic / 1328 us ordered against ~25 us for pack + the row kernels).
+__global__ void __launch_bounds__(256) pack_rows_kernel(Rows x, long long row0, long long n, float* __restrict__ out) {
+  __shared__ float tile[8][32 * 33];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int D = (int)x.D;
+  const int n_dchunks = (D + 31) / 32;
+  float* t = tile[wib];
+  for (long long rt = blockIdx.x; rt * 32 < n; rt += gridDim.x) {
+    const long long r = rt * 32 + lane;                          // this lane's row while reading
+    const float* xr = x.row(row0 + (r < n ? r : n - 1));
+    for (int c = wib; c < n_dchunks; c += 8) {
+      const int d0 = c * 32;
+      __syncwarp();
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) t[j * 33 + lane] = (d0 + j < D) ? __ldg(xr + (long long)(d0 + j) * x.sD) : 0.f;
+      __syncwarp();
+      if (d0 + lane < D) {
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i)
+          if (rt * 32 + i < n) out[(rt * 32 + i) * D + d0 + lane] = t[lane * 33 + i];
+      }
+    }
+  }
+}
+
 static int stats_det_range(const float* x, long long B, long long P, long long D, long long sB, long long sP, long long sD,
                            const int64_t* idx, long long K, int64_t* counts, float* sums, void* ws, cudaStream_t st) {
   const long long n_rows = B * P;
@@ -818,8 +878,13 @@ int vqseg_gather_bwd_codebook_f32(const float* g_q, int64_t B, int64_t P, int64_
   return 0;
 }
 
-size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int deterministic) {
-  (void)D;
+// rows per pass of the chunked paths: at most 64 MB of rows (see vqseg_code_stats_f32)
+static long long stats_rows_per_chunk(long long D) {
+  const long long row_bytes = D * (long long)sizeof(float);
+  long long r = (64ll << 20) / row_bytes;
+  return r < 4096 ? 4096 : r / 1024 * 1024;
+}
+static size_t stats_sort_ws_bytes(long long n_rows, long long K, int deterministic) {
   if (!deterministic) return 256;
   long long nblk = (n_rows + kSortBlock - 1) / kSortBlock;
   size_t b = 0;
@@ -828,6 +893,11 @@ size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, in
   b += round_up((K + 1) * sizeof(long long), 256);     // code_start
   b += round_up(n_rows * sizeof(int), 256);            // perm
   return b + 256;
+}
+size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int deterministic) {
+  // + the packed-row scratch of one chunk (strided inputs are packed chunk by chunk before the row kernels run)
+  const long long chunk = n_rows < stats_rows_per_chunk(D) ? n_rows : stats_rows_per_chunk(D);
+  return stats_sort_ws_bytes(n_rows, K, deterministic) + (size_t)round_up(chunk * D * (long long)sizeof(float), 256);
 }
 
 int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
@@ -839,37 +909,61 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
   if (n_rows >= (1ll << 31)) return VQSEG_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   Rows xr{x, B, P, D, sB, sP, sD};
+  if (!ws || ws_bytes < vqseg_code_stats_workspace_bytes(n_rows, D, K, deterministic)) return VQSEG_EWORKSPACE;
+  const long long rows_per_chunk = stats_rows_per_chunk(D);
+  float* scratch = reinterpret_cast<float*>((char*)ws + stats_sort_ws_bytes(n_rows, K, deterministic));
+  const bool vec_ok = D % 4 == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0;
+  const bool flat = sD == 1 && (B == 1 || sB == P * sP);              // one flat range of rows, stride sP
+  const bool direct = flat && vec_ok && sP % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  auto pack = [&](long long r0, long long len) -> int {
+    long long blocks = (len + 31) / 32;
+    const long long cap = (long long)num_sms() * 8;
+    pack_rows_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xr, r0, len, scratch);
+    VQSEG_LAUNCH_CHECK();
+    return 0;
+  };
   if (!deterministic) {
-    const bool packed_rows = B == 1 && sD == 1 && D % 4 == 0 && sP % 4 == 0 &&
-                             (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0;
-    if (packed_rows)
-      code_stats_atomic_rows_kernel<<<grid_for(n_rows * 32, 256, 16), 256, 0, st>>>(x, sP, n_rows, (int)D, (const long long*)idx,
-                                                                                   (int)K, (unsigned long long*)counts, sums);
-    else
-      code_stats_atomic_kernel<<<grid_for(n_rows * D, 256, 16), 256, 0, st>>>(xr, (const long long*)idx, (int)K,
-                                                                              (unsigned long long*)counts, sums, sP == 1);
+    auto rows_kernel = [&](const float* rows, long long stride, long long len, const int64_t* ix) -> int {
+      code_stats_atomic_rows_kernel<<<grid_for(len * 32, 256, 16), 256, 0, st>>>(rows, stride, len, (int)D, (const long long*)ix,
+                                                                                 (int)K, (unsigned long long*)counts, sums);
+      VQSEG_LAUNCH_CHECK();
+      return 0;
+    };
+    if (direct) return rows_kernel(x, sP, n_rows, idx);
+    if (vec_ok) {                                                     // strided (NCHW maps): pack, then vector reductions
+      for (long long r0 = 0; r0 < n_rows; r0 += rows_per_chunk) {
+        const long long len = n_rows - r0 < rows_per_chunk ? n_rows - r0 : rows_per_chunk;
+        if (int rc = pack(r0, len)) return rc;
+        if (int rc = rows_kernel(scratch, D, len, idx + r0)) return rc;
+      }
+      return 0;
+    }
+    code_stats_atomic_kernel<<<grid_for(n_rows * D, 256, 16), 256, 0, st>>>(xr, (const long long*)idx, (int)K,
+                                                                            (unsigned long long*)counts, sums, sP == 1);
     VQSEG_LAUNCH_CHECK();
     return 0;
   }
-  if (ws_bytes < vqseg_code_stats_workspace_bytes(n_rows, D, K, 1) || !ws) return VQSEG_EWORKSPACE;
   if (K * sizeof(int) > 200 * 1024) return VQSEG_EUNSUPPORTED;
   // The ordered sums visit rows grouped by code, i.e. in random order over the whole array: beyond the TLB reach
   // (256 MB of 2 MB pages) every access misses and the chains crawl at ~1.3 us per row.  Row ranges of at most
-  // kDetChunkBytes are therefore processed one after the other; each (code, d) chain simply continues on top of
+  // 64 MB are therefore processed one after the other; each (code, d) chain simply continues on top of
   // `sums`, so the summation order -- ascending row id per code -- is unchanged.
-  const long long kDetChunkBytes = 64ll << 20;
-  const long long row_bytes = D * (long long)sizeof(float);
-  long long rows_per_chunk = kDetChunkBytes / row_bytes;
-  rows_per_chunk = rows_per_chunk < 4096 ? 4096 : rows_per_chunk / 1024 * 1024;
-  if (n_rows <= rows_per_chunk) return stats_det_range(x, B, P, D, sB, sP, sD, idx, K, counts, sums, ws, st);
-  if (B == 1) {
+  if (direct || vec_ok) {
     for (long long r0 = 0; r0 < n_rows; r0 += rows_per_chunk) {
       const long long len = n_rows - r0 < rows_per_chunk ? n_rows - r0 : rows_per_chunk;
-      int rc = stats_det_range(x + r0 * sP, 1, len, D, sB, sP, sD, idx + r0, K, counts, sums, ws, st);
+      int rc;
+      if (direct) {
+        rc = stats_det_range(x + r0 * sP, 1, len, D, len * sP, sP, 1, idx + r0, K, counts, sums, ws, st);
+      } else {                                                        // strided (NCHW maps): pack the range first
+        if ((rc = pack(r0, len))) return rc;
+        rc = stats_det_range(scratch, 1, len, D, len * D, D, 1, idx + r0, K, counts, sums, ws, st);
+      }
       if (rc) return rc;
     }
     return 0;
   }
+  // any D, any strides: the generic ordered kernel on the strided view
+  if (n_rows <= rows_per_chunk) return stats_det_range(x, B, P, D, sB, sP, sD, idx, K, counts, sums, ws, st);
   if (P <= rows_per_chunk) {                 // whole images per pass
     const long long ipc = rows_per_chunk / P;
     for (long long b0 = 0; b0 < B; b0 += ipc) {
@@ -948,7 +1042,12 @@ int vqseg_l2norm_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
   } else {
     Rows xr{x, B, P, D, sB, sP, sD};
     RowsOut orow{out, B, P, D, oB, oP, oD};
-    l2norm_strided_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(xr, orow);
+    if (sP == 1) {
+      const long long groups = B * ((P + 31) / 32), cap = (long long)num_sms() * 16;
+      l2norm_px_kernel<<<(unsigned)(groups < cap ? groups : cap), 256, 0, st>>>(xr, orow);
+    } else {
+      l2norm_strided_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(xr, orow);
+    }
   }
   VQSEG_LAUNCH_CHECK();
   return 0;
