@@ -404,6 +404,23 @@ __global__ void __launch_bounds__(256) stats_scan_blocks_kernel(int* __restrict_
   code_total[k] = run;
   if (counts) atomicAdd(counts + k, (unsigned long long)run);
 }
+// (2b) the same per (chunk, code): exclusive scan over the chunk's ranking blocks, segment size out (chunk-major)
+__global__ void __launch_bounds__(256) stats_scan_chunks_kernel(int* __restrict__ hist, int nblk, int K, int blocks_per_chunk,
+                                                                int n_chunks, unsigned long long* __restrict__ counts,
+                                                                long long* __restrict__ seg_total) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_chunks * K) return;
+  const int c = (int)(t / K), k = (int)(t % K);
+  const int b1 = min(nblk, (c + 1) * blocks_per_chunk);
+  long long run = 0;
+  for (int b = c * blocks_per_chunk; b < b1; ++b) {
+    const int h = hist[(long long)b * K + k];
+    hist[(long long)b * K + k] = (int)run;
+    run += h;
+  }
+  seg_total[t] = run;
+  if (counts && run) atomicAdd(counts + k, (unsigned long long)run);
+}
 // (3) exclusive scan over codes (single block)
 __global__ void __launch_bounds__(1024) stats_scan_codes_kernel(const long long* __restrict__ code_total, int K,
                                                                 long long* __restrict__ code_start /* K+1 */) {
@@ -424,10 +441,13 @@ __global__ void __launch_bounds__(1024) stats_scan_codes_kernel(const long long*
   for (int i = 0; i < per && k0 + i < K; ++i) { code_start[k0 + i] = run; run += code_total[k0 + i]; }
 }
 // (4) stable scatter: perm[code_start[k] + hist[blk][k] + rank_in_block] = n
+// `blocks_per_chunk` > 0: the sort key is (chunk of blocks_per_chunk ranking blocks, code): code_start then holds one
+// row of K segment starts per chunk.
 __global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __restrict__ idx, long long n_rows, int K,
                                                              const int* __restrict__ hist,
                                                              const long long* __restrict__ code_start,
-                                                             int* __restrict__ perm) {
+                                                             int* __restrict__ perm, int blocks_per_chunk = 0) {
+  if (blocks_per_chunk > 0) code_start += (long long)(blockIdx.x / blocks_per_chunk) * K;
   extern __shared__ int s_run[];    // K running counters
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_run[k] = 0;
   __syncthreads();
@@ -884,20 +904,21 @@ static long long stats_rows_per_chunk(long long D) {
   long long r = (64ll << 20) / row_bytes;
   return r < 4096 ? 4096 : r / 1024 * 1024;
 }
-static size_t stats_sort_ws_bytes(long long n_rows, long long K, int deterministic) {
+static size_t stats_sort_ws_bytes(long long n_rows, long long D, long long K, int deterministic) {
   if (!deterministic) return 256;
   long long nblk = (n_rows + kSortBlock - 1) / kSortBlock;
+  const long long n_chunks = (n_rows + stats_rows_per_chunk(D) - 1) / stats_rows_per_chunk(D);
   size_t b = 0;
-  b += round_up(nblk * K * sizeof(int), 256);          // hist
-  b += round_up(K * sizeof(long long), 256);           // code_total
-  b += round_up((K + 1) * sizeof(long long), 256);     // code_start
-  b += round_up(n_rows * sizeof(int), 256);            // perm
+  b += round_up(nblk * K * sizeof(int), 256);                       // hist
+  b += round_up(n_chunks * K * sizeof(long long), 256);             // segment sizes per (chunk, code)
+  b += round_up((n_chunks * K + 1) * sizeof(long long), 256);       // segment starts
+  b += round_up(n_rows * sizeof(int), 256);                         // perm
   return b + 256;
 }
 size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int deterministic) {
   // + the packed-row scratch of one chunk (strided inputs are packed chunk by chunk before the row kernels run)
   const long long chunk = n_rows < stats_rows_per_chunk(D) ? n_rows : stats_rows_per_chunk(D);
-  return stats_sort_ws_bytes(n_rows, K, deterministic) + (size_t)round_up(chunk * D * (long long)sizeof(float), 256);
+  return stats_sort_ws_bytes(n_rows, D, K, deterministic) + (size_t)round_up(chunk * D * (long long)sizeof(float), 256);
 }
 
 int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
@@ -911,7 +932,7 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
   Rows xr{x, B, P, D, sB, sP, sD};
   if (!ws || ws_bytes < vqseg_code_stats_workspace_bytes(n_rows, D, K, deterministic)) return VQSEG_EWORKSPACE;
   const long long rows_per_chunk = stats_rows_per_chunk(D);
-  float* scratch = reinterpret_cast<float*>((char*)ws + stats_sort_ws_bytes(n_rows, K, deterministic));
+  float* scratch = reinterpret_cast<float*>((char*)ws + stats_sort_ws_bytes(n_rows, D, K, deterministic));
   const bool vec_ok = D % 4 == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0;
   const bool flat = sD == 1 && (B == 1 || sB == P * sP);              // one flat range of rows, stride sP
   const bool direct = flat && vec_ok && sP % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
@@ -949,16 +970,47 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
   // 64 MB are therefore processed one after the other; each (code, d) chain simply continues on top of
   // `sums`, so the summation order -- ascending row id per code -- is unchanged.
   if (direct || vec_ok) {
-    for (long long r0 = 0; r0 < n_rows; r0 += rows_per_chunk) {
+    // ONE stable counting sort of all row ids by (chunk, code) -- histograms per 1024-row block, a scan per (chunk,
+    // code) over the chunk's blocks, a scan over the segments, a stable scatter -- then one ordered-sum launch per
+    // chunk, each continuing the (code, d) chains on top of `sums`.  (Sorting chunk by chunk cost six small launches
+    // per 64 MB: 22.7 ms at config 4's 10 M rows against 5.0 ms for the atomic path.)
+    const long long nblk = (n_rows + kSortBlock - 1) / kSortBlock;
+    const int bpc = (int)(rows_per_chunk / kSortBlock);
+    const long long n_chunks = (n_rows + rows_per_chunk - 1) / rows_per_chunk;
+    char* p = (char*)ws;
+    int* hist = (int*)p;                    p += round_up(nblk * K * sizeof(int), 256);
+    long long* seg_total = (long long*)p;   p += round_up(n_chunks * K * sizeof(long long), 256);
+    long long* seg_start = (long long*)p;   p += round_up((n_chunks * K + 1) * sizeof(long long), 256);
+    int* perm = (int*)p;
+    cudaError_t e = cudaMemsetAsync(hist, 0, nblk * K * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    stats_hist_kernel<<<(unsigned)nblk, kSortBlock, 0, st>>>((const long long*)idx, n_rows, (int)K, hist);
+    VQSEG_LAUNCH_CHECK();
+    stats_scan_chunks_kernel<<<(unsigned)((n_chunks * K + 255) / 256), 256, 0, st>>>(hist, (int)nblk, (int)K, bpc, (int)n_chunks,
+                                                                                    (unsigned long long*)counts, seg_total);
+    VQSEG_LAUNCH_CHECK();
+    if (n_chunks * K >= (1ll << 31)) return VQSEG_EUNSUPPORTED;
+    stats_scan_codes_kernel<<<1, 1024, 0, st>>>(seg_total, (int)(n_chunks * K), seg_start);
+    VQSEG_LAUNCH_CHECK();
+    const size_t smem = (size_t)K * sizeof(int);
+    static size_t configured[kMaxDevices] = {0};
+    if (int rc = ensure_dynamic_smem(stats_scatter_kernel, smem, configured)) return rc;
+    stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>((const long long*)idx, n_rows, (int)K, hist, seg_start, perm, bpc);
+    VQSEG_LAUNCH_CHECK();
+    const long long warps = K * ((D + 127) / 128);
+    for (long long c = 0; c < n_chunks; ++c) {
+      const long long r0 = c * rows_per_chunk;
       const long long len = n_rows - r0 < rows_per_chunk ? n_rows - r0 : rows_per_chunk;
-      int rc;
-      if (direct) {
-        rc = stats_det_range(x + r0 * sP, 1, len, D, len * sP, sP, 1, idx + r0, K, counts, sums, ws, st);
-      } else {                                                        // strided (NCHW maps): pack the range first
-        if ((rc = pack(r0, len))) return rc;
-        rc = stats_det_range(scratch, 1, len, D, len * D, D, 1, idx + r0, K, counts, sums, ws, st);
+      const float* base = x;                                          // perm holds GLOBAL row ids
+      long long stride = sP;
+      if (!direct) {                                                  // strided (NCHW maps): pack the range first
+        if (int rc = pack(r0, len)) return rc;
+        base = scratch - r0 * D;                                      // (only rows [r0, r0 + len) are ever addressed)
+        stride = D;
       }
-      if (rc) return rc;
+      stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(base, stride, (int)D, perm,
+                                                                                          seg_start + c * K, (int)K, sums);
+      VQSEG_LAUNCH_CHECK();
     }
     return 0;
   }
