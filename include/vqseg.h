@@ -214,6 +214,15 @@ int    vqseg_dist_map_bwd_f32(const float* g, const float* dist, int64_t oB, int
                               const float* E, int64_t K,
                               float* gx_out, int64_t gxB, int64_t gxP, int64_t gxD, float* gE_out,
                               const float* score, void* stream);
+/* backward of the cosine similarity map (vqseg_dist_map_f32 with cosine = 1 on x, i.e. CosinesimSegHead's
+ * l2norm(x) @ weight^T, models/modules/vq_segmentation_head.py:97-104): g is the gradient w.r.t. the map (same strides
+ * as the map); gx = (gxn - xn <xn, gxn>) / |x| with gxn = g @ E, gE[k,:] = sum_n g[n,k] xn[n,:].  Same limits as the map. */
+int    vqseg_sim_map_bwd_f32(const float* g, int64_t oB, int64_t oP, int64_t oK,
+                             const float* x, int64_t B, int64_t P, int64_t D,
+                             int64_t sB, int64_t sP, int64_t sD,
+                             const float* E, int64_t K,
+                             float* gx_out, int64_t gxB, int64_t gxP, int64_t gxD, float* gE_out, void* stream);
+
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,8 @@ def test_error_strings_and_sizes(native):
     assert lib.vqseg_codebook_blob_bytes(512, 256) == 1024 + 4096 + 512 * 256 * 2 + 4 * 4096 + 4096
     assert lib.vqseg_codebook_blob_bytes(300, 100) == 1024 + 4096 + 512 * 128 * 2 + 4 * 4096 + 4096
     assert lib.vqseg_assign_workspace_bytes(32768, 256, 512, 0) >= 32768 * 48        # one 48-byte work record per row
-    assert lib.vqseg_code_stats_workspace_bytes(1000, 64, 32, 0) == 256
+    # atomic statistics: 256 bytes + the packed-row scratch of one chunk (strided maps are packed before the row kernels)
+    assert lib.vqseg_code_stats_workspace_bytes(1000, 64, 32, 0) == 256 + 1000 * 64 * 4
 
 
 def test_sass_is_blackwell_native():

@@ -41,6 +41,7 @@ SIGNATURES = {
     "vqseg_dist_map_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, ci, vp, i64, i64, i64, vp, vp, vp, vp]),
     "vqseg_dist_map_bwd_f32": (ci, [vp, vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, vp, i64,
                                     vp, i64, i64, i64, vp, vp, vp]),
+    "vqseg_sim_map_bwd_f32": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, i64, i64, i64, vp, vp]),
 }
 
 

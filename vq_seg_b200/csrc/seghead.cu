@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
                                                                  const float* __restrict__ g, const float* __restrict__ dist,
                                                                  long long oB, long long oP, long long oK,
                                                                  RowsOut gx, float* __restrict__ gE,
-                                                                 const float* __restrict__ score) {
+                                                                 const float* __restrict__ score, int cosine) {
+  // cosine != 0: backward of sim[n,k] = <x_n / max(|x_n|, 1e-12), e_k> (CosinesimSegHead, vq_segmentation_head.py:
+  // 97-104) instead: w = g;  gxn = sum_k w_k e_k;  gx = (gxn - xn <xn, gxn>) / |x|;  gE[k,:] = sum_n w[n,k] xn[n,:]
+  // (`dist` is not read).
   extern __shared__ __align__(16) float dmb_smem[];
   const int D = (int)x.D;
   float* s_e = dmb_smem;                          // [K][D]
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
       gk[k] = 0.f; dv[k] = 0.f;
       if (in && k < K) {
         const long long o = b * oB + pp * oP + (long long)k * oK;
-        dv[k] = __ldg(dist + o);
+        dv[k] = cosine ? 1.f : __ldg(dist + o);
         gk[k] = __ldg(g + o);
       }
     }
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
     for (int k = 0; k < KMAX; ++k) {
       w[k] = 0.f;
       if (k < K) {
-        if (in) w[k] = dv[k] == 0.f ? 0.f : __fdiv_rn(gk[k], dv[k]);
+        if (in) w[k] = cosine ? gk[k] : (dv[k] == 0.f ? 0.f : __fdiv_rn(gk[k], dv[k]));
         s_w[k * kDmThreads + threadIdx.x] = w[k];
         wsum += w[k];
       }
@@ -239,6 +242,23 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
   }
   const float* xr = x.ptr + b * x.sB + pp * x.sP;
   float* gxr = gx.ptr + b * gx.sB + pp * gx.sP;
+  float inv_nrm = 1.f, dot = 0.f;
+  if (cosine) {
+    // |x|^2 and <x, gxn> in one pass over the row (x is read again below: L1 / L2)
+    float ss = 0.f, raw = 0.f;
+    if (in)
+      for (int d = 0; d < D; ++d) {
+        const float v = __ldg(xr + (long long)d * x.sD);
+        float gxn = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) gxn = fmaf(w[k], s_e[k * D + d], gxn);
+        ss = fmaf(v, v, ss);
+        raw = fmaf(v, gxn, raw);
+      }
+    inv_nrm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    dot = raw * inv_nrm;                               // <xn, gxn>
+  }
   for (int d0 = 0; d0 < D; d0 += 32) {
     float xv[32];
 #pragma unroll
@@ -246,12 +266,14 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
     __syncthreads();                               // previous chunk's tile fully consumed (and s_ws visible)
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
+      if (cosine) xv[u] *= inv_nrm;                // the tile (and the prototype gradient) work on xn
       s_x[u * kDmXStride + threadIdx.x] = xv[u];
       if (in && d0 + u < D) {
-        float acc = xv[u] * wsum;                  // sum_k w_k (x - e_k) = x sum_k w_k - sum_k w_k e_k
+        float acc = cosine ? 0.f : xv[u] * wsum;   // sum_k w_k (x - e_k) = x sum_k w_k - sum_k w_k e_k
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
-          if (k < K) acc = fmaf(-w[k], s_e[k * D + d0 + u], acc);
+          if (k < K) acc = fmaf(cosine ? w[k] : -w[k], s_e[k * D + d0 + u], acc);
+        if (cosine) acc = (acc - xv[u] * dot) * inv_nrm;
         gxr[(long long)(d0 + u) * gx.sD] = acc;
       }
     }
@@ -270,7 +292,7 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
           a0 = fmaf(w4.x, x4.x, a0); a1 = fmaf(w4.y, x4.y, a1);
           a2 = fmaf(w4.z, x4.z, a2); a3 = fmaf(w4.w, x4.w, a3);
         }
-        const float r = s_e[k * D + d0 + dd] * s_ws[k] - ((a0 + a1) + (a2 + a3));
+        const float r = cosine ? ((a0 + a1) + (a2 + a3)) : s_e[k * D + d0 + dd] * s_ws[k] - ((a0 + a1) + (a2 + a3));
         if (r != 0.f) atomicAdd(gE + (long long)k * D + d0 + dd, r);
       }
     }
@@ -299,11 +321,11 @@ static int launch_dm(const Rows& x, const float* E, int K, bool cosine, float* d
 
 template <int KMAX>
 static int launch_dm_bwd(const Rows& x, const float* E, int K, const float* g, const float* dist, long long oB, long long oP,
-                         long long oK, const RowsOut& gx, float* gE, const float* score, cudaStream_t st) {
+                         long long oK, const RowsOut& gx, float* gE, const float* score, cudaStream_t st, int cosine = 0) {
   const size_t smem = ((size_t)((K * x.D + 3) & ~3) + (size_t)K * kDmThreads + KMAX + 32 * kDmXStride) * sizeof(float);
   const unsigned grid = (unsigned)((x.n_rows() + kDmThreads - 1) / kDmThreads);
   if (smem > 48 * 1024) cudaFuncSetAttribute(dist_map_bwd_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  dist_map_bwd_kernel<KMAX><<<grid, kDmThreads, smem, st>>>(x, E, K, g, dist, oB, oP, oK, gx, gE, score);
+  dist_map_bwd_kernel<KMAX><<<grid, kDmThreads, smem, st>>>(x, E, K, g, dist, oB, oP, oK, gx, gE, score, cosine);
   VQSEG_LAUNCH_CHECK();
   return 0;
 }
@@ -356,6 +378,26 @@ int vqseg_dist_map_bwd_f32(const float* g, const float* dist, int64_t oB, int64_
   if (K <= 8) return launch_dm_bwd<8>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, score, st);
   if (K <= 16) return launch_dm_bwd<16>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, score, st);
   return launch_dm_bwd<32>(xr, E, (int)K, g, dist, oB, oP, oK, gx, gE_out, score, st);
+}
+
+int vqseg_sim_map_bwd_f32(const float* g, int64_t oB, int64_t oP, int64_t oK,
+                          const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                          const float* E, int64_t K,
+                          float* gx_out, int64_t gxB, int64_t gxP, int64_t gxD, float* gE_out, void* stream) {
+  if (!g || !x || !E || !gx_out || !gE_out || B < 0 || P < 0) return VQSEG_EINVAL;
+  if (!dm_supported(K, D)) return VQSEG_EUNSUPPORTED;
+  int rc = check_arch();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(gE_out, 0, (size_t)K * D * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  if (B * P == 0) return 0;
+  Rows xr{x, B, P, D, sB, sP, sD};
+  RowsOut gx{gx_out, B, P, D, gxB, gxP, gxD};
+  if (K <= 4) return launch_dm_bwd<4>(xr, E, (int)K, g, g, oB, oP, oK, gx, gE_out, nullptr, st, 1);
+  if (K <= 8) return launch_dm_bwd<8>(xr, E, (int)K, g, g, oB, oP, oK, gx, gE_out, nullptr, st, 1);
+  if (K <= 16) return launch_dm_bwd<16>(xr, E, (int)K, g, g, oB, oP, oK, gx, gE_out, nullptr, st, 1);
+  return launch_dm_bwd<32>(xr, E, (int)K, g, g, oB, oP, oK, gx, gE_out, nullptr, st, 1);
 }
 
 }  // extern "C"

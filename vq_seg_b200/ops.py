@@ -502,6 +502,43 @@ def _dist_map_bwd_impl(grad: torch.Tensor, dist: torch.Tensor, x: torch.Tensor,
 dist_map_bwd = torch.library.custom_op("vqseg::dist_map_bwd", mutates_args=())(_dist_map_bwd_impl)
 
 
+def _sim_map_bwd_impl(grad: torch.Tensor, sim: torch.Tensor, x: torch.Tensor, codebook: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Backward of the cosine similarity map l2norm(x) @ codebook^T (codebook rows already unit-norm):
+    (gx with x's (B, P, D) shape in NCHW memory order, gE (K, D)).  `sim` only lends its strides to the gradient."""
+    _require_cuda(grad, sim, x, codebook)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    cb = codebook.detach()
+    if cb.dtype != torch.float32 or not cb.is_contiguous():
+        cb = cb.contiguous().float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    k = cb.shape[0]
+    g = grad.float()
+    if g.stride() != sim.stride():
+        g2 = torch.empty_strided(sim.shape, sim.stride(), dtype=torch.float32, device=sim.device)
+        g2.copy_(g)
+        g = g2
+    gx = torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=x.device)
+    ge = torch.empty((k, d), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_sim_map_bwd_f32(g.data_ptr(), g.stride(0), g.stride(1), g.stride(2),
+                                              x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
+                                              gx.data_ptr(), gx.stride(0), gx.stride(1), gx.stride(2), ge.data_ptr(),
+                                              _stream()), "sim_map_bwd")
+    return gx, ge
+
+
+sim_map_bwd = torch.library.custom_op("vqseg::sim_map_bwd", mutates_args=())(_sim_map_bwd_impl)
+
+
+@sim_map_bwd.register_fake
+def _(grad, sim, x, codebook):
+    b, p, d = x.shape
+    return (torch.empty_strided((b, p, d), (d * p, 1, p), dtype=torch.float32, device=x.device),
+            x.new_empty((codebook.shape[0], d), dtype=torch.float32))
+
+
 @dist_map_bwd.register_fake
 def _(grad, dist, x, codebook, score=None):
     b, p, d = x.shape

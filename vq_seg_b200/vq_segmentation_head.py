@@ -69,27 +69,22 @@ class EuclideanSegHead(_SegHeadBase):
 
 class _CosineMap(torch.autograd.Function):
     """similarity = l2norm(x) @ weight^T with weight already unit-norm (:97-104); gradient through the
-    normalisation to x and directly to the weight (the reference renormalises weight.data in place)."""
+    normalisation to x and directly to the weight (the reference renormalises weight.data in place).  Forward: the
+    map kernel normalises on the fly; backward: one kernel (vqseg_sim_map_bwd_f32)."""
 
     @staticmethod
     def forward(ctx, x, weight):
         xn = ops.l2norm_rows(x)
         sim, idx, counts = (ops._dist_map_impl if ops._fast() else ops.dist_map)(xn, weight, True)
-        ctx.save_for_backward(x, xn, weight)
+        ctx.save_for_backward(x, sim, weight)
         ctx.mark_non_differentiable(idx, counts)
         return sim, idx, counts
 
     @staticmethod
     def backward(ctx, g, g_idx, g_counts):
-        x, xn, weight = ctx.saved_tensors
-        g = g.float()
-        gw = torch.einsum("bpk,bpd->kd", g, xn) if ctx.needs_input_grad[1] else None
-        gx = None
-        if ctx.needs_input_grad[0]:
-            gxn = torch.einsum("bpk,kd->bpd", g, weight.detach())
-            norm = x.float().norm(dim=-1, keepdim=True).clamp_min(1e-12)
-            gx = (gxn - xn * (xn * gxn).sum(-1, keepdim=True)) / norm
-        return gx, gw
+        x, sim, weight = ctx.saved_tensors
+        gx, gw = (ops._sim_map_bwd_impl if ops._fast() else ops.sim_map_bwd)(g, sim, x, weight)
+        return (gx if ctx.needs_input_grad[0] else None), (gw if ctx.needs_input_grad[1] else None)
 
 
 class CosinesimSegHead(_SegHeadBase):
