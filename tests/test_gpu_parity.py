@@ -633,7 +633,7 @@ def test_ema_extension_matches_standard_equations(dev):
     xv = view(x)
     cnt = torch.bincount(idx.cpu().reshape(-1), minlength=e.shape[0])
     sm = torch.zeros_like(e).index_add_(0, idx.cpu().reshape(-1), xv.reshape(-1, 64))
-    _, _, w_exp = O.ema_update(cnt, sm, torch.zeros(e.shape[0]), e.clone(), 0.9, 1e-5)
+    _, _, w_exp = O.ema_update(cnt, sm, torch.ones(e.shape[0]), e.clone(), 0.9, 1e-5)       # cluster_size starts at one per code
     assert torch.equal(idx.cpu().reshape(xv.shape[:2]), O.assign_euclidean(xv, e))     # the lookup used the OLD codebook
     assert torch.allclose(m.codebook.embedding.weight.detach().cpu(), w_exp, rtol=1e-4, atol=1e-5)
     w1 = m.codebook.embedding.weight.detach().cpu().clone()

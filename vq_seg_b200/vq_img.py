@@ -128,19 +128,22 @@ class _CodebookBase(nn.Module):
         self._blob = None
 
     # ---- opt-in EMA codebook update (extension; the reference never reads decay / eps) ----
-    def enable_ema(self, decay=None, eps=1e-5, reduce_fn=None, deterministic=False):
+    def enable_ema(self, decay=None, eps=1e-5, reduce_fn=None, deterministic=False, persistent=False):
         """After every TRAINING forward move the codebook towards the per-code means of that batch with the
         standard VQ-VAE EMA rule (include/vqseg.h, vqseg_ema_update_f32), using the `decay` the constructor stored
         (VectorQuantizer.enable_ema() also passes its stored `eps`).  `reduce_fn(counts, sums)` all-reduces the statistics in data-parallel training
-        (vq_seg_b200.distributed.allreduce_code_stats).  The moving averages are non-persistent buffers, so
-        state_dict keys stay the reference's."""
+        (vq_seg_b200.distributed.allreduce_code_stats).  The moving averages are non-persistent buffers by default, so
+        state_dict keys stay the reference's; `persistent=True` puts `cluster_size` / `embed_avg` into the state_dict so
+        a resumed run continues the averages instead of restarting them.  They start as if every code had been used
+        once (cluster_size = 1, embed_avg = weight): a code that gets no vector in the first steps keeps its weight
+        instead of being divided by ~eps."""
         if decay is not None:
             self.decay = decay
         self.ema_eps = eps
         w = self.embedding.weight
-        self.register_buffer("cluster_size", torch.zeros(self.num_embeddings, dtype=torch.float32, device=w.device),
-                             persistent=False)
-        self.register_buffer("embed_avg", w.detach().clone().float().contiguous(), persistent=False)
+        self.register_buffer("cluster_size", torch.ones(self.num_embeddings, dtype=torch.float32, device=w.device),
+                             persistent=persistent)
+        self.register_buffer("embed_avg", w.detach().clone().float().contiguous(), persistent=persistent)
         self.ema_reduce_fn = reduce_fn
         self.ema_deterministic = deterministic
         self.ema_enabled = True
@@ -148,6 +151,8 @@ class _CodebookBase(nn.Module):
 
     @torch.no_grad()
     def _ema_step(self, x, idx):
+        if idx.numel() == 0:
+            return                              # an empty batch carries no statistics (and n = 0 would divide by zero)
         counts, sums = ops.code_stats(x, idx, self.num_embeddings, self.ema_deterministic)
         if self.ema_reduce_fn is not None:
             self.ema_reduce_fn(counts, sums)
