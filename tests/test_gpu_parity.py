@@ -713,6 +713,54 @@ def test_random_shape_fuzz(dev):
         assert near_tie_ok(x.reshape(b, c, hw, 1), e, i_ex.cpu(), ref_idx), (it, b, c, hw, k)
 
 
+def test_random_shape_fuzz_every_filter_and_metric(dev):
+    """30 random problems through EVERY tensor-core filter that accepts the shape (single-CTA streaming, register-fed
+    pair, TMA-fed pair, TMA-fed streaming pair) in both metrics: each must give the exact scorer's indices and counts;
+    the cosine indices must equal the CPU reference's (einsum + argmax on F.normalize'd inputs) up to near-ties."""
+    from vq_seg_b200 import ops
+    rng = torch.Generator().manual_seed(4321)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=rng))     # noqa: E731
+    algos = {"stream": ops.ALGO_TC_STREAM, "pair": ops.ALGO_TC_PAIR, "tma": ops.ALGO_TC_TMA, "stream_pair": ops.ALGO_TC_STREAM_PAIR}
+    ran = {k: 0 for k in algos}
+    for it in range(30):
+        b, c, hw, k = ri(1, 3), 4 * ri(2, 140), 4 * ri(8, 700), ri(30, 3000)
+        x = torch.randn(b, c, hw, generator=rng)
+        if it % 3 == 0:
+            x = torch.relu(x)
+        e = x.permute(0, 2, 1).reshape(-1, c)[torch.randint(0, b * hw, (k,), generator=rng)] + 0.3 * torch.randn(k, c, generator=rng)
+        xd, ed = x.to(dev), e.to(dev).contiguous()
+        xv = xd.permute(0, 2, 1)
+        if it % 4 == 1:
+            xv = xv.contiguous()
+        for ip in (False, True):
+            xx, ee = xv, ed
+            if ip:
+                xx = ops.l2norm_rows(xv)
+                ee = ed.clone()
+                ops.l2norm_rows_(ee)
+            flag = ops.METRIC_IP if ip else 0
+            blob = ops.prepare_codebook(ee, ip)
+            i_ex, c_ex = ops.assign(xx, ee, None, ops.ALGO_EXACT | flag)
+            for name, algo in algos.items():
+                try:
+                    idx, counts = ops.assign(xx, ee, blob, algo | flag)
+                except RuntimeError as exc:
+                    assert "not supported" in str(exc), exc
+                    continue
+                ran[name] += 1
+                assert torch.equal(idx, i_ex) and torch.equal(counts, c_ex), (it, name, ip, b, c, hw, k)
+            if ip:
+                xn_ref = torch.nn.functional.normalize(xv.cpu(), p=2, dim=-1)
+                en_ref = torch.nn.functional.normalize(e, p=2, dim=-1)
+                sim = torch.einsum("n d, e d -> n e", xn_ref.contiguous().view(-1, c), en_ref).view(b, hw, k)
+                ref = sim.argmax(-1)
+                bad = (ref != i_ex.cpu()).nonzero()
+                for bb, pp in bad.tolist():                      # MKL splits tiny problems along K: last-bit ties only
+                    a, r = sim[bb, pp, i_ex[bb, pp].item()], sim[bb, pp, ref[bb, pp]]
+                    assert (a - r).abs() <= 4 * torch.finfo(torch.float32).eps * r.abs().clamp_min(1e-30), (it, bb, pp)
+    assert all(v > 0 for v in ran.values()), ran
+
+
 def test_empty_batch(dev):
     """A batch of zero images: empty outputs, zero loss, every code unused (usage 100 %), no kernel fault."""
     import vq_seg_b200 as V
