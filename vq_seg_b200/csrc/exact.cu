@@ -242,7 +242,10 @@ int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st) {
     VQSEG_LAUNCH_CHECK();
     return 0;
   }
-  // rescoring pass: rows of (x + staged candidates) per warp pair; as many warps per block as ~96 KB allow
+  // rescoring pass: rows of (x + staged candidates) per warp pair; as many warps per block as ~96 KB allow.
+  // (Tried: staging two candidates per round beyond D = 256 to double the resident warps -- 16 per SM instead of 8 at
+  // D = 512: slower, 290 against 250 us per million config-4 rows; rows with three or more candidates pay a second
+  // round of dependent loads.)
   const size_t es_bytes = xs_bytes + 16;
   int stage_cap = kRsStage;
   while (stage_cap > 1 && 2 * (xs_bytes + stage_cap * es_bytes) > 200 * 1024) --stage_cap;
