@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kExactWarps * 32) rescore_kernel(ExactArgs a, 
 // one feeds the chains), so each lane runs its code's chain -- the same terms in the same order and the same K-blocking
 // as chain_dist2 -- from conflict-free shared memory.
 constexpr int kOvfWarps = 8;
-__global__ void __launch_bounds__(kOvfWarps * 32) overflow_rows_kernel(ExactArgs a) {
+__global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactArgs a) {
   extern __shared__ __align__(16) float smem_x[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int D = (int)a.x.D, K = a.K;
