@@ -34,7 +34,10 @@ extern "C" int vqseg_internal_gather_ticket(const float* x, int64_t B, int64_t P
 //       rebuilds it for the other metric otherwise.
 __global__ void __launch_bounds__(256) assign_prologue_kernel(unsigned long long* counts, int n_counts, float* loss, int* work4,
                                                               const float* __restrict__ E, int K, int D, unsigned char* blob,
-                                                              int ip) {
+                                                              int ip, float4* zero16 = nullptr, long long n_zero16 = 0) {
+  // (d) split-D mode of the streaming filter: its partial-score scratch starts from zero
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_zero16; i += (long long)gridDim.x * blockDim.x)
+    zero16[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (blockIdx.x == 0) {
     for (int k = threadIdx.x; k < n_counts; k += blockDim.x) counts[k] = 0ull;
     if (threadIdx.x == 0) { if (loss) *loss = 0.f; work4[0] = 0; work4[1] = 0; work4[2] = 0; work4[3] = 0; }
@@ -169,12 +172,22 @@ static int codebook_prepare(const float* E, int64_t K, int64_t D, void* blob, si
   return launch_pack(E, (int)K, (int)D, b, st);
 }
 
+// split-D mode (few rows, many dims) sums partial scores in an [n_rows][K_pad] fp32 scratch (+ 2 floats per row):
+// only problems whose scratch stays below 32 MB are eligible
+static size_t splitd_scratch_bytes(long long n_rows, long long K) {
+  const long long kp = round_up(K, 256);
+  const long long bytes = n_rows * kp * 4;
+  if (n_rows <= 0 || bytes > (32ll << 20)) return 0;
+  return (size_t)round_up(bytes, 256) + (size_t)round_up(n_rows * 8, 256);
+}
+
 size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int algo) {
   (void)D; (void)algo;
   size_t b = 256;                                                     // work counter + tickets
   b += (size_t)round_up(n_rows * (long long)sizeof(WorkRec), 256);    // one record per undecided row (worst case: all)
   b += (size_t)round_up(n_rows * (long long)sizeof(int), 256);        // rows whose short-list overflowed (worst case: all)
   b += (size_t)round_up(round_up(K, 256) * sizeof(float), 256);       // enorm when no blob is given
+  b += splitd_scratch_bytes(n_rows, K);                               // split-D mode: partial scores + row norms
   return b;
 }
 
@@ -201,7 +214,9 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   int* work_count = (int*)p;   p += 256;                       // [0] undecided rows, [1] overflow rows, [2] gather ticket, [3] spare
   WorkRec* work = (WorkRec*)p; p += round_up(n_rows * (long long)sizeof(WorkRec), 256);
   int* ovf_rows = (int*)p;     p += round_up(n_rows * (long long)sizeof(int), 256);
-  float* enorm_ws = (float*)p;
+  float* enorm_ws = (float*)p; p += round_up(round_up(K, 256) * sizeof(float), 256);
+  float* part_scores = splitd_scratch_bytes(n_rows, K) ? (float*)p : nullptr;
+  float* part_norms = part_scores ? (float*)(p + round_up(n_rows * round_up(K, 256) * 4, 256)) : nullptr;
 
   bool use_tc = false;
   if (algo == VQSEG_ALGO_AUTO) use_tc = blob != nullptr && n_rows >= 64 && K >= 32;
@@ -209,20 +224,57 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   else if (algo >= VQSEG_ALGO_TC && algo <= VQSEG_ALGO_TC_STREAM_PAIR) { if (!blob) return VQSEG_EINVAL; use_tc = true; }
   else return VQSEG_EINVAL;
 
+  Rows xr{x, B, P, D, sB, sP, sD};
+  long long kp = 0, dp = 0;
+  size_t oe = 0, oi = 0, tot = 0, oa = 0;
+  int n_cc = 0, n_dc = 0, kernel = 0, lay4 = 0, slice_dc = 0, n_slices = 1;
+  const bool force = (best_key_out != nullptr || idx_out == nullptr);
+  if (use_tc) {
+    blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot, &oa);
+    n_cc = (int)(kp / 256); n_dc = (int)(dp / kDChunk);
+    const bool can3 = tc3_supported(xr, n_cc, n_dc), can2 = tc2_supported(n_cc, n_dc);
+    lay4 = tc4_layout(xr, kp, n_dc);
+    const int pairs = num_sms() / 2;
+    // codebook-resident kernels when the codebook fits two SMs; else the streaming pair kernel when its TMA layouts
+    // apply and there is at least one pair tile per SM pair to amortise the A conversion; else the single-CTA kernel
+    const long long ptiles4 = lay4 == 1 ? (B * ((P + 127) / 128) + 1) / 2 : ((n_rows + 127) / 128 + 1) / 2;
+    kernel = can3 ? 3 : (can2 ? 2 : ((lay4 && 4 * ptiles4 >= pairs) ? 4 : 1));
+    // ... unless the single-CTA kernel would leave most of the GPU idle (fewer pair tiles than a quarter of the SM
+    // pairs; or more than 512 dims, which the pair kernel cannot hold as one tile): then the pair kernel in split-D
+    // mode, when the score scratch is small.  Slices as LARGE as still give half the SM pairs an item: every slice
+    // adds N x K_pad float atomics (measured: ~1.9 us per million + ~12 us fixed).
+    if (kernel == 1 && part_scores && (algo == VQSEG_ALGO_AUTO || algo == VQSEG_ALGO_TC)) {
+      for (int sd_ = 8; sd_ >= 2; --sd_) {
+        if (n_dc % sd_ || n_dc / sd_ < 2) continue;
+        const int lay = tc4_layout(xr, kp, sd_);
+        if (!lay) break;
+        const long long tiles = lay == 1 ? B * ((P + 127) / 128) : (n_rows + 127) / 128;
+        if (2 * ((tiles + 1) / 2) * (n_dc / sd_) >= pairs || sd_ == 2) { slice_dc = sd_; n_slices = n_dc / sd_; lay4 = lay; kernel = 5; break; }
+      }
+    }
+    if (algo == VQSEG_ALGO_TC_STREAM) kernel = 1;
+    if (algo == VQSEG_ALGO_TC_STREAM_PAIR) { if (!lay4) return VQSEG_EUNSUPPORTED; kernel = 4; }
+    if (algo == VQSEG_ALGO_TC_PAIR) { if (!can2) return VQSEG_EUNSUPPORTED; kernel = 2; }
+    if (algo == VQSEG_ALGO_TC_TMA) { if (!can3) return VQSEG_EUNSUPPORTED; kernel = 3; }
+  }
+
   // prologue: zeroing + (when a prepared codebook is used) the guard that rebuilds a stale blob in place
   {
-    const int guard_blocks = use_tc ? (int)((K + 7) / 8 < 2 * num_sms() ? (K + 7) / 8 : 2 * num_sms()) : 1;
+    int guard_blocks = use_tc ? (int)((K + 7) / 8 < 2 * num_sms() ? (K + 7) / 8 : 2 * num_sms()) : 1;
+    long long n_zero16 = 0;
+    if (kernel == 5) {
+      n_zero16 = (long long)(splitd_scratch_bytes(n_rows, K) / 16);
+      guard_blocks = 2 * num_sms();
+    }
     assign_prologue_kernel<<<guard_blocks, 256, 0, st>>>(zero_counts ? (unsigned long long*)counts_out : nullptr,
                                                          zero_counts ? (int)K : 0, zero_loss, work_count, E, (int)K, (int)D,
-                                                         use_tc ? (unsigned char*)blob : nullptr, ip);
+                                                         use_tc ? (unsigned char*)blob : nullptr, ip,
+                                                         reinterpret_cast<float4*>(part_scores), n_zero16);
     VQSEG_LAUNCH_CHECK();
   }
 
   const float* enorm = nullptr;
-  long long kp = 0, dp = 0;
-  size_t oe = 0, oi = 0, tot = 0, oa = 0;
   if (use_tc) {
-    blob_geometry(K, D, &kp, &dp, &oe, &oi, &tot, &oa);
     enorm = (const float*)((const char*)blob + oe);
   } else {
     rc = launch_enorm(E, (int)K, (int)D, (int)K, enorm_ws, nullptr, nullptr, st);
@@ -230,7 +282,6 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     enorm = enorm_ws;
   }
 
-  Rows xr{x, B, P, D, sB, sP, sD};
   ExactArgs ea;
   memset(&ea, 0, sizeof(ea));
   ea.x = xr; ea.E = E; ea.K = (int)K; ea.enorm = enorm; ea.kblock = kblock; ea.ip = ip;
@@ -238,17 +289,6 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   ea.key_out = (unsigned long long*)best_key_out; ea.code_base = code_base;
   if (!use_tc) return launch_exact(ea, n_rows, st);
 
-  const int n_cc = (int)(kp / 256), n_dc = (int)(dp / kDChunk);
-  const bool force = (best_key_out != nullptr || idx_out == nullptr);
-  const bool can3 = tc3_supported(xr, n_cc, n_dc), can2 = tc2_supported(n_cc, n_dc);
-  const int lay4 = tc4_layout(xr, kp, n_dc);
-  // codebook-resident kernels when the codebook fits two SMs; else the streaming pair kernel when its TMA layouts
-  // apply and there is at least one pair tile per SM pair to amortise the A conversion; else the single-CTA kernel
-  int kernel = can3 ? 3 : (can2 ? 2 : ((lay4 && n_rows >= 256ll * (num_sms() / 2)) ? 4 : 1));
-  if (algo == VQSEG_ALGO_TC_STREAM) kernel = 1;
-  if (algo == VQSEG_ALGO_TC_STREAM_PAIR) { if (!lay4) return VQSEG_EUNSUPPORTED; kernel = 4; }
-  if (algo == VQSEG_ALGO_TC_PAIR) { if (!can2) return VQSEG_EUNSUPPORTED; kernel = 2; }
-  if (algo == VQSEG_ALGO_TC_TMA) { if (!can3) return VQSEG_EUNSUPPORTED; kernel = 3; }
   prof_record(prof_events, 0, st);
   if (kernel == 3) {
     Tc3Args t3;
@@ -263,19 +303,34 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     t3.work = work; t3.work_count = work_count;
     t3.trace = dev_trace();
     rc = launch_assign_tc3(xr, t3, st);
-  } else if (kernel == 4) {
+  } else if (kernel == 4 || kernel == 5) {
     Tc4Args t4;
     memset(&t4, 0, sizeof(t4));
     t4.B = B; t4.P = P; t4.D = D; t4.n_rows = n_rows; t4.blob = (const unsigned char*)blob;
     if (lay4 == 1) { t4.tiles_per_image = (int)((P + 127) / 128); t4.n_tiles = (int)(B * t4.tiles_per_image); }
     else { t4.tiles_per_image = 0; t4.n_tiles = (int)((n_rows + 127) / 128); }
     t4.n_ptiles = (t4.n_tiles + 1) / 2; t4.n_cc = n_cc; t4.n_dc = n_dc;
+    t4.n_slices = 1; t4.n_dc_total = n_dc;
+    if (kernel == 5) {                              // split-D mode: partial scores into the scratch, short-lists afterwards
+      t4.n_dc = slice_dc; t4.n_slices = n_slices;
+      t4.part_scores = part_scores; t4.part_norms = part_norms;
+    }
     t4.K = (int)K; t4.K_pad = (int)kp; t4.off_image = oi; t4.off_aug = oa; t4.off_enorm = oe;
     t4.idx_out = (long long*)idx_out; t4.counts_out = (unsigned long long*)counts_out; t4.code_base = code_base;
     t4.force_rescore = force ? 1 : 0;
     t4.work = work; t4.work_count = work_count;
     t4.trace = dev_trace();
     rc = launch_assign_tc4(xr, t4, lay4, st);
+    if (!rc && kernel == 5) {
+      ShortlistArgs sl;
+      memset(&sl, 0, sizeof(sl));
+      sl.scores = part_scores; sl.norms = part_norms; sl.n_rows = n_rows; sl.K = (int)K; sl.K_pad = (int)kp; sl.D = (int)D;
+      sl.blob = (const unsigned char*)blob;
+      sl.idx_out = (long long*)idx_out; sl.counts_out = (unsigned long long*)counts_out; sl.code_base = code_base;
+      sl.force_rescore = force ? 1 : 0;
+      sl.work = work; sl.work_count = work_count;
+      rc = launch_shortlist(sl, st);
+    }
   } else if (kernel == 2) {
     Tc2Args t2;
     memset(&t2, 0, sizeof(t2));

@@ -91,27 +91,34 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Tc4Smem::off_tmem);
   float2* xsq = reinterpret_cast<float2*>(smem + Tc4Smem::off_xsq);
 
+  // A work item is a pair tile (256 rows) x one slice of `a.n_dc` dim chunks.  Normally a slice is the whole row
+  // (n_slices == 1).  Split-D mode (few rows, many dims: the 1024- / 2048-channel layers of a model have 2-16 pair
+  // tiles for 74 SM pairs) cuts the dims into n_slices slices so that every SM pair has an item; an item then ADDS
+  // its partial scores into a[.part_scores] and shortlist_kernel builds the short-lists once all slices have landed.
   const int n_pairs = (int)gridDim.x >> 1;
   const int pair = (int)blockIdx.x >> 1;
-  const int my_tiles = a.n_ptiles > pair ? (a.n_ptiles - 1 - pair) / n_pairs + 1 : 0;
+  const int n_items = a.n_ptiles * a.n_slices;
+  const int my_tiles = n_items > pair ? (n_items - 1 - pair) / n_pairs + 1 : 0;
   const int boxes_per_tile = 2 * a.n_dc;
   const int total_boxes = my_tiles * boxes_per_tile;
   const int my_units = my_tiles * a.n_cc;
-  // tile tt of this CTA = global tile 2 * (pair + tt * n_pairs) + rank
-  auto tile_id = [&](int tt) { return 2 * (pair + tt * n_pairs) + (int)rank; };
+  // item tt of this pair = global item pair + tt * n_pairs = (pair tile, slice); this CTA's tile = 2 * pair tile + rank
+  auto tile_id = [&](int tt) { return 2 * ((pair + tt * n_pairs) / a.n_slices) + (int)rank; };
+  auto slice_of = [&](int tt) { return (pair + tt * n_pairs) % a.n_slices; };
   auto issue_box = [&](int q, int issuer) {                   // box q goes to the stage its issuer owns
     const int tt = q / boxes_per_tile, h = q - tt * boxes_per_tile;
     const int t = tile_id(tt);
+    const int dim0 = (slice_of(tt) * boxes_per_tile + h) * k4BoxDims;      // first dim of the box
     mbar_wait(bar_xempty + 8 * issuer, (((uint32_t)(q / k4XStages)) & 1) ^ 1);
     mbar_arrive_expect_tx(bar_xfull + 8 * issuer, k4XBytes);
     const uint32_t dst = sbase + Tc4Smem::off_x + issuer * k4XBytes;
     if (ROWS) {
       // tiles past the end start beyond the last row: the tensor map zero-fills
-      tma4_load_2d(dst, &tmap, h * k4BoxDims, t < a.n_tiles ? t * k4Rows : (int)a.n_rows, bar_xfull + 8 * issuer);
+      tma4_load_2d(dst, &tmap, dim0, t < a.n_tiles ? t * k4Rows : (int)a.n_rows, bar_xfull + 8 * issuer);
     } else {
       int img = (int)a.B, p0 = 0;
       if (t < a.n_tiles) { img = t / a.tiles_per_image; p0 = (t - img * a.tiles_per_image) * k4Rows; }
-      tma4_load_3d(dst, &tmap, p0, h * k4BoxDims, img, bar_xfull + 8 * issuer);
+      tma4_load_3d(dst, &tmap, p0, dim0, img, bar_xfull + 8 * issuer);
     }
   };
 
@@ -231,6 +238,40 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
         }
       }
       const bool in_range = n >= 0;
+      if (a.part_scores) {
+        // ---- split-D mode: add this item's partial scores (and its share of the row norms) to the scratch arrays
+        for (int cc = 0; cc < a.n_cc; ++cc, ++u) {
+          const int buf = u & 1;
+          mbar_wait(bar_tfull + 8 * buf, (uint32_t)(u >> 1) & 1);
+          tc_fence_after();
+          if (cc == 0) {
+            const float2 n0 = xsq[((tt & 1) * 2 + 0) * k4Rows + r], n1 = xsq[((tt & 1) * 2 + 1) * k4Rows + r];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_nempty + 8 * (tt & 1));
+            if (in_range && half == 0) {
+              atomicAdd(a.part_norms + 2 * n, n0.x + n1.x);
+              atomicAdd(a.part_norms + 2 * n + 1, n0.y + n1.y);
+            }
+          }
+          const uint32_t tb = lane_addr + buf * 256;
+          float* dst = a.part_scores + (in_range ? n : 0) * (long long)a.K_pad + cc * 256 + half * 128;
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tb + c, v);
+            if (in_range) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                atomicAdd(reinterpret_cast<float4*>(dst + c + j),
+                          make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
+        }
+        continue;
+      }
       float m_run = __int_as_float(0x7f800000);
       float slack = 0.f;
       int cnt = 0;
@@ -342,6 +383,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
       int u = 0;
       for (int tt = 0; tt < my_tiles; ++tt) {
         int slot = slot0; uint32_t apar = apar0;
+        const bool with_aug = slice_of(tt) == 0;                // |e|^2 enters once per row, with the first slice
         for (int cc = 0; cc < n_cc; ++cc, ++u) {
           const int buf = u & 1;
           const uint32_t acc = tmem_base + buf * 256;
@@ -363,7 +405,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
             if (dc == n_dc - 1) {
               // the limb tile of this unit travelled with its first codebook stage (same barrier)
               const uint64_t baug = make_desc_noswz(sbase + Tc4Smem::off_baug + buf * k4AugBytes, 128, 256);
-              tc_mma_f16_2cta(acc, aaug, baug, k4Idesc, 1u);                 // + s |e_k|^2
+              if (with_aug) tc_mma_f16_2cta(acc, aaug, baug, k4Idesc, 1u);   // + s |e_k|^2
               tc_commit_2cta(bar_gempty + 8 * buf);
               tc_commit_2cta(bar_tfull + 8 * buf);
             }
@@ -393,6 +435,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
       for (int u = 0; u < my_units; ++u) {
         const int cc = u % a.n_cc, buf = u & 1;
         const int cb = 2 * cc + (int)rank;                       // this CTA's 128 codes of chunk cc
+        const int dc0 = slice_of(u / a.n_cc) * a.n_dc;           // first dim chunk of the item's slice
         for (int dc = 0; dc < a.n_dc; ++dc, ++bq) {
           const int bs = bq % k4BStages;
           mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(bq / k4BStages)) & 1) ^ 1);
@@ -403,7 +446,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
           } else {
             mbar_arrive_expect_tx(bar_bfull + 8 * bs, kTileBytes);
           }
-          bulk_g2s(sbase + Tc4Smem::off_b + bs * kTileBytes, img + ((long long)cb * a.n_dc + dc) * kTileBytes, kTileBytes,
+          bulk_g2s(sbase + Tc4Smem::off_b + bs * kTileBytes, img + ((long long)cb * a.n_dc_total + dc0 + dc) * kTileBytes, kTileBytes,
                    bar_bfull + 8 * bs);
         }
       }
@@ -434,6 +477,77 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
   }
 }
 
+// ---- split-D mode, second step: the short-list of every row over its summed scores ------------------------------------
+// One warp per row: the row minimum, the same error bound as the filters' epilogues (from the summed |x|^2 and
+// |fp16(x) - x|^2 and the blob's header), the codes within the bound in ascending order.  One survivor: final index;
+// otherwise a work record for the rescoring pass (more than kWorkCandCap survivors: "score every code").
+__global__ void __launch_bounds__(256) shortlist_kernel(ShortlistArgs a) {
+  const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(a.blob);
+  const int lane = threadIdx.x & 31;
+  const float scale = hdr->scale;
+  const float emax = sqrtf(hdr->max_enorm) * 1.0001f;
+  const float de_max = sqrtf(__uint_as_float(hdr->max_de2_bits)) * 1.0001f;
+  const bool bad_blob = (hdr->flags & 1u) != 0;
+  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long n = w0; n < a.n_rows; n += nw) {
+    const float xn = sqrtf(a.norms[2 * n]) * 1.0001f, dn = sqrtf(a.norms[2 * n + 1]) * 1.0001f;
+    const float e_s = emax * scale, sum = xn + emax;
+    const float slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.D + 8) * 2.4e-7f * sum * sum
+                      + 1.0e-6f * e_s * emax;                                 // (see assign_tc4_kernel's epilogue)
+    bool overflow = !(slack < 3.0e38f) || bad_blob;
+    const float* sc = a.scores + n * (long long)a.K_pad;
+    float m = __int_as_float(0x7f800000);
+    for (int k = 4 * lane; k < a.K_pad; k += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(sc + k);
+      m = fminf(m, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+    }
+    m = warp_min_f(m);
+    const float thr = m + slack;
+    int cnt = 0, mine = -1;                                 // lane l keeps the l-th survivor (l < kWorkCandCap)
+    for (int k0 = 0; k0 < a.K_pad && !overflow; k0 += 32) {
+      const int k = k0 + lane;
+      const bool hit = k < a.K && !(thr - sc[k] < 0.f);     // the epilogues' sign-bit test: a NaN score is a survivor
+      const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+      int pos = cnt + __popc(hm & ((1u << lane) - 1));
+      // survivor number `pos` goes to lane `pos`
+#pragma unroll 1
+      for (uint32_t rest = hm; rest;) {
+        const int src = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int p = __shfl_sync(0xffffffffu, pos, src);
+        if (lane == p) mine = k0 + src;
+      }
+      cnt += __popc(hm);
+      if (cnt > kWorkCandCap) overflow = true;
+    }
+    const int first = __shfl_sync(0xffffffffu, mine, 0);
+    const bool unique = !overflow && cnt == 1 && !a.force_rescore;
+    if (unique) {
+      if (lane == 0) {
+        a.idx_out[n] = (long long)first + a.code_base;
+        if (a.counts_out) atomicAdd(a.counts_out + first, 1ull);
+      }
+    } else {
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(a.work_count, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      int* rec = reinterpret_cast<int*>(a.work + slot);
+      const int nc = (overflow || cnt == 0) ? kWorkCandCap + 1 : cnt;
+      if (lane == 0) { rec[0] = (int)n; rec[1] = nc; }
+      if (lane < kWorkCandCap && lane < cnt && !overflow) rec[4 + lane] = mine;
+    }
+  }
+}
+
+int launch_shortlist(const ShortlistArgs& a, cudaStream_t st) {
+  long long blocks = (a.n_rows * 32 + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  shortlist_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -453,7 +567,7 @@ static EncodeTiledFn4 encode_tiled_fn4() {
 }
 
 // 0: not supported; 1: NCHW maps (pixel-contiguous); 2: packed rows (dim-contiguous, one flat row range)
-int tc4_layout(const Rows& x, long long K_pad, int n_dc) {
+int tc4_layout(const Rows& x, long long K_pad, int n_dc) {      // n_dc: dim chunks per work item (a slice in split-D mode)
   if (n_dc > k4ASlots || n_dc < 1) return 0;
   if (K_pad > 65536) return 0;                                  // short-list entries are 16-bit code ids
   if ((reinterpret_cast<uintptr_t>(x.ptr) & 15) != 0) return 0;
@@ -466,7 +580,7 @@ int tc4_layout(const Rows& x, long long K_pad, int n_dc) {
 
 int launch_assign_tc4(const Rows& x, const Tc4Args& a, int layout, cudaStream_t st) {
   int pairs = num_sms() / 2;
-  if (a.n_ptiles < pairs) pairs = a.n_ptiles;
+  if (a.n_ptiles * a.n_slices < pairs) pairs = a.n_ptiles * a.n_slices;
   if (pairs <= 0) return 0;
   EncodeTiledFn4 enc = encode_tiled_fn4();
   if (!enc) return VQSEG_EUNSUPPORTED;

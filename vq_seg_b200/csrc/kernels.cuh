@@ -85,7 +85,10 @@ struct Tc4Args {
   long long n_rows;
   const unsigned char* blob;
   int n_tiles, tiles_per_image;   // tiles of 128 rows (NCHW: 128 pixels of one image)
-  int n_ptiles, n_cc, n_dc;       // pair tiles (two tiles), code chunks of 256, dim chunks of 64
+  int n_ptiles, n_cc, n_dc;       // pair tiles (two tiles), code chunks of 256, dim chunks of 64 PER WORK ITEM
+  int n_slices, n_dc_total;       // split-D mode: dim slices per row (1 = off), dim chunks of the whole row
+  float* part_scores;             // split-D mode: [n_rows][K_pad] partial scores, zeroed by the prologue (else null)
+  float* part_norms;              //               [n_rows][2] {|x|^2, |fp16(x) - x|^2}
   int K, K_pad;
   unsigned long long off_image, off_aug, off_enorm;
   long long* idx_out; unsigned long long* counts_out; long long code_base;
@@ -93,6 +96,14 @@ struct Tc4Args {
   WorkRec* work; int* work_count;
   long long* trace;
 };
+// split-D mode's second step: per row the short-list over the summed scores (same rule as the filters' epilogues)
+struct ShortlistArgs {
+  const float* scores; const float* norms; long long n_rows; int K, K_pad, D;
+  const unsigned char* blob;
+  long long* idx_out; unsigned long long* counts_out; long long code_base; int force_rescore;
+  WorkRec* work; int* work_count;
+};
+int launch_shortlist(const ShortlistArgs& a, cudaStream_t st);
 int tc4_layout(const Rows& x, long long K_pad, int n_dc);   // 0: unsupported, 1: NCHW maps, 2: packed rows
 int launch_assign_tc4(const Rows& x, const Tc4Args& a, int layout, cudaStream_t st);
 
