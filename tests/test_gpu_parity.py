@@ -113,6 +113,45 @@ def test_short_list_overflow_rows(dev, shape, metric):
     assert torch.equal(c_ex, c_tc)
 
 
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+@pytest.mark.parametrize("shape,layout", [((2, 1024, 32, 32, 512), "nchw"), ((2, 2048, 16, 16, 512), "nchw"),
+                                          ((4, 1024, 32, 32, 512), "nchw"), ((1, 768, 20, 24, 700), "nchw"),
+                                          ((1, 1536, 1, 1000, 300), "rows"), ((3, 640, 10, 12, 1024), "nchw")])
+def test_split_d_mode_equals_exact(dev, shape, layout, metric):
+    """Few rows, many dims (the model's 1024- / 2048-channel layers): the streaming pair kernel runs in split-D mode
+    (partial scores summed by atomics in a scratch, short-lists built from the sums).  Indices, counts and the packed
+    (distance, index) keys of the sharded mode must equal the exact scorer's, run after run."""
+    from vq_seg_b200 import ops, _native
+    b, c, h, w, k = shape
+    g = torch.Generator(device="cuda").manual_seed(c + k)
+    x = torch.relu(torch.randn(b, c, h * w, generator=g, device=dev))
+    xv = x.permute(0, 2, 1)
+    if layout == "rows":
+        xv = xv.contiguous()
+    e = (xv.reshape(-1, c)[torch.randint(0, b * h * w, (k,), generator=g, device=dev)] +
+         0.2 * torch.randn(k, c, generator=g, device=dev)).contiguous()
+    ip = metric == "cosine"
+    if ip:
+        xv = ops.l2norm_rows(xv)
+        ops.l2norm_rows_(e)
+    flag = ops.METRIC_IP if ip else 0
+    blob = ops.prepare_codebook(e, ip)
+    i_ex, c_ex = ops.assign(xv, e, None, ops.ALGO_EXACT | flag)
+    for _ in range(3):
+        i_tc, c_tc = ops.assign(xv, e, blob, ops.ALGO_AUTO | flag)
+        assert torch.equal(i_ex, i_tc) and torch.equal(c_ex, c_tc)
+    # the score scratch (last part of the workspace) was used: this really was the split-D path
+    n, kp = b * h * w, (k + 255) // 256 * 256
+    scratch = (n * kp * 4 + 255) // 256 * 256 + (n * 8 + 255) // 256 * 256
+    ws = ops._last_assign_ws
+    assert ws.numel() == _native.lib().vqseg_assign_workspace_bytes(n, c, k, 0)
+    assert ws[ws.numel() - scratch:].view(torch.float32)[: n * kp].abs().sum().item() > 0
+    if not ip:                                         # sharded mode: exact distances for every row
+        keys_ex = ops.assign_keys(xv, e, None, 1000, ops.ALGO_EXACT)
+        keys_tc = ops.assign_keys(xv, e, blob, 1000, ops.ALGO_AUTO)
+        assert torch.equal(keys_ex, keys_tc)
+
+
 def test_kblock_override_changes_only_near_ties(dev):
     """kblock is the fp32 chain split of the exact scorer; a different split may only move rows
     whose two best reference distances are within 2 ulp."""
