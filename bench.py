@@ -488,6 +488,8 @@ def main():
         t = torch.tensor(e2e_passes, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_passes = t.tolist()
+    sampler.stop_flag = True          # clocks sampled from the first timed step to the end of the e2e passes (same workload)
+    sampler.join(timeout=2)
     e2e_s = statistics.median(e2e_passes)
     e2e_val = N_VEC * world * e2e_steps / e2e_s
     e2e_best = N_VEC * world * e2e_steps / min(e2e_passes)
