@@ -380,8 +380,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.ring):          # every ring slot once before anything is timed: with the module's CUDA graphs
-        step(i)                         # this is where each slot's forward gets captured
+    for i in range(25 * args.ring):     # every ring slot before anything is timed: with the module's CUDA graphs this is
+        step(i)                         # where each slot's forward gets captured; 25 rounds (~10 ms) let clocks and caches settle
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -562,7 +562,8 @@ def main():
                 "vs_baseline": None, "dtype": "f32 (fp16 tensor-core filter, exact fp32 rescoring)", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_vectors": N_VEC, "l2": f"ring of {args.ring} input batches "
                            f"({args.ring * N_VEC * C * 4 / 2**20:.0f} MiB) cycled, larger than L2",
-                           "codebook_prepared": "once (weights static)", "parallelism": f"dp{world} over latent pixels",
+                           "codebook_prepared": "once (weights static)",
+                           "settle": f"{25 * args.ring} untimed calls (graph capture of every ring slot, clock ramp) before the warm-up steps", "parallelism": f"dp{world} over latent pixels",
                            "launch": ("model(x), kernels enqueued from Python" if args.no_graph else
                                       "model(x) with VectorQuantizer.enable_cuda_graphs(): one graph replay per call"),
                            "collectives_in_timed_region": 0, "global_code_usage_pct": global_usage},
