@@ -57,6 +57,30 @@ def _prepare_codebook_impl(codebook: torch.Tensor, ip: bool = False) -> torch.Te
 prepare_codebook = torch.library.custom_op("vqseg::prepare_codebook", mutates_args=())(_prepare_codebook_impl)
 
 
+def _refresh_codebook_impl(blob: torch.Tensor, codebook: torch.Tensor, ip: bool = False) -> None:
+    """Rebuild an existing blob (same K, D) from the current weights with the multi-block preparation kernels.  For
+    callers that KNOW the weights just changed (the cosine codebook renormalises them every forward): the assignment's
+    own guard would notice too, but rebuilds inside one block."""
+    _require_cuda(blob, codebook)
+    L = _native.lib()
+    cb = codebook.detach().contiguous().float()
+    k, d = cb.shape
+    n = L.vqseg_codebook_blob_bytes(k, d)
+    if blob.numel() < n:
+        raise RuntimeError("refresh_codebook: the blob was prepared for another codebook shape")
+    with torch.cuda.device(cb.device):
+        fn = L.vqseg_codebook_prepare_ip_f32 if ip else L.vqseg_codebook_prepare_f32
+        _native.check(fn(cb.data_ptr(), k, d, blob.data_ptr(), n, _stream()), "codebook_prepare")
+
+
+refresh_codebook = torch.library.custom_op("vqseg::refresh_codebook", mutates_args=("blob",))(_refresh_codebook_impl)
+
+
+@refresh_codebook.register_fake
+def _(blob, codebook, ip=False):
+    return None
+
+
 @prepare_codebook.register_fake
 def _(codebook, ip=False):
     k, d = codebook.shape
@@ -756,6 +780,10 @@ def fast_assign(x, codebook, blob, algo=ALGO_AUTO, kblock=0):
 
 def fast_code_usage(counts):
     return (_code_usage_impl if _fast() else code_usage)(counts)
+
+
+def fast_refresh_codebook(blob, codebook, ip=False):
+    return (_refresh_codebook_impl if _fast() else refresh_codebook)(blob, codebook, ip)
 
 
 def fast_prepare_codebook(codebook, ip=False):
