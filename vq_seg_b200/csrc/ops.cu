@@ -653,15 +653,29 @@ __global__ void __launch_bounds__(256) l2norm_px_kernel(Rows x, RowsOut out) {
       __syncthreads();
       for (int j = wib; j < dn; j += 8) tile[j * 32 + lane] = on ? __ldg(xp + (long long)(d0 + j) * x.sD) : 0.f;
       __syncthreads();
-      if (wib == 0)
-        for (int j = 0; j < dn; ++j) { const float v = tile[j * 32 + lane]; acc = __fadd_rn(acc, __fmul_rn(v, v)); }
+      if (wib == 0) {
+        int j = 0;
+        for (; j + 8 <= dn; j += 8) {                 // loads and squares of 8 terms ahead of the dependent adds
+          float q[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const float v = tile[(j + u) * 32 + lane]; q[u] = __fmul_rn(v, v); }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, q[u]);
+        }
+        for (; j < dn; ++j) { const float v = tile[j * 32 + lane]; acc = __fadd_rn(acc, __fmul_rn(v, v)); }
+      }
     }
     if (wib == 0) s_nrm[lane] = fmaxf(__fsqrt_rn(acc), 1e-12f);
     __syncthreads();
     const float nrm = s_nrm[lane];
     float* op = out.ptr + b * out.sB + (on ? p : 0) * out.sP;
-    if (on)
-      for (int d = wib; d < D; d += 8) op[(long long)d * out.sD] = __fdiv_rn(__ldg(xp + (long long)d * x.sD), nrm);
+    if (on) {
+      if (D <= 256) {                                  // the whole row is still in the tile
+        for (int d = wib; d < D; d += 8) op[(long long)d * out.sD] = __fdiv_rn(tile[d * 32 + lane], nrm);
+      } else {
+        for (int d = wib; d < D; d += 8) op[(long long)d * out.sD] = __fdiv_rn(__ldg(xp + (long long)d * x.sD), nrm);
+      }
+    }
   }
 }
 
@@ -1096,6 +1110,11 @@ int vqseg_l2norm_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
     RowsOut orow{out, B, P, D, oB, oP, oD};
     if (sP == 1) {
       const long long groups = B * ((P + 31) / 32), cap = (long long)num_sms() * 16;
+      static bool carved[kMaxDevices] = {false};        // 32 KB of static shared memory per block: ask for the large carve-out
+      if (!carved[current_device()]) {
+        cudaFuncSetAttribute(l2norm_px_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carved[current_device()] = true;
+      }
       l2norm_px_kernel<<<(unsigned)(groups < cap ? groups : cap), 256, 0, st>>>(xr, orow);
     } else {
       l2norm_strided_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(xr, orow);
