@@ -157,6 +157,9 @@ def _cos_dup_case():
     return x, e.contiguous()
 
 
+L2NORM_LASTDIM_DIMS = [1, 3, 4, 7, 8, 9, 12, 13, 15, 16, 23, 31, 64, 100, 103, 255, 511, 1000]
+L2NORM_VIEW_SHAPES = [(1, 5, 7), (2, 33, 45), (3, 100, 131), (2, 300, 64), (1, 17, 1000)]
+
 COSINE2_CASES = {"cos2_small": (lambda: _randn_case(73, 2, 64, 16, 16, 48)),
                  "cos2_relu": (lambda: _relu_case(74, 2, 256, 32, 32, 512)),
                  "cos2_dup": _cos_dup_case,

@@ -49,6 +49,18 @@ def main():
         print(f"{name:12s} usage={usage.item():.3f} loss_train={rec['loss_train'].item():.6f} "
               f"train==eval idx: {bool(torch.equal(rec['idx_train'], rec['idx_eval']))}")
     out["cosine2"] = cos
+    # F.normalize itself, where ATen's summation order shows: contiguous rows of every tail length D % 8 (the
+    # vectorised last-dim reduction: 8 lanes, then 4 unfused + <= 3 fused tail terms) and strided (B, HW, C) views with
+    # pixel counts that are not multiples of 32 (one sequential chain per pixel)
+    norm = {}
+    g = torch.Generator().manual_seed(4242)
+    for d in cases.L2NORM_LASTDIM_DIMS:
+        e = torch.randn(200, d, generator=g)
+        norm[f"rows_d{d}"] = {"in_sha": cases.sha(e), "out_sha": cases.sha(R.l2norm(e))}
+    for (b, c, p) in cases.L2NORM_VIEW_SHAPES:
+        x = torch.randn(b, c, p, generator=g)
+        norm[f"view_{b}x{c}x{p}"] = {"in_sha": cases.sha(x), "out_sha": cases.sha(R.l2norm(x.permute(0, 2, 1)))}
+    out["l2norm"] = norm
     path = os.path.join(HERE, "golden_cosine_v2.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes")

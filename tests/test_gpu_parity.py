@@ -302,6 +302,30 @@ def golden_cosine():
                       weights_only=False)["cosine2"]
 
 
+def test_l2norm_matches_aten_summation_orders(dev):
+    """vqseg_l2norm_f32 against F.normalize on the reference's CPU (SHA-256 goldens, make_golden_cosine.py): contiguous
+    rows of every tail length D % 8, in place and out of place, and strided (B, HW, C) views with ragged pixel counts."""
+    from vq_seg_b200 import ops
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cosine_v2.pt"),
+                      weights_only=False)["l2norm"]
+    g = torch.Generator().manual_seed(4242)
+    for d in cases.L2NORM_LASTDIM_DIMS:
+        e = torch.randn(200, d, generator=g)
+        rec = gold[f"rows_d{d}"]
+        assert cases.sha(e) == rec["in_sha"]
+        out = ops.l2norm_rows(e.to(dev).unsqueeze(0))[0]
+        assert cases.sha(out) == rec["out_sha"], f"D = {d}: contiguous rows"
+        w = e.to(dev).clone()
+        ops.l2norm_rows_(w)
+        assert cases.sha(w) == rec["out_sha"], f"D = {d}: in place"
+    for (b, c, p) in cases.L2NORM_VIEW_SHAPES:
+        x = torch.randn(b, c, p, generator=g)
+        rec = gold[f"view_{b}x{c}x{p}"]
+        assert cases.sha(x) == rec["in_sha"]
+        out = ops.l2norm_rows(x.to(dev).permute(0, 2, 1))
+        assert cases.sha(out) == rec["out_sha"], f"view {(b, c, p)}"
+
+
 @pytest.mark.parametrize("name", list(cases.COSINE2_CASES))
 def test_cosine_codebook_bit_exact_train_and_eval(dev, golden_cosine, name):
     """The cosine codebook against the live reference's outputs (tests/golden/make_golden_cosine.py): l2norm of the
