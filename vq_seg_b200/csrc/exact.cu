@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
 // ---- rescoring pass over the filter's work records (body: exact_chain.cuh, shared with the fused tail of assign_tc3)
 __global__ void __launch_bounds__(kExactWarps * 32) rescore_kernel(ExactArgs a, int stage_cap, long long rec_cap) {
   extern __shared__ __align__(16) float smem_x[];
+  pdl_trigger();                                  // the overflow kernel behind may become resident (it waits for us)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int hw = lane >> 4, hl = lane & 15;
   const int D = (int)a.x.D;
@@ -136,6 +137,8 @@ __global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactA
   __shared__ float s_best[kOvfWarps];
   __shared__ int s_bestk[kOvfWarps];
   __shared__ float s_xnorm;
+  pdl_trigger();                                  // the gather behind may become resident ...
+  pdl_wait();                                     // ... and we need the rescoring pass's overflow list
   const int n_ovf = *reinterpret_cast<volatile const int*>(a.ovf_count);
   const int L = ip ? D : D + 2;
   int kb = a.kblock;
@@ -267,7 +270,8 @@ int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st) {
     static size_t oconf[kMaxDevices] = {0};
     if (int rc = ensure_dynamic_smem(overflow_rows_kernel, osmem, oconf)) return rc;
     long long ob = max_work < 2ll * num_sms() ? max_work : 2ll * num_sms();
-    overflow_rows_kernel<<<(unsigned)ob, kOvfWarps * 32, osmem, st>>>(a);
+    cudaError_t le = launch_dependent(overflow_rows_kernel, dim3((unsigned)ob), dim3(kOvfWarps * 32), osmem, st, pdl_enabled(), a);
+    if (le != cudaSuccess) return (int)le;
     VQSEG_LAUNCH_CHECK();
   }
   return 0;

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) gather_ste_pxc_kernel(Rows x, const float
   __shared__ float tile[kGTile][kGPix + 1];
   __shared__ int s_idx[kGPix];
   __shared__ float s_red[8];
+  pdl_wait();                                     // (launched as a programmatic dependent of the assignment's last kernel)
   const int D = (int)x.D;
   const long long n_rows = x.n_rows();
   const long long n0 = (long long)blockIdx.x * kGPix;
@@ -260,8 +261,10 @@ static int launch_gather(const Rows& x, const float* E, int K, const long long* 
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool vec = (x.P % 4 == 0) && al(q.ptr) && (q.sD % 4 == 0) && (q.sB % 4 == 0) &&
                      (!train || (al(x.ptr) && (x.sD % 4 == 0) && (x.sB % 4 == 0)));
-    if (vec) gather_ste_pxc_kernel<MODE, true><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr, tail);
-    else     gather_ste_pxc_kernel<MODE, false><<<grid, 256, 0, st>>>(x, E, K, idx, q, want_loss ? partial : nullptr, tail);
+    cudaError_t le;
+    if (vec) le = launch_dependent(gather_ste_pxc_kernel<MODE, true>, grid, dim3(256), 0, st, pdl_enabled(), x, E, K, idx, q, want_loss ? partial : nullptr, tail);
+    else     le = launch_dependent(gather_ste_pxc_kernel<MODE, false>, grid, dim3(256), 0, st, pdl_enabled(), x, E, K, idx, q, want_loss ? partial : nullptr, tail);
+    if (le != cudaSuccess) return (int)le;
   } else {
     long long blocks = (n_rows + 7) / 8;
     long long cap = (long long)num_sms() * 16;
