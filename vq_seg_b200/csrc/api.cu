@@ -35,6 +35,7 @@ extern "C" int vqseg_internal_gather_ticket(const float* x, int64_t B, int64_t P
 __global__ void __launch_bounds__(256) assign_prologue_kernel(unsigned long long* counts, int n_counts, float* loss, int* work4,
                                                               const float* __restrict__ E, int K, int D, unsigned char* blob,
                                                               int ip, float4* zero16 = nullptr, long long n_zero16 = 0) {
+  pdl_trigger();     // the filter behind may become resident: it sets up and requests x while this kernel runs
   // (d) split-D mode of the streaming filter: its partial-score scratch starts from zero
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_zero16; i += (long long)gridDim.x * blockDim.x)
     zero16[i] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -144,6 +144,12 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // launched as a programmatic dependent of the prologue kernel (zeroing + codebook guard): everything above -- and the
+  // x boxes the loader warps already have in flight -- overlapped it; what reads the blob or accumulates into the
+  // outputs waits here (warps 18-19 only ever load x)
+  if (warp < 18) pdl_wait();
+  // (tried: pdl_trigger() here + the rescoring kernel as a programmatic dependent, so that its blocks take the SMs of
+  // pairs that finish early: 47.8-49.0 -> 50.8-51.8 us per step -- not kept)
   stamp(1);
 
   const uint32_t lead_afull = mapa_u32(bar_afull, 0);
@@ -475,7 +481,8 @@ int launch_assign_tc3(const Rows& x, const Tc3Args& a, cudaStream_t st) {
   if (rc != CUDA_SUCCESS) return VQSEG_EUNSUPPORTED;
   static size_t configured[kMaxDevices] = {0};
   if (int e = ensure_dynamic_smem(assign_tc3_kernel, Tc3Smem::total, configured)) return e;
-  assign_tc3_kernel<<<2 * pairs, k3Threads, Tc3Smem::total, st>>>(tmap, a);
+  cudaError_t le = launch_dependent(assign_tc3_kernel, dim3(2 * pairs), dim3(k3Threads), (size_t)Tc3Smem::total, st, pdl_enabled(), tmap, a);
+  if (le != cudaSuccess) return (int)le;
   VQSEG_LAUNCH_CHECK();
   return 0;
 }
