@@ -153,8 +153,12 @@ def extras_c1(dev):
         with torch.no_grad():
             m.eval()
             us_eval = _ev_time(lambda: m(x), 30, 5) * 1e3
+            m.enable_cuda_graphs()                 # the same call replayed as one CUDA graph: GPU time, not host time
+            xd = x.detach()
+            us_graph = _ev_time(lambda: m(xd), 50, 5) * 1e3
         n = b * h * w
-        out[name] = {"shape": [b, c, h, w], "train_fwd_bwd_us": us, "eval_fwd_us": us_eval, "train_vectors_per_s": n / (us * 1e-6)}
+        out[name] = {"shape": [b, c, h, w], "train_fwd_bwd_us": us, "eval_fwd_us": us_eval, "eval_fwd_cuda_graph_us": us_graph,
+                     "train_vectors_per_s": n / (us * 1e-6)}
     return out
 
 

@@ -147,6 +147,9 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // a programmatic dependent of the prologue kernel (zeroing, codebook guard, split-D scratch): the set-up above and
+  // the x boxes already in flight overlapped it; the warps that read the blob or write outputs wait here
+  if (warp >= 8 && warp < 19) pdl_wait();
   const uint32_t lead_afull = mapa_u32(bar_afull, 0);
   const uint32_t lead_tempty = mapa_u32(bar_tempty, 0);
   const uint32_t lead_bready = mapa_u32(bar_bready, 0);
@@ -608,11 +611,13 @@ int launch_assign_tc4(const Rows& x, const Tc4Args& a, int layout, cudaStream_t 
   if (layout == 1) {
     static size_t configured[kMaxDevices] = {0};
     if (int e = ensure_dynamic_smem(assign_tc4_kernel<false>, Tc4Smem::total, configured)) return e;
-    assign_tc4_kernel<false><<<2 * pairs, k4Threads, Tc4Smem::total, st>>>(tmap, a);
+    cudaError_t le = launch_dependent(assign_tc4_kernel<false>, dim3(2 * pairs), dim3(k4Threads), (size_t)Tc4Smem::total, st, pdl_enabled(), tmap, a);
+    if (le != cudaSuccess) return (int)le;
   } else {
     static size_t configured[kMaxDevices] = {0};
     if (int e = ensure_dynamic_smem(assign_tc4_kernel<true>, Tc4Smem::total, configured)) return e;
-    assign_tc4_kernel<true><<<2 * pairs, k4Threads, Tc4Smem::total, st>>>(tmap, a);
+    cudaError_t le = launch_dependent(assign_tc4_kernel<true>, dim3(2 * pairs), dim3(k4Threads), (size_t)Tc4Smem::total, st, pdl_enabled(), tmap, a);
+    if (le != cudaSuccess) return (int)le;
   }
   VQSEG_LAUNCH_CHECK();
   return 0;
