@@ -86,14 +86,31 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_kernel(Rows x, const floa
       for (int k = 0; k < KMAX; ++k)
         if (k < K) t[k] = __fmaf_rn(xv, s_e[k * D + d], t[k]);
     };
+    const bool v4 = (D & 3) == 0;              // prototype rows 16-byte aligned: one LDS.128 feeds four chain steps
     for (int i = 0; i < size_ilp; ++i) {
       float xv[32];
 #pragma unroll
       for (int u = 0; u < 32; ++u) xv[u] = __ldg(xr + (long long)(32 * i + u) * x.sD);
+      if (v4) {
 #pragma unroll
-      for (int u = 0; u < 32; ++u) {
-        if (!COSINE) sq.a[u] = __fadd_rn(sq.a[u], __fmul_rn(xv[u], xv[u]));
-        step(32 * i + u, xv[u]);
+        for (int u = 0; u < 32; u += 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (!COSINE) sq.a[u + j] = __fadd_rn(sq.a[u + j], __fmul_rn(xv[u + j], xv[u + j]));
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k < K) {                           // (the scalar broadcast loads made the kernel issue-bound: one LDS per FMA)
+              const float4 e4 = *reinterpret_cast<const float4*>(s_e + k * D + 32 * i + u);
+              t[k] = __fmaf_rn(xv[u], e4.x, t[k]); t[k] = __fmaf_rn(xv[u + 1], e4.y, t[k]);
+              t[k] = __fmaf_rn(xv[u + 2], e4.z, t[k]); t[k] = __fmaf_rn(xv[u + 3], e4.w, t[k]);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          if (!COSINE) sq.a[u] = __fadd_rn(sq.a[u], __fmul_rn(xv[u], xv[u]));
+          step(32 * i + u, xv[u]);
+        }
       }
     }
     for (int v = size_ilp * 4; v < vec_size; ++v) {
@@ -268,13 +285,40 @@ __global__ void __launch_bounds__(kDmThreads) dist_map_bwd_kernel(Rows x, const 
     for (int u = 0; u < 32; ++u) {
       if (cosine) xv[u] *= inv_nrm;                // the tile (and the prototype gradient) work on xn
       s_x[u * kDmXStride + threadIdx.x] = xv[u];
-      if (in && d0 + u < D) {
-        float acc = cosine ? 0.f : xv[u] * wsum;   // sum_k w_k (x - e_k) = x sum_k w_k - sum_k w_k e_k
+    }
+    if (in && (D & 3) == 0 && d0 + 32 <= D) {
+      // four dims per LDS.128 of a prototype row (same sums in the same order as the scalar loop below)
+#pragma unroll
+      for (int u = 0; u < 32; u += 4) {
+        float a4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a4[j] = cosine ? 0.f : xv[u + j] * wsum;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
-          if (k < K) acc = fmaf(cosine ? w[k] : -w[k], s_e[k * D + d0 + u], acc);
-        if (cosine) acc = (acc - xv[u] * dot) * inv_nrm;
-        gxr[(long long)(d0 + u) * gx.sD] = acc;
+          if (k < K) {
+            const float4 e4 = *reinterpret_cast<const float4*>(s_e + k * D + d0 + u);
+            const float wk = cosine ? w[k] : -w[k];
+            a4[0] = fmaf(wk, e4.x, a4[0]); a4[1] = fmaf(wk, e4.y, a4[1]);
+            a4[2] = fmaf(wk, e4.z, a4[2]); a4[3] = fmaf(wk, e4.w, a4[3]);
+          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float acc = a4[j];
+          if (cosine) acc = (acc - xv[u + j] * dot) * inv_nrm;
+          gxr[(long long)(d0 + u + j) * gx.sD] = acc;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        if (in && d0 + u < D) {
+          float acc = cosine ? 0.f : xv[u] * wsum;   // sum_k w_k (x - e_k) = x sum_k w_k - sum_k w_k e_k
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k < K) acc = fmaf(cosine ? w[k] : -w[k], s_e[k * D + d0 + u], acc);
+          if (cosine) acc = (acc - xv[u] * dot) * inv_nrm;
+          gxr[(long long)(d0 + u) * gx.sD] = acc;
+        }
       }
     }
     __syncthreads();
