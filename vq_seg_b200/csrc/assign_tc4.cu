@@ -208,10 +208,10 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
         xsq[((tt & 1) * 2 + chh) * k4Rows + r] = make_float2(ss, sd);
         ss = 0.f; sd = 0.f;
       }
-      fence_proxy_async();
+      if (hh == 1) fence_proxy_async();          // the chunk's A writes (both boxes) -> visible to the tensor core's proxy
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar_xempty + 8 * s);                                   // stage free for the next box
+        mbar_arrive(bar_xempty + 8 * s);                                   // stage free for the next box (reads only: no fence)
         if (hh == 1) mbar_arrive_cluster_relaxed(lead_afull + 8 * slot);   // chunk complete; leader's barrier (remote for rank 1)
       }
       if (hh == 1 && ++slot == k4ASlots) { slot = 0; apar ^= 1u; }
