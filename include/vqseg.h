@@ -96,6 +96,22 @@ int    vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D,
 /* prof_events (nullable): four cudaEvent_t owned by the caller; the call records [0],[1] around the tensor-core
  * filter kernel and [2],[3] around the rescoring kernel on `stream` (bench.py's roofline line).  No library state. */
 
+/* ---- prepared samples: for inputs that are assigned many times (the Lloyd iterations of kmeans, vq_img.py:35-61:
+ * the same samples against new means every iteration).  vqseg_samples_prepare_f32 builds, once, the fp16 operand of
+ * the tensor-core filter as ready-made shared-memory tiles plus the per-row norms of its error bound;
+ * vqseg_assign_prepared_f32 is vqseg_assign_f32 whose filter streams those tiles instead of converting x on the fly
+ * (D <= 512, K <= 65536; otherwise `samples` is ignored).  x is still needed: the exact rescoring reads it.  Results are
+ * identical to vqseg_assign_f32's.  The blob must be 1024-byte aligned. */
+size_t vqseg_samples_blob_bytes(int64_t n_rows, int64_t D);
+int    vqseg_samples_prepare_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                                 int64_t sB, int64_t sP, int64_t sD,
+                                 void* samples_blob, size_t blob_bytes, void* stream);
+int    vqseg_assign_prepared_f32(const float* x, int64_t B, int64_t P, int64_t D,
+                                 int64_t sB, int64_t sP, int64_t sD,
+                                 const void* samples_blob, const float* E, int64_t K, void* blob,
+                                 int64_t* idx_out, int64_t* counts_out, int algo,
+                                 void* ws, size_t ws_bytes, void* stream, void* const* prof_events);
+
 /* unpack the keys of the sharded mode after the cross-rank min: idx = key & 0xffffffff           */
 int    vqseg_unpack_keys(const uint64_t* keys, int64_t n, int64_t* idx_out, float* dist_out,
                          int64_t* counts_out, int64_t K, void* stream);

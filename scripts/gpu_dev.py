@@ -398,23 +398,28 @@ def stage_stream():
         e = torch.randn(k, d, generator=g, device=dev)
         blob = ops.prepare_codebook(e)
         res = {}
-        for an, algo in (("single", ops.ALGO_TC_STREAM), ("pair", ops.ALGO_TC_STREAM_PAIR)):
+        samples = ops.prepare_samples(xv) if d <= 512 else None
+        for an, algo in (("single", ops.ALGO_TC_STREAM), ("pair", ops.ALGO_TC_STREAM_PAIR), ("prepared", ops.ALGO_AUTO)):
+            smp = samples if an == "prepared" else None
+            if an == "prepared" and samples is None:
+                continue
             for _ in range(2):
-                out = ops.assign(xv, e, blob, algo)
+                out = ops.assign(xv, e, blob, algo, 0, smp)
             prof = _native.ProfileEvents()
             ops.set_profile_events(prof)
             kt, rt = [], []
             for _ in range(5):
-                out = ops.assign(xv, e, blob, algo); torch.cuda.synchronize()
+                out = ops.assign(xv, e, blob, algo, 0, smp); torch.cuda.synchronize()
                 kt.append(prof.filter_ms() * 1e3); rt.append(prof.rescore_ms() * 1e3)
             ops.set_profile_events(None)
             kt.sort(); rt.sort()
             flagged = ops._last_assign_ws[:4].view(torch.int32).item()
             res[an] = (kt[2], rt[2], flagged, out)
         fl = 2.0 * n * k * d
-        same = torch.equal(res["single"][3][0], res["pair"][3][0])
+        same = torch.equal(res["single"][3][0], res["pair"][3][0]) and ("prepared" not in res or torch.equal(res["pair"][3][0], res["prepared"][3][0]))
+        prep = f"prepared {res['prepared'][0]:9.1f} us ({fl / res['prepared'][0] / 1e6:6.1f} TF)  " if "prepared" in res else ""
         print(f"[stream] {nm:16s} N={n:8d} D={d:4d} K={k:6d}: single {res['single'][0]:9.1f} us ({fl / res['single'][0] / 1e6:6.1f} TF)  "
-              f"pair {res['pair'][0]:9.1f} us ({fl / res['pair'][0] / 1e6:6.1f} TF)  rescoring {res['pair'][1]:7.1f} us  "
+              f"pair {res['pair'][0]:9.1f} us ({fl / res['pair'][0] / 1e6:6.1f} TF)  {prep}rescoring {res['pair'][1]:7.1f} us  "
               f"rescored {100.0 * res['pair'][2] / n:4.1f}%  same idx {same}", flush=True)
 
 

@@ -152,6 +152,49 @@ def test_split_d_mode_equals_exact(dev, shape, layout, metric):
         assert torch.equal(keys_ex, keys_tc)
 
 
+@pytest.mark.parametrize("shape,layout", [((1, 70000, 512, 1024), "rows"), ((1, 33001, 256, 4096), "rows"),
+                                          ((3, 9000, 320, 700), "rows"), ((8, 9216, 128, 2000), "nchw"), ((1, 300, 512, 600), "rows")])
+def test_prepared_samples_equal_plain_assignment(dev, shape, layout):
+    """vqseg_samples_prepare_f32 + vqseg_assign_prepared_f32 (the filter streams ready-made fp16 tiles: k-means assigns
+    the same samples every Lloyd iteration): indices and counts identical to the exact scorer and to the plain path,
+    for ragged row counts (odd tile counts, a padded last pair tile) and both layouts of the source."""
+    from vq_seg_b200 import ops
+    B, P, D, K = shape
+    g = torch.Generator(device="cuda").manual_seed(B + P + D + K)
+    centres = torch.randn(K, D, generator=g, device=dev)
+    pick = torch.randint(0, K, (B, P), generator=g, device=dev)
+    rows = centres[pick] * 0.7 + 0.8 * torch.randn(B, P, D, generator=g, device=dev)
+    xv = rows.permute(0, 2, 1).contiguous().permute(0, 2, 1) if layout == "nchw" else rows
+    blob = ops.prepare_codebook(centres)
+    samples = ops.prepare_samples(xv)
+    i_ex, c_ex = ops.assign(xv, centres, None, ops.ALGO_EXACT)
+    i_pl, c_pl = ops.assign(xv, centres, blob, ops.ALGO_TC_STREAM_PAIR if P % 4 == 0 or layout == "rows" else ops.ALGO_TC)
+    for _ in range(2):
+        i_pr, c_pr = ops.assign(xv, centres, blob, ops.ALGO_AUTO, 0, samples)
+        assert torch.equal(i_ex, i_pr), f"{(i_ex != i_pr).sum().item()} rows differ"
+        assert torch.equal(c_ex, c_pr)
+    assert torch.equal(i_pl, i_pr) and torch.equal(c_pl, c_pr)
+    # new means, same samples (what a Lloyd iteration does)
+    centres2 = centres + 0.05 * torch.randn(K, D, generator=g, device=dev)
+    i2, c2 = ops.assign(xv, centres2, ops.prepare_codebook(centres2), ops.ALGO_AUTO, 0, samples)
+    i2e, c2e = ops.assign(xv, centres2, None, ops.ALGO_EXACT)
+    assert torch.equal(i2, i2e) and torch.equal(c2, c2e)
+
+
+def test_kmeans_with_prepared_samples_is_bit_equal(dev):
+    """kmeans() prepares large sample sets once; the result must equal the iteration-by-iteration conversion."""
+    import vq_seg_b200 as V
+    from vq_seg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(77)
+    centres = torch.randn(600, 192, generator=g, device=dev)
+    x = centres[torch.randint(0, 600, (1, 80000), generator=g, device=dev)] + 0.5 * torch.randn(1, 80000, 192, generator=g, device=dev)
+    init = torch.randperm(80000, generator=g, device=dev)[:600]
+    m1, b1 = V.kmeans(x, 600, 3, init_indices=init)                       # eligible: prepared samples
+    m2, b2 = V.kmeans(x, 600, 3, init_indices=init, algo=ops.ALGO_TC_STREAM_PAIR)   # forced plain streaming kernel
+    m3, b3 = V.kmeans(x, 600, 3, init_indices=init, algo=ops.ALGO_EXACT)
+    assert torch.equal(b1, b2) and torch.equal(m1, m2) and torch.equal(b1, b3) and torch.equal(m1, m3)
+
+
 def test_kblock_override_changes_only_near_ties(dev):
     """kblock is the fp32 chain split of the exact scorer; a different split may only move rows
     whose two best reference distances are within 2 ulp."""

@@ -20,6 +20,9 @@ SIGNATURES = {
     "vqseg_codebook_blob_bytes": (sz, [i64, i64]),
     "vqseg_codebook_prepare_f32": (ci, [vp, i64, i64, vp, sz, vp]),
     "vqseg_codebook_prepare_ip_f32": (ci, [vp, i64, i64, vp, sz, vp]),
+    "vqseg_samples_blob_bytes": (sz, [i64, i64]),
+    "vqseg_samples_prepare_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, sz, vp]),
+    "vqseg_assign_prepared_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, vp, vp, vp, ci, vp, sz, vp, vp]),
     "vqseg_assign_workspace_bytes": (sz, [i64, i64, i64, ci]),
     "vqseg_assign_f32": (ci, [vp, i64, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, sz, vp, vp]),
     "vqseg_unpack_keys": (ci, [vp, i64, vp, vp, vp, i64, vp]),

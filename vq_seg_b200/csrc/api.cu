@@ -173,6 +173,31 @@ static int codebook_prepare(const float* E, int64_t K, int64_t D, void* blob, si
   return launch_pack(E, (int)K, (int)D, b, st);
 }
 
+// ---- prepared samples: [0, 256) header | norms float2[rows_padded] | image (1024-aligned) ------------------------------
+static void samples_geometry(long long n_rows, long long D, long long* rows_padded, long long* D_pad, size_t* off_img, size_t* total) {
+  *rows_padded = round_up(n_rows, 256);                 // whole PAIR tiles: the second CTA of the last pair finds zeros
+  *D_pad = round_up(D, kDChunk);
+  *off_img = (size_t)round_up(256 + *rows_padded * 8, 1024);
+  *total = *off_img + (size_t)(*rows_padded) * (size_t)(*D_pad) * 2;
+}
+size_t vqseg_samples_blob_bytes(int64_t n_rows, int64_t D) {
+  if (n_rows <= 0 || D <= 0) return 0;
+  long long rp, dp; size_t oi, tot;
+  samples_geometry(n_rows, D, &rp, &dp, &oi, &tot);
+  return tot;
+}
+int vqseg_samples_prepare_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                              void* blob, size_t blob_bytes, void* stream) {
+  if (!x || !blob || B <= 0 || P <= 0 || D <= 0 || B * P >= (1ll << 31)) return VQSEG_EINVAL;
+  long long rp, dp; size_t oi, tot;
+  samples_geometry(B * P, D, &rp, &dp, &oi, &tot);
+  if (blob_bytes < tot) return VQSEG_EWORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(blob) & 1023) != 0) return VQSEG_EINVAL;
+  Rows xr{x, B, P, D, sB, sP, sD};
+  return launch_samples_prepare(xr, rp, (int)dp, (unsigned char*)blob + oi, reinterpret_cast<float2*>((unsigned char*)blob + 256),
+                                (cudaStream_t)stream);
+}
+
 // split-D mode (few rows, many dims) sums partial scores in an [n_rows][K_pad] fp32 scratch (+ 2 floats per row):
 // only problems whose scratch stays below 32 MB are eligible
 static size_t splitd_scratch_bytes(long long n_rows, long long K) {
@@ -196,7 +221,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
                            const float* E, int64_t K, void* blob,
                            int64_t* idx_out, int64_t* counts_out, uint64_t* best_key_out,
                            int64_t code_base, int kblock, int algo, void* ws, size_t ws_bytes, void* stream,
-                           void* const* prof_events, float* zero_loss, bool zero_counts) {
+                           void* const* prof_events, float* zero_loss, bool zero_counts, const void* samples = nullptr) {
   if (!x || !E || B < 0 || P < 0 || D <= 0 || K <= 0) return VQSEG_EINVAL;
   if (!idx_out && !best_key_out) return VQSEG_EINVAL;
   const int ip = (algo & VQSEG_METRIC_IP) ? 1 : 0;
@@ -252,6 +277,10 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
         const long long tiles = lay == 1 ? B * ((P + 127) / 128) : (n_rows + 127) / 128;
         if (2 * ((tiles + 1) / 2) * (n_dc / sd_) >= pairs || sd_ == 2) { slice_dc = sd_; n_slices = n_dc / sd_; lay4 = lay; kernel = 5; break; }
       }
+    }
+    // prepared samples (vqseg_samples_prepare_f32): the streaming pair kernel reads its A operand ready-made
+    if (samples && n_dc <= 8 && kp <= 65536 && (algo == VQSEG_ALGO_AUTO || algo == VQSEG_ALGO_TC || algo == VQSEG_ALGO_TC_STREAM_PAIR)) {
+      kernel = 4; lay4 = 3; n_slices = 1;
     }
     if (algo == VQSEG_ALGO_TC_STREAM) kernel = 1;
     if (algo == VQSEG_ALGO_TC_STREAM_PAIR) { if (!lay4) return VQSEG_EUNSUPPORTED; kernel = 4; }
@@ -310,6 +339,12 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     t4.B = B; t4.P = P; t4.D = D; t4.n_rows = n_rows; t4.blob = (const unsigned char*)blob;
     if (lay4 == 1) { t4.tiles_per_image = (int)((P + 127) / 128); t4.n_tiles = (int)(B * t4.tiles_per_image); }
     else { t4.tiles_per_image = 0; t4.n_tiles = (int)((n_rows + 127) / 128); }
+    if (lay4 == 3) {
+      long long rp, dpp; size_t soi, stot;
+      samples_geometry(n_rows, D, &rp, &dpp, &soi, &stot);
+      t4.samp_img = (const unsigned char*)samples + soi;
+      t4.samp_norms = reinterpret_cast<const float2*>((const unsigned char*)samples + 256);
+    }
     t4.n_ptiles = (t4.n_tiles + 1) / 2; t4.n_cc = n_cc; t4.n_dc = n_dc;
     t4.n_slices = 1; t4.n_dc_total = n_dc;
     if (kernel == 5) {                              // split-D mode: partial scores into the scratch, short-lists afterwards
@@ -375,6 +410,15 @@ int vqseg_assign_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB
                      void* const* prof_events) {
   return assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, best_key_out, code_base, kblock, algo,
                          ws, ws_bytes, stream, prof_events, nullptr, false);
+}
+
+int vqseg_assign_prepared_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_t sB, int64_t sP, int64_t sD,
+                              const void* samples, const float* E, int64_t K, void* blob,
+                              int64_t* idx_out, int64_t* counts_out, int algo, void* ws, size_t ws_bytes, void* stream,
+                              void* const* prof_events) {
+  if (!samples || !blob) return VQSEG_EINVAL;
+  return assign_internal(x, B, P, D, sB, sP, sD, E, K, blob, idx_out, counts_out, nullptr, 0, 0, algo,
+                         ws, ws_bytes, stream, prof_events, nullptr, false, samples);
 }
 
 size_t vqseg_forward_workspace_bytes(int64_t n_rows, int64_t D, int64_t K) {

@@ -18,6 +18,7 @@
 // Roles per CTA (21 warps): 0-7 converters, 8-15 epilogue, 16 MMA issuer (leader CTA) + TMEM alloc, 17 codebook
 // loader (cp.async.bulk), 18 relay (local stage landed -> leader's "both halves resident" barrier), 19-20 x loaders.
 #include <cuda.h>
+#include <string.h>
 #include "tc_common.cuh"
 #include "kernels.cuh"
 
@@ -44,7 +45,7 @@ struct Tc4Smem {
   static constexpr int off_xchg = off_cand + 2 * k4Rows * k4CandCap * 2;     // [128] {m_run, cnt|overflow} of the upper-half warp
   static constexpr int off_xsq = off_xchg + k4Rows * 8;                      // [2 tiles][2 halves of a box][128] float2
   static constexpr int off_bar = off_xsq + 2 * 2 * k4Rows * 8;
-  static constexpr int n_bars = 2 * k4ASlots + 3 * k4BStages + 2 * k4XStages + 4 + 2 + 2;
+  static constexpr int n_bars = 2 * k4ASlots + 3 * k4BStages + 2 * k4XStages + 4 + 2 + 2 + k4ASlots;
   static constexpr int off_tmem = off_bar + 8 * n_bars;
   static constexpr int total = off_tmem + 16 + 1024;
 };
@@ -66,10 +67,17 @@ __device__ __forceinline__ void tma4_load_2d(uint32_t dst, const CUtensorMap* ma
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-// ROWS = false: NCHW maps (pixel-contiguous), tiles of 128 pixels of one image; true: packed rows (dim-contiguous)
-template <bool ROWS>
+// MODE 0: NCHW maps (pixel-contiguous), tiles of 128 pixels of one image; 1: packed rows (dim-contiguous);
+// 2: PREPARED samples (vqseg_samples_prepare_f32): the fp16 A chunks already exist in global memory as ready-made
+//    SWIZZLE_128B tiles, [row tile][dim chunk] x 16 KiB, and arrive by cp.async.bulk straight into the A ring -- no
+//    converter warps, no fp32 staging; the row norms come from the blob.  For inputs that are assigned many times
+//    (the Lloyd iterations of k-means: the same samples against new means): the conversion, which bounds the kernel
+//    at K ~ 1024, is paid once.
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k4Threads, 1)
 assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
+  constexpr bool ROWS = MODE != 0;        // row index = tile * 128 + r (no images)
+  constexpr bool PRE = MODE == 2;
   extern __shared__ __align__(1024) unsigned char smem_raw4[];
   unsigned char* smem = smem_raw4 + ((1024u - (smem_u32(smem_raw4) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
@@ -88,6 +96,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
   const uint32_t bar_tempty = bar_tfull + 16;                          // [2] leader: 16 epilogue-warp arrivals
   const uint32_t bar_gempty = bar_tempty + 16;                         // [2] each CTA: 1 (multicast commit): limb tile free
   const uint32_t bar_nempty = bar_gempty + 16;                         // [2] local: 8 epilogue warps have read the tile's row norms
+  const uint32_t bar_aload = bar_nempty + 16;                          // [A slots] MODE 2, local: 1 + tx bytes (bulk copy of a chunk)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Tc4Smem::off_tmem);
   float2* xsq = reinterpret_cast<float2*>(smem + Tc4Smem::off_xsq);
 
@@ -123,7 +132,9 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < k4ASlots; ++s) { mbar_init(bar_afull + 8 * s, 16); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < k4ASlots; ++s) {
+      mbar_init(bar_afull + 8 * s, PRE ? 2 : 16); mbar_init(bar_aempty + 8 * s, 1); mbar_init(bar_aload + 8 * s, 1);
+    }
     for (int s = 0; s < k4BStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bready + 8 * s, 2); mbar_init(bar_bempty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 16); mbar_init(bar_gempty + 8 * b, 1); mbar_init(bar_nempty + 8 * b, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -132,7 +143,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
-  if (warp >= 19) {
+  if (warp >= 19 && !PRE) {
     // the x pipeline starts before the CTA / cluster set-up completes (see assign_tc3.cu)
     if (warp == 19 && lane == 0) {
       for (int s = 0; s < k4XStages; ++s) { mbar_init(bar_xfull + 8 * s, 1); mbar_init(bar_xempty + 8 * s, 8); }
@@ -164,7 +175,8 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
     // loop counters kept incrementally (a division by the runtime box count per box is 20+ dependent instructions)
     int slot = 0; uint32_t apar = 1;                           // A slot of the current chunk, parity of its "empty" phase
     int q = 0;
-    for (int tt = 0; tt < my_tiles; ++tt)
+    const int conv_tiles = PRE ? 0 : my_tiles;                 // (MODE 2: nothing to convert)
+    for (int tt = 0; tt < conv_tiles; ++tt)
     for (int h = 0; h < boxes_per_tile; ++h, ++q) {
       const int hh = h & 1;
       const int s = q & (k4XStages - 1);
@@ -251,7 +263,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
             const float2 n0 = xsq[((tt & 1) * 2 + 0) * k4Rows + r], n1 = xsq[((tt & 1) * 2 + 1) * k4Rows + r];
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_nempty + 8 * (tt & 1));
-            if (in_range && half == 0) {
+            if (in_range && half == 0) {                               // (split-D mode is never combined with MODE 2)
               atomicAdd(a.part_norms + 2 * n, n0.x + n1.x);
               atomicAdd(a.part_norms + 2 * n + 1, n0.y + n1.y);
             }
@@ -286,7 +298,12 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
         tc_fence_after();
         if (warp == 8) VQ4_TRACE(2, 4 * u + 1);
         if (cc == 0) {
-          const float2 n0 = xsq[((tt & 1) * 2 + 0) * k4Rows + r], n1 = xsq[((tt & 1) * 2 + 1) * k4Rows + r];
+          float2 n0, n1 = make_float2(0.f, 0.f);
+          if (PRE) {
+            n0 = a.samp_norms[(long long)t * k4Rows + r];               // {|x|^2, |fp16(x) - x|^2} from the prepared blob
+          } else {
+            n0 = xsq[((tt & 1) * 2 + 0) * k4Rows + r]; n1 = xsq[((tt & 1) * 2 + 1) * k4Rows + r];
+          }
           const float xn = sqrtf(n0.x + n1.x) * 1.0001f, dn = sqrtf(n0.y + n1.y) * 1.0001f;
           const float e_s = emax * scale;
           const float sum = xn + emax;
@@ -296,7 +313,7 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
                 + 1.0e-6f * e_s * emax;
           if (!(slack < 3.0e38f) || bad_blob) overflow = true;
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_nempty + 8 * (tt & 1));         // the converters may reuse this norm buffer
+          if (!PRE && lane == 0) mbar_arrive(bar_nempty + 8 * (tt & 1));  // the converters may reuse this norm buffer
         }
         const uint32_t tb = lane_addr + buf * 256;
 #pragma unroll 1
@@ -465,7 +482,28 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
     }
   } else {
     // ================= x loaders (warps 19-20): issuer i owns stage i, boxes q = i, i + 2, ... =================
-    if (lane == 0) {
+    if (PRE) {
+      // MODE 2: warp 19 streams this CTA's ready-made A chunks into the ring, warp 20 tells the leader's MMA issuer
+      // when a chunk has landed here (the "full" barrier of a slot then counts the two CTAs)
+      if (lane == 0) {
+        int slot = 0; uint32_t par = warp == 19 ? 1u : 0u;     // 19: parity of the slot's "empty" phase; 20: of its "landed" phase
+        for (int tt = 0; tt < my_tiles; ++tt) {
+          const long long t = tile_id(tt);
+          for (int dc = 0; dc < a.n_dc; ++dc) {
+            if (warp == 19) {
+              mbar_wait(bar_aempty + 8 * slot, par);
+              mbar_arrive_expect_tx(bar_aload + 8 * slot, kTileBytes);
+              bulk_g2s(sbase + Tc4Smem::off_a + slot * kTileBytes, a.samp_img + (t * a.n_dc_total + dc) * kTileBytes, kTileBytes,
+                       bar_aload + 8 * slot);
+            } else {
+              mbar_wait(bar_aload + 8 * slot, par);
+              mbar_arrive_cluster(lead_afull + 8 * slot);
+            }
+            if (++slot == k4ASlots) { slot = 0; par ^= 1u; }
+          }
+        }
+      }
+    } else if (lane == 0) {
       const int issuer = warp - 19;
       for (int q = issuer + k4XStages; q < total_boxes; q += k4XStages) issue_box(q, issuer);
     }
@@ -478,6 +516,56 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
   if (warp == 16) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
+}
+
+// ---- prepared samples (MODE 2): fp16 A tiles + row norms, built once per input --------------------------------------
+// image tile (row tile, dc): 128 rows x 64 dims of fp16(x), SWIZZLE_128B K-major like the codebook image:
+//   byte = row*128 + ((col/8) ^ (row & 7))*16 + (col % 8)*2;  rows past the end and dims past D are zero
+__global__ void __launch_bounds__(256) samples_pack_kernel(Rows x, long long n_rows, long long rows_padded, int D_pad,
+                                                           unsigned char* __restrict__ img) {
+  const int D = (int)x.D, g8 = D_pad / 8, n_dc = D_pad / kDChunk;
+  const long long total = rows_padded * g8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / g8;
+    const int d8 = (int)(i % g8) * 8;
+    __align__(16) __half h[8];
+    const float* xr = n < n_rows ? x.row(n) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = __float2half_rn((xr && d8 + j < D) ? __ldg(xr + (long long)(d8 + j) * x.sD) : 0.f);
+    const long long tile = n / 128;
+    const int row = (int)(n % 128), dc = d8 / kDChunk, c8 = (d8 % kDChunk) / 8;
+    unsigned char* tp = img + (tile * n_dc + dc) * kTileBytes;
+    *reinterpret_cast<uint4*>(tp + row * 128 + ((c8 ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+__global__ void __launch_bounds__(256) samples_norms_kernel(Rows x, long long n_rows, long long rows_padded, float2* __restrict__ norms) {
+  const int lane = threadIdx.x & 31, D = (int)x.D;
+  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long n = w0; n < rows_padded; n += nw) {
+    float ss = 0.f, sd = 0.f;
+    if (n < n_rows) {
+      const float* xr = x.row(n);
+      for (int d = lane; d < D; d += 32) {
+        const float v = __ldg(xr + (long long)d * x.sD);
+        const float e = __half2float(__float2half_rn(v)) - v;
+        ss = fmaf(v, v, ss); sd = fmaf(e, e, sd);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); sd += __shfl_xor_sync(0xffffffffu, sd, o); }
+    if (lane == 0) norms[n] = make_float2(ss * 1.0001f, sd * 1.0001f);     // (any summation order: upper-bound slack)
+  }
+}
+int launch_samples_prepare(const Rows& x, long long rows_padded, int D_pad, unsigned char* img, float2* norms, cudaStream_t st) {
+  const long long n_rows = x.n_rows();
+  long long blocks = (rows_padded * (D_pad / 8) + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  samples_pack_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(x, n_rows, rows_padded, D_pad, img);
+  VQSEG_LAUNCH_CHECK();
+  blocks = (rows_padded * 32 + 255) / 256;
+  samples_norms_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(x, n_rows, rows_padded, norms);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---- split-D mode, second step: the short-list of every row over its summed scores ------------------------------------
@@ -585,6 +673,16 @@ int launch_assign_tc4(const Rows& x, const Tc4Args& a, int layout, cudaStream_t 
   int pairs = num_sms() / 2;
   if (a.n_ptiles * a.n_slices < pairs) pairs = a.n_ptiles * a.n_slices;
   if (pairs <= 0) return 0;
+  if (layout == 3) {                                           // prepared samples: no tensor map
+    CUtensorMap none;
+    memset(&none, 0, sizeof(none));
+    static size_t configured[kMaxDevices] = {0};
+    if (int e = ensure_dynamic_smem(assign_tc4_kernel<2>, Tc4Smem::total, configured)) return e;
+    cudaError_t le = launch_dependent(assign_tc4_kernel<2>, dim3(2 * pairs), dim3(k4Threads), (size_t)Tc4Smem::total, st, pdl_enabled(), none, a);
+    if (le != cudaSuccess) return (int)le;
+    VQSEG_LAUNCH_CHECK();
+    return 0;
+  }
   EncodeTiledFn4 enc = encode_tiled_fn4();
   if (!enc) return VQSEG_EUNSUPPORTED;
   CUtensorMap tmap;
@@ -610,13 +708,13 @@ int launch_assign_tc4(const Rows& x, const Tc4Args& a, int layout, cudaStream_t 
   if (rc != CUDA_SUCCESS) return VQSEG_EUNSUPPORTED;
   if (layout == 1) {
     static size_t configured[kMaxDevices] = {0};
-    if (int e = ensure_dynamic_smem(assign_tc4_kernel<false>, Tc4Smem::total, configured)) return e;
-    cudaError_t le = launch_dependent(assign_tc4_kernel<false>, dim3(2 * pairs), dim3(k4Threads), (size_t)Tc4Smem::total, st, pdl_enabled(), tmap, a);
+    if (int e = ensure_dynamic_smem(assign_tc4_kernel<0>, Tc4Smem::total, configured)) return e;
+    cudaError_t le = launch_dependent(assign_tc4_kernel<0>, dim3(2 * pairs), dim3(k4Threads), (size_t)Tc4Smem::total, st, pdl_enabled(), tmap, a);
     if (le != cudaSuccess) return (int)le;
   } else {
     static size_t configured[kMaxDevices] = {0};
-    if (int e = ensure_dynamic_smem(assign_tc4_kernel<true>, Tc4Smem::total, configured)) return e;
-    cudaError_t le = launch_dependent(assign_tc4_kernel<true>, dim3(2 * pairs), dim3(k4Threads), (size_t)Tc4Smem::total, st, pdl_enabled(), tmap, a);
+    if (int e = ensure_dynamic_smem(assign_tc4_kernel<1>, Tc4Smem::total, configured)) return e;
+    cudaError_t le = launch_dependent(assign_tc4_kernel<1>, dim3(2 * pairs), dim3(k4Threads), (size_t)Tc4Smem::total, st, pdl_enabled(), tmap, a);
     if (le != cudaSuccess) return (int)le;
   }
   VQSEG_LAUNCH_CHECK();

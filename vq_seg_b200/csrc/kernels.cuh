@@ -89,6 +89,8 @@ struct Tc4Args {
   int n_slices, n_dc_total;       // split-D mode: dim slices per row (1 = off), dim chunks of the whole row
   float* part_scores;             // split-D mode: [n_rows][K_pad] partial scores, zeroed by the prologue (else null)
   float* part_norms;              //               [n_rows][2] {|x|^2, |fp16(x) - x|^2}
+  const unsigned char* samp_img;  // MODE 2 (prepared samples): fp16 A tiles [row tile][dim chunk] x 16 KiB
+  const float2* samp_norms;       //                            [padded rows] {|x|^2, |fp16(x) - x|^2}
   int K, K_pad;
   unsigned long long off_image, off_aug, off_enorm;
   long long* idx_out; unsigned long long* counts_out; long long code_base;
@@ -105,6 +107,7 @@ struct ShortlistArgs {
 };
 int launch_shortlist(const ShortlistArgs& a, cudaStream_t st);
 int tc4_layout(const Rows& x, long long K_pad, int n_dc);   // 0: unsupported, 1: NCHW maps, 2: packed rows
-int launch_assign_tc4(const Rows& x, const Tc4Args& a, int layout, cudaStream_t st);
+int launch_assign_tc4(const Rows& x, const Tc4Args& a, int layout, cudaStream_t st);    // layout 3: prepared samples
+int launch_samples_prepare(const Rows& x, long long rows_padded, int D_pad, unsigned char* img, float2* norms, cudaStream_t st);
 
 }  // namespace vqseg

@@ -100,10 +100,34 @@ def _prof():
     return _profile.array if _profile is not None else None
 
 
+def _prepare_samples_impl(x: torch.Tensor) -> torch.Tensor:
+    """The fp16 operand tiles + row norms of the tensor-core filter for a (B, P, D) input that will be assigned many
+    times (k-means: the same samples against new means every Lloyd iteration); pass it to assign(..., samples=)."""
+    _require_cuda(x)
+    L = _native.lib()
+    if x.dtype != torch.float32:
+        x = x.float()
+    b, p, d, sb, sp, sd = _bpd(x)
+    n = L.vqseg_samples_blob_bytes(b * p, d)
+    blob = _aligned_bytes(n, x.device)
+    with torch.cuda.device(x.device):
+        _native.check(L.vqseg_samples_prepare_f32(x.data_ptr(), b, p, d, sb, sp, sd, blob.data_ptr(), n, _stream()), "samples_prepare")
+    return blob
+
+
+prepare_samples = torch.library.custom_op("vqseg::prepare_samples", mutates_args=())(_prepare_samples_impl)
+
+
+@prepare_samples.register_fake
+def _(x):
+    return x.new_empty(_native.lib().vqseg_samples_blob_bytes(x.shape[0] * x.shape[1], x.shape[2]), dtype=torch.uint8)
+
+
 def _assign_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.Tensor], algo: int = 0,
-           kblock: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(idx (B,P) int64, counts (K,) int64): first-index argmin of the reference's fp32 cdist."""
-    _require_cuda(x, codebook, blob)
+           kblock: int = 0, samples: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(idx (B,P) int64, counts (K,) int64): first-index argmin of the reference's fp32 cdist.
+    `samples` = prepare_samples(x): the filter streams the prepared operand instead of converting x (same results)."""
+    _require_cuda(x, codebook, blob, samples)
     L = _native.lib()
     if x.dtype != torch.float32:
         x = x.float()
@@ -117,10 +141,15 @@ def _assign_impl(x: torch.Tensor, codebook: torch.Tensor, blob: Optional[torch.T
     nws = L.vqseg_assign_workspace_bytes(b * p, d, k, algo)
     ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        _native.check(L.vqseg_assign_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
-                                         blob.data_ptr() if blob is not None else None,
-                                         idx.data_ptr(), counts.data_ptr(), None, 0, kblock, algo,
-                                         ws.data_ptr(), nws, _stream(), _prof()), "assign")
+        if samples is not None and blob is not None and kblock == 0:
+            _native.check(L.vqseg_assign_prepared_f32(x.data_ptr(), b, p, d, sb, sp, sd, samples.data_ptr(), cb.data_ptr(), k,
+                                                      blob.data_ptr(), idx.data_ptr(), counts.data_ptr(), algo,
+                                                      ws.data_ptr(), nws, _stream(), _prof()), "assign_prepared")
+        else:
+            _native.check(L.vqseg_assign_f32(x.data_ptr(), b, p, d, sb, sp, sd, cb.data_ptr(), k,
+                                             blob.data_ptr() if blob is not None else None,
+                                             idx.data_ptr(), counts.data_ptr(), None, 0, kblock, algo,
+                                             ws.data_ptr(), nws, _stream(), _prof()), "assign")
     global _last_assign_ws
     _last_assign_ws = ws            # dev diagnostics: ws[0:4] = number of rows sent to the exact pass
     return idx, counts
@@ -130,7 +159,7 @@ assign = torch.library.custom_op("vqseg::assign", mutates_args=())(_assign_impl)
 
 
 @assign.register_fake
-def _(x, codebook, blob, algo=0, kblock=0):
+def _(x, codebook, blob, algo=0, kblock=0, samples=None):
     return (x.new_empty((x.shape[0], x.shape[1]), dtype=torch.int64),
             x.new_empty((codebook.shape[0],), dtype=torch.int64))
 
@@ -774,8 +803,8 @@ def eval_gather(codebook, x_like, idx, amp_fp16=False):
     return _EvalGather.apply(codebook, x_like, idx, MODE_EVAL_AMP if amp_fp16 else MODE_EVAL)
 
 
-def fast_assign(x, codebook, blob, algo=ALGO_AUTO, kblock=0):
-    return (_assign_impl if _fast() else assign)(x, codebook, blob, algo, kblock)
+def fast_assign(x, codebook, blob, algo=ALGO_AUTO, kblock=0, samples=None):
+    return (_assign_impl if _fast() else assign)(x, codebook, blob, algo, kblock, samples)
 
 
 def fast_code_usage(counts):

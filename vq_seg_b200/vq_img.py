@@ -69,6 +69,7 @@ def kmeans(flatten_x: torch.Tensor, num_clusters: int, num_iters: int, use_cosin
     reference; bins belong to the LAST assignment."""
     x = flatten_x if flatten_x.dim() == 3 else flatten_x.reshape(1, -1, flatten_x.shape[-1])
     x = x.detach()
+    n_rows = x.shape[0] * x.shape[1]
     means = _sample_rows(x, num_clusters, init_indices)            # batched_sample_vectors of vq_img.py:33, one codebook
     if reduce_fn is not None and init_indices is None:
         # data-parallel: every rank drew its own rows; all must iterate from ONE start (rank 0's), or the first
@@ -77,12 +78,18 @@ def kmeans(flatten_x: torch.Tensor, num_clusters: int, num_iters: int, use_cosin
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.broadcast(means, src=0)
     bins = torch.zeros(num_clusters, dtype=torch.int64, device=x.device)
+    # many samples, several iterations, a codebook that is streamed (not resident): convert the samples to the
+    # filter's fp16 operand ONCE -- the conversion bounds the streaming kernel at K ~ 1024
+    samples = None
+    if (not use_cosine_sim and algo in (ops.ALGO_AUTO, ops.ALGO_TC) and num_iters > 1 and n_rows >= 65536
+            and x.shape[-1] <= 512 and 256 < num_clusters <= 65536):
+        samples = ops.prepare_samples(x)
     for _ in range(num_iters):
         if use_cosine_sim:
             buckets, _ = ops.assign_cosine(x, means, None, algo)
         else:
             blob = ops.prepare_codebook(means) if algo != ops.ALGO_EXACT else None
-            buckets, _ = ops.assign(x, means, blob, algo)
+            buckets, _ = ops.assign(x, means, blob, algo, 0, samples)
         bins, sums = ops.code_stats(x, buckets, num_clusters, deterministic)
         if reduce_fn is not None:
             reduce_fn(bins, sums)
