@@ -522,48 +522,53 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
 // image tile (row tile, dc): 128 rows x 64 dims of fp16(x), SWIZZLE_128B K-major like the codebook image:
 //   byte = row*128 + ((col/8) ^ (row & 7))*16 + (col % 8)*2;  rows past the end and dims past D are zero
 __global__ void __launch_bounds__(256) samples_pack_kernel(Rows x, long long n_rows, long long rows_padded, int D_pad,
-                                                           unsigned char* __restrict__ img) {
-  const int D = (int)x.D, g8 = D_pad / 8, n_dc = D_pad / kDChunk;
+                                                           unsigned char* __restrict__ img, float* __restrict__ norms) {
+  // thread = (row, group of 8 dims): 32 bytes in, 16 bytes out; the row's |x|^2 and |fp16(x) - x|^2 are reduced over the
+  // lanes that share the row (contiguous lanes: a segmented suffix sum by shuffles) and added to `norms` (zeroed)
+  const int D = (int)x.D, g8 = D_pad / 8, n_dc = D_pad / kDChunk, lane = threadIdx.x & 31;
   const long long total = rows_padded * g8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long n = i / g8;
-    const int d8 = (int)(i % g8) * 8;
-    __align__(16) __half h[8];
-    const float* xr = n < n_rows ? x.row(n) : nullptr;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = __float2half_rn((xr && d8 + j < D) ? __ldg(xr + (long long)(d8 + j) * x.sD) : 0.f);
-    const long long tile = n / 128;
-    const int row = (int)(n % 128), dc = d8 / kDChunk, c8 = (d8 % kDChunk) / 8;
-    unsigned char* tp = img + (tile * n_dc + dc) * kTileBytes;
-    *reinterpret_cast<uint4*>(tp + row * 128 + ((c8 ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h);
-  }
-}
-__global__ void __launch_bounds__(256) samples_norms_kernel(Rows x, long long n_rows, long long rows_padded, float2* __restrict__ norms) {
-  const int lane = threadIdx.x & 31, D = (int)x.D;
-  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long n = w0; n < rows_padded; n += nw) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += stride) {
+    const long long i = base + lane;
+    const bool valid = i < total;
+    const long long n = valid ? i / g8 : -1 - lane;
+    const int d8 = valid ? (int)(i % g8) * 8 : 0;
     float ss = 0.f, sd = 0.f;
-    if (n < n_rows) {
-      const float* xr = x.row(n);
-      for (int d = lane; d < D; d += 32) {
-        const float v = __ldg(xr + (long long)d * x.sD);
-        const float e = __half2float(__float2half_rn(v)) - v;
+    if (valid) {
+      __align__(16) __half h[8];
+      const float* xr = n < n_rows ? x.row(n) : nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = (xr && d8 + j < D) ? __ldg(xr + (long long)(d8 + j) * x.sD) : 0.f;
+        h[j] = __float2half_rn(v);
+        const float e = __half2float(h[j]) - v;
         ss = fmaf(v, v, ss); sd = fmaf(e, e, sd);
       }
+      const long long tile = n / 128;
+      const int row = (int)(n % 128), dc = d8 / kDChunk, c8 = (d8 % kDChunk) / 8;
+      unsigned char* tp = img + (tile * n_dc + dc) * kTileBytes;
+      *reinterpret_cast<uint4*>(tp + row * 128 + ((c8 ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h);
     }
+    const unsigned same = __match_any_sync(0xffffffffu, n);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); sd += __shfl_xor_sync(0xffffffffu, sd, o); }
-    if (lane == 0) norms[n] = make_float2(ss * 1.0001f, sd * 1.0001f);     // (any summation order: upper-bound slack)
+    for (int o = 1; o < 32; o <<= 1) {
+      const float a = __shfl_down_sync(0xffffffffu, ss, o), b2 = __shfl_down_sync(0xffffffffu, sd, o);
+      if (lane + o < 32 && ((same >> (lane + o)) & 1u)) { ss += a; sd += b2; }
+    }
+    if (valid && n < n_rows && (lane == 0 || !((same >> (lane - 1)) & 1u))) {     // first lane of the row's segment
+      atomicAdd(norms + 2 * n, ss);
+      atomicAdd(norms + 2 * n + 1, sd);
+    }
   }
 }
 int launch_samples_prepare(const Rows& x, long long rows_padded, int D_pad, unsigned char* img, float2* norms, cudaStream_t st) {
   const long long n_rows = x.n_rows();
+  cudaError_t e = cudaMemsetAsync(norms, 0, (size_t)rows_padded * sizeof(float2), st);
+  if (e != cudaSuccess) return (int)e;
   long long blocks = (rows_padded * (D_pad / 8) + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
-  samples_pack_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(x, n_rows, rows_padded, D_pad, img);
-  VQSEG_LAUNCH_CHECK();
-  blocks = (rows_padded * 32 + 255) / 256;
-  samples_norms_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(x, n_rows, rows_padded, norms);
+  samples_pack_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(x, n_rows, rows_padded, D_pad, img,
+                                                                               reinterpret_cast<float*>(norms));
   VQSEG_LAUNCH_CHECK();
   return 0;
 }
