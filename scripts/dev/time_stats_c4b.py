@@ -1,5 +1,5 @@
-"""Developer tool: ordered statistics at the config-4 shape -- wall (CUDA events), host enqueue time, result equality
-between the per-range launches and the single launch (VQSEG_STATS_ONE=1)."""
+"""Developer tool: ordered (bit-exact) against atomic per-code statistics at the config-4 shape (10 M packed rows,
+D = 512, K = 1024) for uniform and skewed cluster sizes: wall by CUDA events and host enqueue time."""
 import os, sys, time, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -8,24 +8,18 @@ dev = torch.device("cuda:0")
 n, d, k = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000, 512, 1024
 g = torch.Generator(device="cuda").manual_seed(1)
 rows = torch.randn(1, n, d, generator=g, device=dev)
-idx = torch.randint(0, k, (1, n), generator=g, device=dev)
-def run(tag):
-    for _ in range(2): out = ops.code_stats(rows, idx, k, True)
+def run(tag, idx, det):
+    for _ in range(2): ops.code_stats(rows, idx, k, det)
     torch.cuda.synchronize()
     ts, hs = [], []
     for _ in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); t0 = time.perf_counter(); out = ops.code_stats(rows, idx, k, True); h = time.perf_counter() - t0; b.record()
+        a.record(); t0 = time.perf_counter(); ops.code_stats(rows, idx, k, det); h = time.perf_counter() - t0; b.record()
         torch.cuda.synchronize(); ts.append(a.elapsed_time(b)); hs.append(h * 1e3)
     print(f"{tag}: {sorted(ts)[2]:.2f} ms by events, host enqueue {sorted(hs)[2]:.2f} ms", flush=True)
-    return out
-os.environ.pop("VQSEG_STATS_ONE", None)
-c0, s0 = run("one launch per 64 MB range")
-os.environ["VQSEG_STATS_ONE"] = "1"
-c1, s1 = run("single launch")
-print("equal:", bool(torch.equal(c0, c1) and torch.equal(s0, s1)))
-ta = []
-for _ in range(5):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); ops.code_stats(rows, idx, k, False); b.record(); torch.cuda.synchronize(); ta.append(a.elapsed_time(b))
-print(f"atomic: {sorted(ta)[2]:.2f} ms")
+for name, p in (("uniform", 1.0), ("skewed u^2", 2.0), ("skewed u^4", 4.0)):
+    idx = (torch.rand(1, n, generator=g, device=dev) ** p * k).long().clamp_(0, k - 1)
+    big = int(torch.bincount(idx.reshape(-1), minlength=k).max().item())
+    print(f"--- {name}: largest cluster {big} rows ({big * k / n:.1f}x the mean)")
+    run("  ordered", idx, True)
+    run("  atomic ", idx, False)

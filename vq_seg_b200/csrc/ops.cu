@@ -424,24 +424,41 @@ __global__ void __launch_bounds__(256) stats_scan_chunks_kernel(int* __restrict_
   seg_total[t] = run;
   if (counts && run) atomicAdd(counts + k, (unsigned long long)run);
 }
-// (3) exclusive scan over codes (single block)
+// (3) exclusive scan over codes / (chunk, code) segments (single block): warp w owns a contiguous range, lanes read
+// it coalesced -- range totals first, then 32-element tiles with a shuffle scan and a running carry (the strided
+// per-thread version took 350 us for config 4's 313 k segments)
 __global__ void __launch_bounds__(1024) stats_scan_codes_kernel(const long long* __restrict__ code_total, int K,
                                                                 long long* __restrict__ code_start /* K+1 */) {
-  __shared__ long long s_part[1024];
-  const int per = (K + 1023) / 1024;
-  const int k0 = threadIdx.x * per;
+  __shared__ long long s_warp[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long R = (((long long)K + 31) / 32 + 31) / 32 * 32;          // elements per warp, a multiple of 32
+  const long long beg = min((long long)K, warp * R), end = min((long long)K, beg + R);
   long long s = 0;
-  for (int i = 0; i < per && k0 + i < K; ++i) s += code_total[k0 + i];
-  s_part[threadIdx.x] = s;
+#pragma unroll 4
+  for (long long i = beg + lane; i < end; i += 32) s += code_total[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) s_warp[warp] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    long long run = 0;
-    for (int t = 0; t < 1024; ++t) { long long v = s_part[t]; s_part[t] = run; run += v; }
-    code_start[K] = run;
+  if (warp == 0) {
+    const long long v = s_warp[lane];
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    s_warp[lane] = inc - v;
+    if (lane == 31) code_start[K] = inc;
   }
   __syncthreads();
-  long long run = s_part[threadIdx.x];
-  for (int i = 0; i < per && k0 + i < K; ++i) { code_start[k0 + i] = run; run += code_total[k0 + i]; }
+  long long run = s_warp[warp];
+#pragma unroll 4
+  for (long long base = beg; base < end; base += 32) {
+    const long long v = base + lane < end ? code_total[base + lane] : 0;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (base + lane < end) code_start[base + lane] = run + inc - v;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
 }
 // (4) stable scatter: perm[code_start[k] + hist[blk][k] + rank_in_block] = n
 // `blocks_per_chunk` > 0: the sort key is (chunk of blocks_per_chunk ranking blocks, code): code_start then holds one
@@ -478,17 +495,32 @@ __global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __
 // Packed rows (sD == 1, B == 1): one warp per (code, 128-dim slab), float4 per lane, 16 rows in flight (the row
 // ids of the next batch are fetched lane-parallel and broadcast with shuffles).  The chain of a code is
 // inherently sequential (that is what makes it bit-exact), so the critical path is max_k count[k] * latency / 16.
+// `big_counts` (optional, with `big_thr`): codes holding more than big_thr rows are summed by FOUR warps of 32 dims each
+// (one float per lane, 32 rows in flight) instead of one warp of 128 dims -- a code's chain is as long as its cluster,
+// and skewed clusterings (k-means on real features: a few codes own most rows) are bounded by the longest chain.  The
+// grid then carries four blocks per eight (code, slab) pairs; blocks 1-3 exit at once unless one of their codes is big.
 __global__ void __launch_bounds__(256) stats_ordered_sum_rows_kernel(const float* __restrict__ x, long long row_stride,
                                                                      int D, const int* __restrict__ perm,
                                                                      const long long* __restrict__ code_start, int K,
-                                                                     float* __restrict__ sums, int n_chunks) {
+                                                                     float* __restrict__ sums, int n_chunks,
+                                                                     const unsigned long long* __restrict__ big_counts,
+                                                                     unsigned long long big_thr) {
   const int slabs = (D + 127) / 128;
   const int lane = threadIdx.x & 31;
-  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nsub = big_counts ? 4 : 1;
+  const int sub = (int)(blockIdx.x % nsub);
+  const long long wid = (long long)(blockIdx.x / nsub) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)K * slabs) return;
-  const int k = (int)(wid / slabs), d = (int)(wid % slabs) * 128 + 4 * lane;
+  const int k = (int)(wid / slabs);
+  const bool big = big_counts && big_counts[k] > big_thr;
+  if (!big && sub != 0) return;
+  const int d = (int)(wid % slabs) * 128 + (big ? 32 * sub + lane : 4 * lane);
   const bool act = d < D;                       // D % 4 == 0 is guaranteed by the launcher
-  float4 s = act ? *reinterpret_cast<const float4*>(sums + (long long)k * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) {
+    if (big) s.x = sums[(long long)k * D + d];
+    else s = *reinterpret_cast<const float4*>(sums + (long long)k * D + d);
+  }
   const float* xd = x + (act ? d : 0);
   // n_chunks > 1: the (chunk, code) segments of this code one after the other (packed rows of a flat array: the row
   // ranges are visited in order by every warp, which keeps the accesses of the whole grid within a few ranges)
@@ -508,22 +540,34 @@ __global__ void __launch_bounds__(256) stats_ordered_sum_rows_kernel(const float
       const long long jn = j + 32;
       nxt = (jn + lane < end) ? __ldg(perm + jn + lane) : 0;
       const int cnt = (int)min((long long)32, end - j);
+      // UNCONDITIONAL loads (rows past the end re-read the last valid row and are simply not added): with a
+      // predicate on the load the compiler fuses it with the predicated add below and the loads serialise
+      if (big) {
+        float v[32];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (16 * h >= cnt) break;
-        float4 v[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          // UNCONDITIONAL loads (rows past the end re-read the last valid row and are simply not added): with a
-          // predicate on the load the compiler fuses it with the predicated add below and the 16 loads serialise
-          const int r = __shfl_sync(0xffffffffu, ids, min(16 * h + u, cnt - 1));
-          v[u] = __ldg(reinterpret_cast<const float4*>(xd + (long long)r * row_stride));
+        for (int u = 0; u < 32; ++u) {
+          const int r = __shfl_sync(0xffffffffu, ids, min(u, cnt - 1));
+          v[u] = __ldg(xd + (long long)r * row_stride);
         }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          if (16 * h + u < cnt) {
-            s.x = __fadd_rn(s.x, v[u].x); s.y = __fadd_rn(s.y, v[u].y);
-            s.z = __fadd_rn(s.z, v[u].z); s.w = __fadd_rn(s.w, v[u].w);
+        for (int u = 0; u < 32; ++u)
+          if (u < cnt) s.x = __fadd_rn(s.x, v[u]);
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (16 * h >= cnt) break;
+          float4 v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int r = __shfl_sync(0xffffffffu, ids, min(16 * h + u, cnt - 1));
+            v[u] = __ldg(reinterpret_cast<const float4*>(xd + (long long)r * row_stride));
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            if (16 * h + u < cnt) {
+              s.x = __fadd_rn(s.x, v[u].x); s.y = __fadd_rn(s.y, v[u].y);
+              s.z = __fadd_rn(s.z, v[u].z); s.w = __fadd_rn(s.w, v[u].w);
+            }
           }
         }
       }
@@ -531,7 +575,10 @@ __global__ void __launch_bounds__(256) stats_ordered_sum_rows_kernel(const float
     }
     beg = nbeg; end = nend; nxt = nfirst;
   }
-  if (act) *reinterpret_cast<float4*>(sums + (long long)k * D + d) = s;
+  if (act) {
+    if (big) sums[(long long)k * D + d] = s.x;
+    else *reinterpret_cast<float4*>(sums + (long long)k * D + d) = s;
+  }
 }
 
 // Any strides (NCHW feature maps): one warp per (code, 32-dim slab), lanes along d.
@@ -816,7 +863,7 @@ static int stats_det_range(const float* x, long long B, long long P, long long D
   if (packed) {
     const long long warps = K * ((D + 127) / 128);
     stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(x, sP, (int)D, perm, code_start,
-                                                                                        (int)K, sums, 1);
+                                                                                        (int)K, sums, 1, nullptr, 0ull);
   } else {
     const long long warps = K * ((D + 31) / 32);
     stats_ordered_sum_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(xr, perm, code_start, (int)K, sums);
@@ -1030,8 +1077,10 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     VQSEG_LAUNCH_CHECK();
     const long long warps = K * ((D + 127) / 128);
     if (direct) {                                                  // rows in place: ONE launch walks the ranges in order
-      stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(x, sP, (int)D, perm, seg_start, (int)K,
-                                                                                          sums, (int)n_chunks);
+      // (codes with more than twice the mean share of the rows, and at least 4096: four warps each)
+      const unsigned long long thr = (unsigned long long)(2 * n_rows / K > 4096 ? 2 * n_rows / K : 4096);
+      stats_ordered_sum_rows_kernel<<<(unsigned)(4 * ((warps * 32 + 255) / 256)), 256, 0, st>>>(
+          x, sP, (int)D, perm, seg_start, (int)K, sums, (int)n_chunks, (const unsigned long long*)counts, thr);
       VQSEG_LAUNCH_CHECK();
       return 0;
     }
@@ -1046,7 +1095,7 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
         stride = D;
       }
       stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(base, stride, (int)D, perm,
-                                                                                          seg_start + c * K, (int)K, sums, 1);
+                                                                                          seg_start + c * K, (int)K, sums, 1, nullptr, 0ull);
       VQSEG_LAUNCH_CHECK();
     }
     return 0;
