@@ -593,6 +593,15 @@ def test_code_stats_chunked_large(dev):
     c, s = ops.code_stats(x.unsqueeze(0).to(dev), idx.unsqueeze(0).to(dev), k, False)
     assert torch.equal(c.cpu(), ref_counts)
     torch.testing.assert_close(s.cpu(), ref_sums, rtol=2e-5, atol=2e-3)
+    # a big cluster (more than twice the mean share and > 4096 rows: the cp.async ring kernel) at a width that fills
+    # neither a 32-dim warp nor a 128-dim slab
+    n2, d2, k2 = 30_000, 100, 3
+    x2 = torch.randn(n2, d2, generator=g)
+    i2 = (torch.rand(n2, generator=g) ** 4 * k2).long().clamp_(0, k2 - 1)
+    assert int(torch.bincount(i2, minlength=k2).max()) > 2 * n2 // k2
+    ref2 = torch.zeros(k2, d2).scatter_add_(0, i2.reshape(-1, 1).expand(-1, d2).contiguous(), x2)
+    c, s = ops.code_stats(x2.unsqueeze(0).to(dev), i2.unsqueeze(0).to(dev), k2, True)
+    assert torch.equal(c.cpu(), torch.bincount(i2, minlength=k2)) and torch.equal(s.cpu(), ref2)
     # many images (NCHW): whole-image groups per pass
     xi = torch.randn(40, 256, 4096, generator=g)                                  # 40 images x 4 MiB
     ii = torch.randint(0, k, (40, 4096), generator=g)

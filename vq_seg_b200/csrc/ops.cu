@@ -495,10 +495,8 @@ __global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __
 // Packed rows (sD == 1, B == 1): one warp per (code, 128-dim slab), float4 per lane, 16 rows in flight (the row
 // ids of the next batch are fetched lane-parallel and broadcast with shuffles).  The chain of a code is
 // inherently sequential (that is what makes it bit-exact), so the critical path is max_k count[k] * latency / 16.
-// `big_counts` (optional, with `big_thr`): codes holding more than big_thr rows are summed by FOUR warps of 32 dims each
-// (one float per lane, 32 rows in flight) instead of one warp of 128 dims -- a code's chain is as long as its cluster,
-// and skewed clusterings (k-means on real features: a few codes own most rows) are bounded by the longest chain.  The
-// grid then carries four blocks per eight (code, slab) pairs; blocks 1-3 exit at once unless one of their codes is big.
+// `big_counts` (optional, with `big_thr`): codes holding more than big_thr rows are left to
+// stats_ordered_sum_big_kernel below.
 __global__ void __launch_bounds__(256) stats_ordered_sum_rows_kernel(const float* __restrict__ x, long long row_stride,
                                                                      int D, const int* __restrict__ perm,
                                                                      const long long* __restrict__ code_start, int K,
@@ -507,20 +505,12 @@ __global__ void __launch_bounds__(256) stats_ordered_sum_rows_kernel(const float
                                                                      unsigned long long big_thr) {
   const int slabs = (D + 127) / 128;
   const int lane = threadIdx.x & 31;
-  const int nsub = big_counts ? 4 : 1;
-  const int sub = (int)(blockIdx.x % nsub);
-  const long long wid = (long long)(blockIdx.x / nsub) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= (long long)K * slabs) return;
-  const int k = (int)(wid / slabs);
-  const bool big = big_counts && big_counts[k] > big_thr;
-  if (!big && sub != 0) return;
-  const int d = (int)(wid % slabs) * 128 + (big ? 32 * sub + lane : 4 * lane);
+  const int k = (int)(wid / slabs), d = (int)(wid % slabs) * 128 + 4 * lane;
+  if (big_counts && big_counts[k] > big_thr) return;
   const bool act = d < D;                       // D % 4 == 0 is guaranteed by the launcher
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (act) {
-    if (big) s.x = sums[(long long)k * D + d];
-    else s = *reinterpret_cast<const float4*>(sums + (long long)k * D + d);
-  }
+  float4 s = act ? *reinterpret_cast<const float4*>(sums + (long long)k * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float* xd = x + (act ? d : 0);
   // n_chunks > 1: the (chunk, code) segments of this code one after the other (packed rows of a flat array: the row
   // ranges are visited in order by every warp, which keeps the accesses of the whole grid within a few ranges)
@@ -540,34 +530,22 @@ __global__ void __launch_bounds__(256) stats_ordered_sum_rows_kernel(const float
       const long long jn = j + 32;
       nxt = (jn + lane < end) ? __ldg(perm + jn + lane) : 0;
       const int cnt = (int)min((long long)32, end - j);
-      // UNCONDITIONAL loads (rows past the end re-read the last valid row and are simply not added): with a
-      // predicate on the load the compiler fuses it with the predicated add below and the loads serialise
-      if (big) {
-        float v[32];
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const int r = __shfl_sync(0xffffffffu, ids, min(u, cnt - 1));
-          v[u] = __ldg(xd + (long long)r * row_stride);
+      for (int h = 0; h < 2; ++h) {
+        if (16 * h >= cnt) break;
+        float4 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          // UNCONDITIONAL loads (rows past the end re-read the last valid row and are simply not added): with a
+          // predicate on the load the compiler fuses it with the predicated add below and the 16 loads serialise
+          const int r = __shfl_sync(0xffffffffu, ids, min(16 * h + u, cnt - 1));
+          v[u] = __ldg(reinterpret_cast<const float4*>(xd + (long long)r * row_stride));
         }
 #pragma unroll
-        for (int u = 0; u < 32; ++u)
-          if (u < cnt) s.x = __fadd_rn(s.x, v[u]);
-      } else {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (16 * h >= cnt) break;
-          float4 v[16];
-#pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int r = __shfl_sync(0xffffffffu, ids, min(16 * h + u, cnt - 1));
-            v[u] = __ldg(reinterpret_cast<const float4*>(xd + (long long)r * row_stride));
-          }
-#pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            if (16 * h + u < cnt) {
-              s.x = __fadd_rn(s.x, v[u].x); s.y = __fadd_rn(s.y, v[u].y);
-              s.z = __fadd_rn(s.z, v[u].z); s.w = __fadd_rn(s.w, v[u].w);
-            }
+        for (int u = 0; u < 16; ++u) {
+          if (16 * h + u < cnt) {
+            s.x = __fadd_rn(s.x, v[u].x); s.y = __fadd_rn(s.y, v[u].y);
+            s.z = __fadd_rn(s.z, v[u].z); s.w = __fadd_rn(s.w, v[u].w);
           }
         }
       }
@@ -575,10 +553,96 @@ __global__ void __launch_bounds__(256) stats_ordered_sum_rows_kernel(const float
     }
     beg = nbeg; end = nend; nxt = nfirst;
   }
-  if (act) {
-    if (big) sums[(long long)k * D + d] = s.x;
-    else *reinterpret_cast<float4*>(sums + (long long)k * D + d) = s;
+  if (act) *reinterpret_cast<float4*>(sums + (long long)k * D + d) = s;
+}
+
+// Big clusters (more than big_thr rows): a code's (k, d) chains are as long as its cluster and strictly sequential, so
+// what bounds them is how fast ONE warp gets through the rows -- 16 rows in flight in registers above, i.e. ~13-25 rows
+// per microsecond of memory latency.  Here a warp owns 32 dims of one big code and streams its rows through a
+// shared-memory ring with 16-byte cp.async (4-byte requests issue too slowly): sixteen groups of up to 32 rows (128 B
+// each) in flight, the row ids themselves requested thirty-two groups ahead; the adds run out of shared memory in row
+// order.  One warp per block: four warps on one SM ran at a quarter of the rate each.  Measured (10 M x 512, one cluster
+// holding 5-50 % of the rows): 85-100 rows/us per chain against 25-30 before; ncu: memory stalls are gone (long
+// scoreboard 2 % of samples), the warp is bound by its own ~180 instructions per 32 rows at ~4 cycles each.
+constexpr int kBigGroups = 16, kBigIdsAhead = 32;
+struct __align__(16) BigWarpSmem { float rows[kBigGroups][32][32]; int ids[kBigIdsAhead][32]; int cnt[kBigIdsAhead]; };
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__global__ void __launch_bounds__(32) stats_ordered_sum_big_kernel(const float* __restrict__ x, long long row_stride, int D,
+                                                                    const int* __restrict__ perm,
+                                                                    const long long* __restrict__ seg_start, int K,
+                                                                    float* __restrict__ sums, int n_chunks,
+                                                                    const unsigned long long* __restrict__ counts,
+                                                                    unsigned long long big_thr) {
+  extern __shared__ __align__(16) unsigned char big_smem[];
+  const int lane = threadIdx.x;
+  const int slabs = (D + 31) / 32;
+  const int k = (int)(blockIdx.x / slabs);
+  if (!(counts[k] > big_thr)) return;
+  const int d0 = (int)(blockIdx.x % slabs) * 32;
+  const int d = d0 + lane;
+  const bool act = d < D;
+  BigWarpSmem& sm = *reinterpret_cast<BigWarpSmem*>(big_smem);
+  const float* xd = x + (act ? d : 0);
+  float s = act ? sums[(long long)k * D + d] : 0.f;
+  // generator of id vectors: walks this code's (chunk, code) segments in order, up to 32 rows per vector
+  int gc = 0;
+  long long gj = seg_start[k], gend = seg_start[k + 1], nb = 0, ne = 0;
+  if (n_chunks > 1) { nb = __ldg(seg_start + (long long)K + k); ne = __ldg(seg_start + (long long)K + k + 1); }
+  auto generate = [&](int v) {
+    while (gj >= gend && gc + 1 < n_chunks) {
+      ++gc; gj = nb; gend = ne;
+      if (gc + 1 < n_chunks) { nb = __ldg(seg_start + (long long)(gc + 1) * K + k); ne = __ldg(seg_start + (long long)(gc + 1) * K + k + 1); }
+    }
+    const int cnt = (int)min((long long)32, gend - gj);
+    if (lane < cnt) cp_async4(&sm.ids[v % kBigIdsAhead][lane], perm + gj + lane);
+    if (lane == 0) sm.cnt[v % kBigIdsAhead] = cnt;
+    gj += cnt;
+  };
+  // a row's 32-dim segment is 128 B = eight 16-byte requests: lane l asks for quad l % 8 of row 4 i + l / 8.
+  // (Tried: separate paths without per-row predicates for full vectors and a 32 x 32 -> 64 bit address multiply --
+  // fewer instructions, yet 86 rows/us against 98: kept the plain form.)
+  const int qd = lane & 7, qr = lane >> 3;
+  const bool qact = d0 + 4 * qd < D;
+  const float* xq = x + d0 + (qact ? 4 * qd : 0);
+  auto issue_rows = [&](int v) {
+    const int cnt = sm.cnt[v % kBigIdsAhead];
+    const int my = sm.ids[v % kBigIdsAhead][lane];
+    float* dst = &sm.rows[v % kBigGroups][qr][4 * qd];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = __shfl_sync(0xffffffffu, my, 4 * i + qr);
+      if (4 * i + qr < cnt && qact) cp_async16(dst + 128 * i, xq + (long long)r * row_stride);
+    }
+  };
+  for (int v = 0; v < kBigIdsAhead; ++v) generate(v);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  for (int v = 0; v < kBigGroups; ++v) { issue_rows(v); asm volatile("cp.async.commit_group;" ::: "memory"); }
+  for (int t = 0;; ++t) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kBigGroups - 1) : "memory");   // group of vector t (rows) and t + 8 (ids) landed
+    __syncwarp();
+    const int cnt = sm.cnt[t % kBigIdsAhead];
+    if (cnt == 0) break;
+    const float* src = &sm.rows[t % kBigGroups][0][lane];
+    float v[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) v[u] = src[32 * u];
+#pragma unroll
+    for (int u = 0; u < 32; ++u)
+      if (u < cnt) s = __fadd_rn(s, v[u]);
+    __syncwarp();                                   // every lane is done with vector t's ids / cnt slots
+    issue_rows(t + kBigGroups);
+    generate(t + kBigIdsAhead);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (act) sums[(long long)k * D + d] = s;
 }
 
 // Any strides (NCHW feature maps): one warp per (code, 32-dim slab), lanes along d.
@@ -1077,10 +1141,19 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     VQSEG_LAUNCH_CHECK();
     const long long warps = K * ((D + 127) / 128);
     if (direct) {                                                  // rows in place: ONE launch walks the ranges in order
-      // (codes with more than twice the mean share of the rows, and at least 4096: four warps each)
+      // (codes with more than twice the mean share of the rows, and at least 4096, go to the big-cluster kernel)
       const unsigned long long thr = (unsigned long long)(2 * n_rows / K > 4096 ? 2 * n_rows / K : 4096);
-      stats_ordered_sum_rows_kernel<<<(unsigned)(4 * ((warps * 32 + 255) / 256)), 256, 0, st>>>(
-          x, sP, (int)D, perm, seg_start, (int)K, sums, (int)n_chunks, (const unsigned long long*)counts, thr);
+      const bool any_big = (unsigned long long)n_rows > thr;
+      stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+          x, sP, (int)D, perm, seg_start, (int)K, sums, (int)n_chunks, any_big ? (const unsigned long long*)counts : nullptr, thr);
+      VQSEG_LAUNCH_CHECK();
+      if (any_big) {
+        const size_t bsm = sizeof(BigWarpSmem);
+        static size_t bconf[kMaxDevices] = {0};
+        if (int rc = ensure_dynamic_smem(stats_ordered_sum_big_kernel, bsm, bconf)) return rc;
+        stats_ordered_sum_big_kernel<<<(unsigned)(K * ((D + 31) / 32)), 32, bsm, st>>>(
+            x, sP, (int)D, perm, seg_start, (int)K, sums, (int)n_chunks, (const unsigned long long*)counts, thr);
+      }
       VQSEG_LAUNCH_CHECK();
       return 0;
     }
