@@ -576,6 +576,13 @@ def test_code_stats_paths(dev):
     torch.testing.assert_close(s.cpu(), ref_sums, rtol=1e-5, atol=1e-5)               # atomics: order not fixed
     c, s = ops.code_stats(flat.contiguous().unsqueeze(0).to(dev), idx.reshape(1, -1).to(dev), 50, True)
     assert torch.equal(s.cpu(), ref_sums)
+    # one code owning 70 % of the pixels (the big-cluster kernel) on the NCHW view and on packed rows
+    hot = torch.where(torch.rand(2, 900, generator=g) < 0.7, torch.zeros(2, 900, dtype=torch.long), idx)
+    assert int((hot == 0).sum()) > 1024
+    ref_hot = torch.zeros(50, 96).scatter_add_(0, hot.reshape(-1, 1).expand(-1, 96).contiguous(), flat.contiguous())
+    for view in (xv, flat.contiguous().unsqueeze(0)):
+        c, s = ops.code_stats(view.to(dev), hot.reshape(view.shape[0], -1).to(dev), 50, True)
+        assert torch.equal(c.cpu(), torch.bincount(hot.reshape(-1), minlength=50)) and torch.equal(s.cpu(), ref_hot)
 
 
 def test_code_stats_chunked_large(dev):

@@ -1139,37 +1139,35 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     if (int rc = ensure_dynamic_smem(stats_scatter_kernel, smem, configured)) return rc;
     stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>((const long long*)idx, n_rows, (int)K, hist, seg_start, perm, bpc);
     VQSEG_LAUNCH_CHECK();
-    const long long warps = K * ((D + 127) / 128);
-    if (direct) {                                                  // rows in place: ONE launch walks the ranges in order
-      // (codes with more than twice the mean share of the rows, and at least 4096, go to the big-cluster kernel)
-      const unsigned long long thr = (unsigned long long)(2 * n_rows / K > 4096 ? 2 * n_rows / K : 4096);
-      const bool any_big = (unsigned long long)n_rows > thr;
-      stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-          x, sP, (int)D, perm, seg_start, (int)K, sums, (int)n_chunks, any_big ? (const unsigned long long*)counts : nullptr, thr);
+    // codes with more than twice the mean share of the rows (and at least 1024: a chain of that length already costs
+    // ~40 us through registers) go to the big-cluster kernel; `counts` is final here, so every launch decides alike
+    const unsigned long long thr = (unsigned long long)(2 * n_rows / K > 1024 ? 2 * n_rows / K : 1024);
+    const bool any_big = (unsigned long long)n_rows > thr;
+    const unsigned long long* big_counts = any_big ? (const unsigned long long*)counts : nullptr;
+    const size_t bsm = sizeof(BigWarpSmem);
+    if (any_big) {
+      static size_t bconf[kMaxDevices] = {0};
+      if (int rc = ensure_dynamic_smem(stats_ordered_sum_big_kernel, bsm, bconf)) return rc;
+    }
+    auto sum_launch = [&](const float* base, long long stride, const long long* seg, int nch) -> int {
+      const long long warps = K * ((D + 127) / 128);
+      stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(base, stride, (int)D, perm, seg, (int)K,
+                                                                                          sums, nch, big_counts, thr);
       VQSEG_LAUNCH_CHECK();
       if (any_big) {
-        const size_t bsm = sizeof(BigWarpSmem);
-        static size_t bconf[kMaxDevices] = {0};
-        if (int rc = ensure_dynamic_smem(stats_ordered_sum_big_kernel, bsm, bconf)) return rc;
-        stats_ordered_sum_big_kernel<<<(unsigned)(K * ((D + 31) / 32)), 32, bsm, st>>>(
-            x, sP, (int)D, perm, seg_start, (int)K, sums, (int)n_chunks, (const unsigned long long*)counts, thr);
+        stats_ordered_sum_big_kernel<<<(unsigned)(K * ((D + 31) / 32)), 32, bsm, st>>>(base, stride, (int)D, perm, seg, (int)K,
+                                                                                       sums, nch, big_counts, thr);
+        VQSEG_LAUNCH_CHECK();
       }
-      VQSEG_LAUNCH_CHECK();
       return 0;
-    }
-    for (long long c = 0; c < n_chunks; ++c) {
+    };
+    if (direct) return sum_launch(x, sP, seg_start, (int)n_chunks);   // rows in place: ONE launch walks the ranges in order
+    for (long long c = 0; c < n_chunks; ++c) {                        // strided (NCHW maps): pack a range, sum it
       const long long r0 = c * rows_per_chunk;
       const long long len = n_rows - r0 < rows_per_chunk ? n_rows - r0 : rows_per_chunk;
-      const float* base = x;                                          // perm holds GLOBAL row ids
-      long long stride = sP;
-      if (!direct) {                                                  // strided (NCHW maps): pack the range first
-        if (int rc = pack(r0, len)) return rc;
-        base = scratch - r0 * D;                                      // (only rows [r0, r0 + len) are ever addressed)
-        stride = D;
-      }
-      stats_ordered_sum_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(base, stride, (int)D, perm,
-                                                                                          seg_start + c * K, (int)K, sums, 1, nullptr, 0ull);
-      VQSEG_LAUNCH_CHECK();
+      if (int rc = pack(r0, len)) return rc;
+      // perm holds GLOBAL row ids: only rows [r0, r0 + len) are ever addressed through the shifted base
+      if (int rc = sum_launch(scratch - r0 * D, D, seg_start + c * K, 1)) return rc;
     }
     return 0;
   }
