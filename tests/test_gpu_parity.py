@@ -576,6 +576,11 @@ def test_code_stats_paths(dev):
     torch.testing.assert_close(s.cpu(), ref_sums, rtol=1e-5, atol=1e-5)               # atomics: order not fixed
     c, s = ops.code_stats(flat.contiguous().unsqueeze(0).to(dev), idx.reshape(1, -1).to(dev), 50, True)
     assert torch.equal(s.cpu(), ref_sums)
+    # more codes than the counter table of the fast scatter holds (the turn-taking scatter), more than one scan tile
+    wide = torch.randint(0, 5000, (2, 900), generator=g)
+    ref_wide = torch.zeros(5000, 96).scatter_add_(0, wide.reshape(-1, 1).expand(-1, 96).contiguous(), flat.contiguous())
+    c, s = ops.code_stats(xv.to(dev), wide.to(dev), 5000, True)
+    assert torch.equal(c.cpu(), torch.bincount(wide.reshape(-1), minlength=5000)) and torch.equal(s.cpu(), ref_wide)
     # one code owning 70 % of the pixels (the big-cluster kernel) on the NCHW view and on packed rows
     hot = torch.where(torch.rand(2, 900, generator=g) < 0.7, torch.zeros(2, 900, dtype=torch.long), idx)
     assert int((hot == 0).sum()) > 1024
@@ -609,6 +614,12 @@ def test_code_stats_chunked_large(dev):
     ref2 = torch.zeros(k2, d2).scatter_add_(0, i2.reshape(-1, 1).expand(-1, d2).contiguous(), x2)
     c, s = ops.code_stats(x2.unsqueeze(0).to(dev), i2.unsqueeze(0).to(dev), k2, True)
     assert torch.equal(c.cpu(), torch.bincount(i2, minlength=k2)) and torch.equal(s.cpu(), ref2)
+    # sorted assignments: the big code fills the first row ranges and is absent from the last one (empty segments on
+    # the big-cluster path), the other codes live only in the later ranges (empty leading segments on the plain path)
+    i3 = torch.cat([torch.zeros(54_000, dtype=torch.long), torch.randint(1, 8, (n - 54_000,), generator=g).sort().values])
+    ref3 = torch.zeros(8, d).scatter_add_(0, i3.reshape(-1, 1).expand(-1, d).contiguous(), x)
+    c, s = ops.code_stats(x.unsqueeze(0).to(dev), i3.unsqueeze(0).to(dev), 8, True)
+    assert torch.equal(c.cpu(), torch.bincount(i3, minlength=8)) and torch.equal(s.cpu(), ref3)
     # many images (NCHW): whole-image groups per pass
     xi = torch.randn(40, 256, 4096, generator=g)                                  # 40 images x 4 MiB
     ii = torch.randint(0, k, (40, 4096), generator=g)

@@ -416,49 +416,99 @@ __global__ void __launch_bounds__(256) stats_scan_chunks_kernel(int* __restrict_
   const int c = (int)(t / K), k = (int)(t % K);
   const int b1 = min(nblk, (c + 1) * blocks_per_chunk);
   long long run = 0;
-  for (int b = c * blocks_per_chunk; b < b1; ++b) {
-    const int h = hist[(long long)b * K + k];
-    hist[(long long)b * K + k] = (int)run;
-    run += h;
+  for (int b0 = c * blocks_per_chunk; b0 < b1; b0 += 8) {        // eight loads in flight, then the dependent stores
+    int h[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) h[u] = b0 + u < b1 ? hist[(long long)(b0 + u) * K + k] : 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (b0 + u < b1) { hist[(long long)(b0 + u) * K + k] = (int)run; run += h[u]; }
   }
   seg_total[t] = run;
   if (counts && run) atomicAdd(counts + k, (unsigned long long)run);
 }
-// (3) exclusive scan over codes / (chunk, code) segments (single block): warp w owns a contiguous range, lanes read
-// it coalesced -- range totals first, then 32-element tiles with a shuffle scan and a running carry (the strided
-// per-thread version took 350 us for config 4's 313 k segments)
-__global__ void __launch_bounds__(1024) stats_scan_codes_kernel(const long long* __restrict__ code_total, int K,
-                                                                long long* __restrict__ code_start /* K+1 */) {
+// (3) exclusive scan over codes / (chunk, code) segments: tiles of 4096 elements, one block each -- tile totals first
+// (skipped for a single tile), then every block adds up the totals of the tiles before it and scans its own tile
+// (a single block walking config 4's 313 k segments took 160-350 us)
+constexpr int kScanTile = 4096;
+__global__ void __launch_bounds__(1024) stats_scan_totals_kernel(const long long* __restrict__ in, long long L,
+                                                                 long long* __restrict__ tile_tot) {
   __shared__ long long s_warp[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long R = (((long long)K + 31) / 32 + 31) / 32 * 32;          // elements per warp, a multiple of 32
-  const long long beg = min((long long)K, warp * R), end = min((long long)K, beg + R);
+  const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x;
   long long s = 0;
-#pragma unroll 4
-  for (long long i = beg + lane; i < end; i += 32) s += code_total[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += base + 1024 * i < L ? in[base + 1024 * i] : 0;
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) s_warp[warp] = s;
   __syncthreads();
   if (warp == 0) {
-    const long long v = s_warp[lane];
-    long long inc = v;
+    s = s_warp[lane];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    s_warp[lane] = inc - v;
-    if (lane == 31) code_start[K] = inc;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) tile_tot[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(1024) stats_scan_codes_kernel(const long long* __restrict__ in, long long L,
+                                                                long long* __restrict__ out /* L + 1 */,
+                                                                const long long* __restrict__ tile_tot) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // offset of this tile = the totals of the tiles before it
+  long long o = 0;
+  for (long long b = threadIdx.x; b < (long long)blockIdx.x; b += 1024) o += tile_tot[b];
+#pragma unroll
+  for (int w = 16; w; w >>= 1) o += __shfl_xor_sync(0xffffffffu, o, w);
+  if (lane == 0) s_warp[warp] = o;
+  __syncthreads();
+  if (warp == 0) {
+    o = s_warp[lane];
+#pragma unroll
+    for (int w = 16; w; w >>= 1) o += __shfl_xor_sync(0xffffffffu, o, w);
+    if (lane == 0) s_off = o;
   }
   __syncthreads();
-  long long run = s_warp[warp];
-#pragma unroll 4
-  for (long long base = beg; base < end; base += 32) {
-    const long long v = base + lane < end ? code_total[base + lane] : 0;
-    long long inc = v;
+  const long long off = s_off;
+  // thread t scans elements 4t .. 4t+3 of the tile
+  const long long base = (long long)blockIdx.x * kScanTile + 4 * threadIdx.x;
+  long long v[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (base + lane < end) code_start[base + lane] = run + inc - v;
-    run += __shfl_sync(0xffffffffu, inc, 31);
+  for (int i = 0; i < 4; ++i) v[i] = base + i < L ? in[base + i] : 0;
+  const long long t = v[0] + v[1] + v[2] + v[3];
+  long long inc = t;
+#pragma unroll
+  for (int w = 1; w < 32; w <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, inc, w); if (lane >= w) inc += u; }
+  __syncthreads();                                  // (s_warp is reused)
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const long long wv = s_warp[lane];
+    long long winc = wv;
+#pragma unroll
+    for (int w = 1; w < 32; w <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, winc, w); if (lane >= w) winc += u; }
+    s_warp[lane] = winc - wv;
+    if (lane == 31 && blockIdx.x == gridDim.x - 1) out[L] = off + winc;
   }
+  __syncthreads();
+  long long run = off + s_warp[warp] + inc - t;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (base + i < L) out[base + i] = run;
+    run += v[i];
+  }
+}
+// launcher: `scratch` holds one long long per tile (callers lend the front of `perm`, which the scatter fills later)
+static int launch_scan_codes(const long long* in, long long L, long long* out, long long* scratch, cudaStream_t st) {
+  const long long tiles = (L + kScanTile - 1) / kScanTile;
+  if (tiles > 1) {
+    stats_scan_totals_kernel<<<(unsigned)tiles, 1024, 0, st>>>(in, L, scratch);
+    VQSEG_LAUNCH_CHECK();
+  }
+  stats_scan_codes_kernel<<<(unsigned)tiles, 1024, 0, st>>>(in, L, out, scratch);
+  VQSEG_LAUNCH_CHECK();
+  return 0;
 }
 // (4) stable scatter: perm[code_start[k] + hist[blk][k] + rank_in_block] = n
 // `blocks_per_chunk` > 0: the sort key is (chunk of blocks_per_chunk ranking blocks, code): code_start then holds one
@@ -480,16 +530,49 @@ __global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __
   const int rank_in_warp = __popc(peers & ((1u << lane) - 1));
   const int group = __popc(peers);
   const bool leader = rank_in_warp == 0;
+  // (the global reads happen BEFORE the turns: inside them their latency was paid 32 times per block, 520 us of
+  // config 4's ordered statistics)
+  const long long off = valid ? code_start[kk] + hist[(long long)blockIdx.x * K + kk] + rank_in_warp : 0;
+  int base = 0;
   for (int w = 0; w < 32; ++w) {          // warps take turns in row order -> stable
     if (warp == w && valid) {
-      int base = s_run[kk];
+      base = s_run[kk];
       __syncwarp(peers);
       if (leader) s_run[kk] = base + group;
-      long long pos = code_start[kk] + hist[(long long)blockIdx.x * K + kk] + base + rank_in_warp;
-      perm[pos] = (int)n;
     }
     __syncthreads();
   }
+  if (valid) perm[off + base] = (int)n;
+}
+// (4b) the same without the turns, for K up to ~3000: every warp leaves its per-code group sizes in its own row of a
+// [32 warps][K] table of 16-bit counters, one pass per code turns the table into exclusive prefixes over the warps
+// (the turn-taking version spent 500 us on config 4's 10 M rows: 32 block-wide barriers per 1024 rows)
+__global__ void __launch_bounds__(1024) stats_scatter_table_kernel(const long long* __restrict__ idx, long long n_rows, int K,
+                                                                   const int* __restrict__ hist,
+                                                                   const long long* __restrict__ code_start,
+                                                                   int* __restrict__ perm, int blocks_per_chunk) {
+  if (blocks_per_chunk > 0) code_start += (long long)(blockIdx.x / blocks_per_chunk) * K;
+  extern __shared__ unsigned short s_cnt[];            // [32][Ke], Ke = K rounded up to even
+  const int Ke = (K + 1) & ~1;
+  for (int i = threadIdx.x; i < 16 * Ke; i += blockDim.x) reinterpret_cast<uint32_t*>(s_cnt)[i] = 0u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n = (long long)blockIdx.x * kSortBlock + threadIdx.x;
+  long long k = n < n_rows ? idx[n] : -1;
+  const bool valid = k >= 0 && k < K;
+  const int kk = valid ? (int)k : -1 - lane;            // unique key for invalid lanes
+  const unsigned peers = __match_any_sync(0xffffffffu, kk);
+  const int rank_in_warp = __popc(peers & ((1u << lane) - 1));
+  const long long off = valid ? code_start[kk] + hist[(long long)blockIdx.x * K + kk] + rank_in_warp : 0;
+  __syncthreads();
+  if (valid && rank_in_warp == 0) s_cnt[warp * Ke + kk] = (unsigned short)__popc(peers);
+  __syncthreads();
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    unsigned run = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { const unsigned v = s_cnt[w * Ke + c]; s_cnt[w * Ke + c] = (unsigned short)run; run += v; }
+  }
+  __syncthreads();
+  if (valid) perm[off + s_cnt[warp * Ke + kk]] = (int)n;
 }
 // (5) ordered per-code sums: ascending-row fp32 chain per (k, d).
 // Packed rows (sD == 1, B == 1): one warp per (code, 128-dim slab), float4 per lane, 16 rows in flight (the row
@@ -898,6 +981,22 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(Rows x, long long row0, 
   }
 }
 
+static int launch_scatter(const long long* idx, long long n_rows, int K, const int* hist, const long long* code_start,
+                          int* perm, int blocks_per_chunk, long long nblk, cudaStream_t st) {
+  const size_t table = (size_t)32 * ((K + 1) & ~1) * sizeof(unsigned short);
+  if (table <= 96 * 1024) {
+    static size_t tconf[kMaxDevices] = {0};
+    if (int rc = ensure_dynamic_smem(stats_scatter_table_kernel, table, tconf)) return rc;
+    stats_scatter_table_kernel<<<(unsigned)nblk, kSortBlock, table, st>>>(idx, n_rows, K, hist, code_start, perm, blocks_per_chunk);
+  } else {
+    const size_t smem = (size_t)K * sizeof(int);
+    static size_t configured[kMaxDevices] = {0};
+    if (int rc = ensure_dynamic_smem(stats_scatter_kernel, smem, configured)) return rc;
+    stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>(idx, n_rows, K, hist, code_start, perm, blocks_per_chunk);
+  }
+  VQSEG_LAUNCH_CHECK();
+  return 0;
+}
 static int stats_det_range(const float* x, long long B, long long P, long long D, long long sB, long long sP, long long sD,
                            const int64_t* idx, long long K, int64_t* counts, float* sums, void* ws, cudaStream_t st) {
   const long long n_rows = B * P;
@@ -915,13 +1014,8 @@ static int stats_det_range(const float* x, long long B, long long P, long long D
   stats_scan_blocks_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(hist, (int)nblk, (int)K,
                                                                          (unsigned long long*)counts, code_total);
   VQSEG_LAUNCH_CHECK();
-  stats_scan_codes_kernel<<<1, 1024, 0, st>>>(code_total, (int)K, code_start);
-  VQSEG_LAUNCH_CHECK();
-  size_t smem = (size_t)K * sizeof(int);
-  static size_t configured[kMaxDevices] = {0};
-  if (int rc = ensure_dynamic_smem(stats_scatter_kernel, smem, configured)) return rc;
-  stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>((const long long*)idx, n_rows, (int)K, hist, code_start, perm);
-  VQSEG_LAUNCH_CHECK();
+  if (int rc = launch_scan_codes(code_total, K, code_start, reinterpret_cast<long long*>(perm), st)) return rc;
+  if (int rc = launch_scatter((const long long*)idx, n_rows, (int)K, hist, code_start, perm, 0, nblk, st)) return rc;
   const bool packed = B == 1 && sD == 1 && D % 4 == 0 && sP % 4 == 0 &&
                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0;
   if (packed) {
@@ -1132,13 +1226,8 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
                                                                                     (unsigned long long*)counts, seg_total);
     VQSEG_LAUNCH_CHECK();
     if (n_chunks * K >= (1ll << 31)) return VQSEG_EUNSUPPORTED;
-    stats_scan_codes_kernel<<<1, 1024, 0, st>>>(seg_total, (int)(n_chunks * K), seg_start);
-    VQSEG_LAUNCH_CHECK();
-    const size_t smem = (size_t)K * sizeof(int);
-    static size_t configured[kMaxDevices] = {0};
-    if (int rc = ensure_dynamic_smem(stats_scatter_kernel, smem, configured)) return rc;
-    stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>((const long long*)idx, n_rows, (int)K, hist, seg_start, perm, bpc);
-    VQSEG_LAUNCH_CHECK();
+    if (int rc = launch_scan_codes(seg_total, n_chunks * K, seg_start, reinterpret_cast<long long*>(perm), st)) return rc;
+    if (int rc = launch_scatter((const long long*)idx, n_rows, (int)K, hist, seg_start, perm, bpc, nblk, st)) return rc;
     // codes with more than twice the mean share of the rows (and at least 1024: a chain of that length already costs
     // ~40 us through registers) go to the big-cluster kernel; `counts` is final here, so every launch decides alike
     const unsigned long long thr = (unsigned long long)(2 * n_rows / K > 1024 ? 2 * n_rows / K : 1024);
