@@ -620,6 +620,19 @@ def test_code_stats_chunked_large(dev):
     ref3 = torch.zeros(8, d).scatter_add_(0, i3.reshape(-1, 1).expand(-1, d).contiguous(), x)
     c, s = ops.code_stats(x.unsqueeze(0).to(dev), i3.unsqueeze(0).to(dev), 8, True)
     assert torch.equal(c.cpu(), torch.bincount(i3, minlength=8)) and torch.equal(s.cpu(), ref3)
+    # >= 2^18 packed rows, unordered: the sorted-window kernel (one RED per code met in a window of 64 sorted rows);
+    # a hot code, a width that is not a multiple of 128, some rows without a code
+    n4, d4, k4 = 300_000, 200, 100
+    x4 = torch.randn(n4, d4, generator=g)
+    i4 = (torch.rand(n4, generator=g) ** 3 * k4).long().clamp_(0, k4 - 1)
+    i4[::1000] = -1
+    keep = i4 >= 0
+    ref4 = torch.zeros(k4, d4).scatter_add_(0, i4[keep].reshape(-1, 1).expand(-1, d4).contiguous(), x4[keep])
+    c, s = ops.code_stats(x4.unsqueeze(0).to(dev), i4.unsqueeze(0).to(dev), k4, False)
+    assert torch.equal(c.cpu(), torch.bincount(i4[keep], minlength=k4))
+    torch.testing.assert_close(s.cpu(), ref4, rtol=2e-5, atol=5e-3)
+    c, s = ops.code_stats(x4.unsqueeze(0).to(dev), i4.unsqueeze(0).to(dev), k4, True)
+    assert torch.equal(c.cpu(), torch.bincount(i4[keep], minlength=k4)) and torch.equal(s.cpu(), ref4)
     # many images (NCHW): whole-image groups per pass
     xi = torch.randn(40, 256, 4096, generator=g)                                  # 40 images x 4 MiB
     ii = torch.randint(0, k, (40, 4096), generator=g)

@@ -516,7 +516,8 @@ static int launch_scan_codes(const long long* in, long long L, long long* out, l
 __global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __restrict__ idx, long long n_rows, int K,
                                                              const int* __restrict__ hist,
                                                              const long long* __restrict__ code_start,
-                                                             int* __restrict__ perm, int blocks_per_chunk = 0) {
+                                                             int* __restrict__ perm, int blocks_per_chunk = 0,
+                                                             int* __restrict__ pcode = nullptr) {
   if (blocks_per_chunk > 0) code_start += (long long)(blockIdx.x / blocks_per_chunk) * K;
   extern __shared__ int s_run[];    // K running counters
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_run[k] = 0;
@@ -542,7 +543,10 @@ __global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __
     }
     __syncthreads();
   }
-  if (valid) perm[off + base] = (int)n;
+  if (valid) {
+    perm[off + base] = (int)n;
+    if (pcode) pcode[off + base] = kk;
+  }
 }
 // (4b) the same without the turns, for K up to ~3000: every warp leaves its per-code group sizes in its own row of a
 // [32 warps][K] table of 16-bit counters, one pass per code turns the table into exclusive prefixes over the warps
@@ -550,7 +554,8 @@ __global__ void __launch_bounds__(1024) stats_scatter_kernel(const long long* __
 __global__ void __launch_bounds__(1024) stats_scatter_table_kernel(const long long* __restrict__ idx, long long n_rows, int K,
                                                                    const int* __restrict__ hist,
                                                                    const long long* __restrict__ code_start,
-                                                                   int* __restrict__ perm, int blocks_per_chunk) {
+                                                                   int* __restrict__ perm, int blocks_per_chunk,
+                                                                   int* __restrict__ pcode) {
   if (blocks_per_chunk > 0) code_start += (long long)(blockIdx.x / blocks_per_chunk) * K;
   extern __shared__ unsigned short s_cnt[];            // [32][Ke], Ke = K rounded up to even
   const int Ke = (K + 1) & ~1;
@@ -572,7 +577,11 @@ __global__ void __launch_bounds__(1024) stats_scatter_table_kernel(const long lo
     for (int w = 0; w < 32; ++w) { const unsigned v = s_cnt[w * Ke + c]; s_cnt[w * Ke + c] = (unsigned short)run; run += v; }
   }
   __syncthreads();
-  if (valid) perm[off + s_cnt[warp * Ke + kk]] = (int)n;
+  if (valid) {
+    const long long pos = off + s_cnt[warp * Ke + kk];
+    perm[pos] = (int)n;
+    if (pcode) pcode[pos] = kk;                  // (the unordered sorted-sum kernel reads the code beside the row id)
+  }
 }
 // (5) ordered per-code sums: ascending-row fp32 chain per (k, d).
 // Packed rows (sD == 1, B == 1): one warp per (code, 128-dim slab), float4 per lane, 16 rows in flight (the row
@@ -726,6 +735,58 @@ __global__ void __launch_bounds__(32) stats_ordered_sum_big_kernel(const float* 
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (act) sums[(long long)k * D + d] = s;
+}
+
+// Unordered statistics of LARGE packed inputs (deterministic = 0): the same counting sort, then every warp sums a
+// window of 64 consecutive sorted positions x one 128-dim slab in registers and issues one vector RED per code it meets
+// (two or three per window instead of one per row).  Rows of one code are spread over as many warps as the code has
+// windows, so neither a hot code (same-address atomics: 44 ms for a code owning half of config 4's rows) nor a long
+// chain exists: 3.3-3.5 ms whatever the clustering, against 4.6-5.0 ms for one RED per row.
+constexpr int kSortedWin = 64;
+constexpr long long kSortedMinRows = 1ll << 18;
+__global__ void __launch_bounds__(256) stats_sorted_sum_kernel(const float* __restrict__ x, long long row_stride, int D,
+                                                               const int* __restrict__ perm, const int* __restrict__ pcode,
+                                                               const long long* __restrict__ total_ptr,
+                                                               float* __restrict__ sums) {
+  const int slabs = (D + 127) / 128;
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = *total_ptr;
+  const long long j0 = (wid / slabs) * kSortedWin;
+  if (j0 >= total) return;
+  const long long j1 = min(j0 + kSortedWin, total);
+  const int d = (int)(wid % slabs) * 128 + 4 * lane;
+  const bool act = d < D;
+  const float* xd = x + (act ? d : 0);
+  int cur = -1;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto flush = [&]() {
+    if (cur >= 0 && act) atomicAdd(reinterpret_cast<float4*>(sums + (long long)cur * D + d), acc);
+  };
+  for (long long jb = j0; jb < j1; jb += 32) {
+    const int cnt = (int)min((long long)32, j1 - jb);
+    const int ids = lane < cnt ? __ldg(perm + jb + lane) : 0;
+    const int cds = lane < cnt ? __ldg(pcode + jb + lane) : -1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (16 * h >= cnt) break;
+      float4 v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {                     // unconditional loads (see stats_ordered_sum_rows_kernel)
+        const int r = __shfl_sync(0xffffffffu, ids, min(16 * h + u, cnt - 1));
+        v[u] = __ldg(reinterpret_cast<const float4*>(xd + (long long)r * row_stride));
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (16 * h + u < cnt) {
+          const int c = __shfl_sync(0xffffffffu, cds, 16 * h + u);
+          if (c != cur) { flush(); cur = c; acc = make_float4(0.f, 0.f, 0.f, 0.f); }
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        }
+      }
+    }
+  }
+  flush();
 }
 
 // Any strides (NCHW feature maps): one warp per (code, 32-dim slab), lanes along d.
@@ -982,17 +1043,17 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(Rows x, long long row0, 
 }
 
 static int launch_scatter(const long long* idx, long long n_rows, int K, const int* hist, const long long* code_start,
-                          int* perm, int blocks_per_chunk, long long nblk, cudaStream_t st) {
+                          int* perm, int blocks_per_chunk, long long nblk, cudaStream_t st, int* pcode = nullptr) {
   const size_t table = (size_t)32 * ((K + 1) & ~1) * sizeof(unsigned short);
   if (table <= 96 * 1024) {
     static size_t tconf[kMaxDevices] = {0};
     if (int rc = ensure_dynamic_smem(stats_scatter_table_kernel, table, tconf)) return rc;
-    stats_scatter_table_kernel<<<(unsigned)nblk, kSortBlock, table, st>>>(idx, n_rows, K, hist, code_start, perm, blocks_per_chunk);
+    stats_scatter_table_kernel<<<(unsigned)nblk, kSortBlock, table, st>>>(idx, n_rows, K, hist, code_start, perm, blocks_per_chunk, pcode);
   } else {
     const size_t smem = (size_t)K * sizeof(int);
     static size_t configured[kMaxDevices] = {0};
     if (int rc = ensure_dynamic_smem(stats_scatter_kernel, smem, configured)) return rc;
-    stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>(idx, n_rows, K, hist, code_start, perm, blocks_per_chunk);
+    stats_scatter_kernel<<<(unsigned)nblk, kSortBlock, smem, st>>>(idx, n_rows, K, hist, code_start, perm, blocks_per_chunk, pcode);
   }
   VQSEG_LAUNCH_CHECK();
   return 0;
@@ -1139,8 +1200,12 @@ static long long stats_rows_per_chunk(long long D) {
   long long r = (64ll << 20) / row_bytes;
   return r < 4096 ? 4096 : r / 1024 * 1024;
 }
+static bool stats_sorted_eligible(long long n_rows, long long D, long long K) {
+  const long long n_chunks = (n_rows + stats_rows_per_chunk(D) - 1) / stats_rows_per_chunk(D);
+  return n_rows >= kSortedMinRows && K * (long long)sizeof(int) <= 200 * 1024 && n_chunks * K < (1ll << 31);
+}
 static size_t stats_sort_ws_bytes(long long n_rows, long long D, long long K, int deterministic) {
-  if (!deterministic) return 256;
+  if (!deterministic && !stats_sorted_eligible(n_rows, D, K)) return 256;
   long long nblk = (n_rows + kSortBlock - 1) / kSortBlock;
   const long long n_chunks = (n_rows + stats_rows_per_chunk(D) - 1) / stats_rows_per_chunk(D);
   size_t b = 0;
@@ -1148,6 +1213,7 @@ static size_t stats_sort_ws_bytes(long long n_rows, long long D, long long K, in
   b += round_up(n_chunks * K * sizeof(long long), 256);             // segment sizes per (chunk, code)
   b += round_up((n_chunks * K + 1) * sizeof(long long), 256);       // segment starts
   b += round_up(n_rows * sizeof(int), 256);                         // perm
+  if (!deterministic) b += round_up(n_rows * sizeof(int), 256);     // the code of every sorted position (unordered sums)
   return b + 256;
 }
 size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int deterministic) {
@@ -1178,7 +1244,8 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     VQSEG_LAUNCH_CHECK();
     return 0;
   };
-  if (!deterministic) {
+  const bool sorted_fast = !deterministic && direct && stats_sorted_eligible(n_rows, D, K);
+  if (!deterministic && !sorted_fast) {
     auto rows_kernel = [&](const float* rows, long long stride, long long len, const int64_t* ix) -> int {
       code_stats_atomic_rows_kernel<<<grid_for(len * 32, 256, 16), 256, 0, st>>>(rows, stride, len, (int)D, (const long long*)ix,
                                                                                  (int)K, (unsigned long long*)counts, sums);
@@ -1217,7 +1284,8 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     int* hist = (int*)p;                    p += round_up(nblk * K * sizeof(int), 256);
     long long* seg_total = (long long*)p;   p += round_up(n_chunks * K * sizeof(long long), 256);
     long long* seg_start = (long long*)p;   p += round_up((n_chunks * K + 1) * sizeof(long long), 256);
-    int* perm = (int*)p;
+    int* perm = (int*)p;                    p += round_up(n_rows * sizeof(int), 256);
+    int* pcode = sorted_fast ? (int*)p : nullptr;
     cudaError_t e = cudaMemsetAsync(hist, 0, nblk * K * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     stats_hist_kernel<<<(unsigned)nblk, kSortBlock, 0, st>>>((const long long*)idx, n_rows, (int)K, hist);
@@ -1227,7 +1295,14 @@ int vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D, int64_
     VQSEG_LAUNCH_CHECK();
     if (n_chunks * K >= (1ll << 31)) return VQSEG_EUNSUPPORTED;
     if (int rc = launch_scan_codes(seg_total, n_chunks * K, seg_start, reinterpret_cast<long long*>(perm), st)) return rc;
-    if (int rc = launch_scatter((const long long*)idx, n_rows, (int)K, hist, seg_start, perm, bpc, nblk, st)) return rc;
+    if (int rc = launch_scatter((const long long*)idx, n_rows, (int)K, hist, seg_start, perm, bpc, nblk, st, pcode)) return rc;
+    if (sorted_fast) {                                                // unordered: windows of sorted positions, one RED per code met
+      const long long warps = ((n_rows + kSortedWin - 1) / kSortedWin) * ((D + 127) / 128);
+      stats_sorted_sum_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(x, sP, (int)D, perm, pcode,
+                                                                                    seg_start + n_chunks * K, sums);
+      VQSEG_LAUNCH_CHECK();
+      return 0;
+    }
     // codes with more than twice the mean share of the rows (and at least 1024: a chain of that length already costs
     // ~40 us through registers) go to the big-cluster kernel; `counts` is final here, so every launch decides alike
     const unsigned long long thr = (unsigned long long)(2 * n_rows / K > 1024 ? 2 * n_rows / K : 1024);
