@@ -4,6 +4,7 @@ vectors (produced by the live reference) and vs the CPU oracle on the same seede
 Bars (north_star): bit-exact indices and code counts; quantize / loss / gradients within 1e-5 relative
 (in fact quantize and the k-means means come out bit-exact, which the tests assert where it holds by
 construction)."""
+import itertools
 import os
 
 import pytest
@@ -857,6 +858,41 @@ def test_random_shape_fuzz(dev):
                 assert abs(mse.item() - ref) <= 1e-5 * max(ref, 1e-30), tag
         ref_idx = O.assign_euclidean(xv.cpu(), e)
         assert near_tie_ok(x.reshape(b, c, hw, 1), e, i_ex.cpu(), ref_idx), (it, b, c, hw, k)
+
+
+def test_filter_slack_over_operand_scales(dev):
+    """The filters' slack (common.cuh filter_slack) must stay a rigorous bound at every ratio of |e| to |x|: the
+    reference's default uniform(-1/K, 1/K) init against unit-scale features (|e| << |x|, where the slack is governed
+    by the few roundings at the magnitude of |x|^2), the opposite ratio, and equal scales -- every tensor-core filter
+    that takes the shape against the brute-force exact scorer, and the default-init case against the CPU reference's
+    cdist + argmin itself."""
+    from vq_seg_b200 import ops
+    g = torch.Generator().manual_seed(97)
+    algos = (ops.ALGO_AUTO, ops.ALGO_TC_STREAM, ops.ALGO_TC_PAIR, ops.ALGO_TC_TMA, ops.ALGO_TC_STREAM_PAIR)
+    undecided = {}
+    for (d, k, p), xs, es, relu in itertools.product(((256, 512, 2048), (64, 200, 1024), (512, 1024, 1024), (1024, 512, 512)),
+                                                      (1e-3, 1.0, 40.0), (1e-4, None, 1.0, 40.0), (False, True)):
+        es = 1.0 / k if es is None else es
+        x = torch.randn(2, d, p, generator=g) * xs
+        if relu:
+            x = torch.relu(x)
+        e = (torch.rand(k, d, generator=g) * 2 - 1) * es
+        xv, ed = x.to(dev).permute(0, 2, 1), e.to(dev).contiguous()
+        blob = ops.prepare_codebook(ed)
+        i_ex, c_ex = ops.assign(xv, ed, None, ops.ALGO_EXACT)
+        for algo in algos:
+            try:
+                idx, counts = ops.assign(xv, ed, blob, algo)
+            except RuntimeError as exc:
+                assert "not supported" in str(exc), exc
+                continue
+            assert torch.equal(idx, i_ex) and torch.equal(counts, c_ex), (d, k, p, xs, es, relu, algo)
+            if algo == ops.ALGO_AUTO:
+                undecided[(d, xs, es, relu)] = int(ops._last_assign_ws[:4].view(torch.int32).item()) / (2 * p)
+        if xs == 1.0 and es == 1.0 / k and d <= 256:
+            assert torch.equal(i_ex.cpu(), O.assign_euclidean(x.permute(0, 2, 1), e))
+    # the default init must not be a cliff: most rows are decided by the filter itself
+    assert undecided[(256, 1.0, 1.0 / 512, True)] < 0.25, undecided[(256, 1.0, 1.0 / 512, True)]
 
 
 def test_random_shape_fuzz_every_filter_and_metric(dev):

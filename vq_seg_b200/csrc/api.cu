@@ -319,6 +319,10 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   ea.key_out = (unsigned long long*)best_key_out; ea.code_base = code_base;
   if (!use_tc) return launch_exact(ea, n_rows, st);
 
+  // (3 nb + 9) u: nb = K-blocks of the reference chain the exact scorer restates (filter_slack, common.cuh)
+  const long long chain_len = ip ? D : D + 2;
+  const long long kb_eff = (kblock <= 0 || kblock > chain_len) ? chain_len : kblock;
+  const float slack_t2 = (float)(3 * ((chain_len + kb_eff - 1) / kb_eff) + 9) * 5.97e-8f;
   prof_record(prof_events, 0, st);
   if (kernel == 3) {
     Tc3Args t3;
@@ -329,7 +333,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     t3.n_ptiles = (t3.n_tiles + 1) / 2; t3.n_cc = n_cc; t3.n_dc = n_dc;
     t3.K = (int)K; t3.K_pad = (int)kp; t3.off_image = oi; t3.off_aug = oa; t3.off_enorm = oe;
     t3.idx_out = (long long*)idx_out; t3.counts_out = (unsigned long long*)counts_out; t3.code_base = code_base;
-    t3.force_rescore = force ? 1 : 0;
+    t3.force_rescore = force ? 1 : 0; t3.slack_t2 = slack_t2;
     t3.work = work; t3.work_count = work_count;
     t3.trace = dev_trace();
     rc = launch_assign_tc3(xr, t3, st);
@@ -353,7 +357,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     }
     t4.K = (int)K; t4.K_pad = (int)kp; t4.off_image = oi; t4.off_aug = oa; t4.off_enorm = oe;
     t4.idx_out = (long long*)idx_out; t4.counts_out = (unsigned long long*)counts_out; t4.code_base = code_base;
-    t4.force_rescore = force ? 1 : 0;
+    t4.force_rescore = force ? 1 : 0; t4.slack_t2 = slack_t2;
     t4.work = work; t4.work_count = work_count;
     t4.trace = dev_trace();
     rc = launch_assign_tc4(xr, t4, lay4, st);
@@ -363,7 +367,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
       sl.scores = part_scores; sl.norms = part_norms; sl.n_rows = n_rows; sl.K = (int)K; sl.K_pad = (int)kp; sl.D = (int)D;
       sl.blob = (const unsigned char*)blob;
       sl.idx_out = (long long*)idx_out; sl.counts_out = (unsigned long long*)counts_out; sl.code_base = code_base;
-      sl.force_rescore = force ? 1 : 0;
+      sl.force_rescore = force ? 1 : 0; sl.slack_t2 = slack_t2;
       sl.work = work; sl.work_count = work_count;
       rc = launch_shortlist(sl, st);
     }
@@ -375,7 +379,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     t2.K = (int)K; t2.K_pad = (int)kp; t2.off_image = oi; t2.off_aug = oa; t2.off_enorm = oe;
     t2.tau = 0.f;
     t2.idx_out = (long long*)idx_out; t2.counts_out = (unsigned long long*)counts_out; t2.code_base = code_base;
-    t2.force_rescore = force ? 1 : 0;
+    t2.force_rescore = force ? 1 : 0; t2.slack_t2 = slack_t2;
     t2.work = work; t2.work_count = work_count;
     t2.trace = dev_trace();
     rc = launch_assign_tc2(t2, st);
@@ -387,7 +391,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
     ta.K = (int)K;
     ta.tau = 0.f;
     ta.idx_out = (long long*)idx_out; ta.counts_out = (unsigned long long*)counts_out; ta.code_base = code_base;
-    ta.force_rescore = force ? 1 : 0;
+    ta.force_rescore = force ? 1 : 0; ta.slack_t2 = slack_t2;
     ta.work = work; ta.work_count = work_count;
     ta.trace = dev_trace();
     rc = launch_assign_tc(ta, st);

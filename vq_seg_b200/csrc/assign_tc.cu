@@ -250,13 +250,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) assign_tc_kernel(TcArgs a) {
           // all A chunks of this tile's first unit are in: the row's |x|^2 and |fp16(x)-x|^2 have been published
           const float2 nr = reinterpret_cast<const float2*>(xsq)[(t & (kXsqBufs - 1)) * kTileM + r];
           const float xn = sqrtf(nr.x) * 1.0001f, dn = sqrtf(nr.y) * 1.0001f;
-          const float e_s = emax * scale;
-          const float sum = xn + emax;
           // |approx - exact| <= |dx| |e^| + |x| |de|  (Cauchy-Schwarz on the ACTUAL operand rounding errors, both
           // measured exactly: dx by the producers, de by codebook_rounding_error_kernel), two-sided, plus the fp32
           // accumulation error of the tensor core and of the exact scorer's chain and the |e|^2 limb residual
-          slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum
-                + 1.0e-6f * e_s * emax;
+          slack = filter_slack(xn, dn, emax, de_max, scale, (int)a.x.D, a.slack_t2);
           if (!(slack < 3.0e38f) || bad_blob) overflow = true;
         }
         const uint32_t tb = lane_addr + buf * kUnitN;

@@ -233,12 +233,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) assign
         if (cc == 0) {
           const float2 nr = reinterpret_cast<const float2*>(xsq)[(tt & (k2XsqBufs - 1)) * k2Rows + r];
           const float xn = sqrtf(nr.x) * 1.0001f, dn = sqrtf(nr.y) * 1.0001f;
-          const float e_s = emax * scale;
-          const float sum = xn + emax;
           // |approx - exact| <= |dx| |e^| + |x| |de| (Cauchy-Schwarz on the ACTUAL operand rounding errors, see
           // assign_tc.cu), two-sided, + fp32 accumulation / exact-chain error + limb residual of |e|^2
-          slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.x.D + 8) * 2.4e-7f * sum * sum
-                + 1.0e-6f * e_s * emax;
+          slack = filter_slack(xn, dn, emax, de_max, scale, (int)a.x.D, a.slack_t2);
           if (!(slack < 3.0e38f) || bad_blob) overflow = true;
         }
         const uint32_t tb = lane_addr + buf * 256;

@@ -241,12 +241,9 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
         if (cc == 0) {
           const float2 n0 = xsq[((tt & 1) * 2 + 0) * k3Rows + r], n1 = xsq[((tt & 1) * 2 + 1) * k3Rows + r];
           const float xn = sqrtf(n0.x + n1.x) * 1.0001f, dn = sqrtf(n0.y + n1.y) * 1.0001f;
-          const float e_s = emax * scale;
-          const float sum = xn + emax;
           // |approx - exact| <= |dx| |e^| + |x| |de| (Cauchy-Schwarz on the ACTUAL operand rounding errors, see
           // assign_tc.cu), two-sided, + fp32 accumulation / exact-chain error + limb residual of |e|^2
-          slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.D + 8) * 2.4e-7f * sum * sum
-                + 1.0e-6f * e_s * emax;
+          slack = filter_slack(xn, dn, emax, de_max, scale, (int)a.D, a.slack_t2);
           if (!(slack < 3.0e38f) || bad_blob) overflow = true;
         }
         const uint32_t tb = lane_addr + cc * 256;

@@ -305,12 +305,9 @@ assign_tc4_kernel(const __grid_constant__ CUtensorMap tmap, Tc4Args a) {
             n0 = xsq[((tt & 1) * 2 + 0) * k4Rows + r]; n1 = xsq[((tt & 1) * 2 + 1) * k4Rows + r];
           }
           const float xn = sqrtf(n0.x + n1.x) * 1.0001f, dn = sqrtf(n0.y + n1.y) * 1.0001f;
-          const float e_s = emax * scale;
-          const float sum = xn + emax;
           // |approx - exact| <= |dx| |e^| + |x| |de| (Cauchy-Schwarz on the ACTUAL operand rounding errors, see
           // assign_tc.cu), two-sided, + fp32 accumulation / exact-chain error + limb residual of |e|^2
-          slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.D + 8) * 2.4e-7f * sum * sum
-                + 1.0e-6f * e_s * emax;
+          slack = filter_slack(xn, dn, emax, de_max, scale, (int)a.D, a.slack_t2);
           if (!(slack < 3.0e38f) || bad_blob) overflow = true;
           __syncwarp();
           if (!PRE && lane == 0) mbar_arrive(bar_nempty + 8 * (tt & 1));  // the converters may reuse this norm buffer
@@ -587,9 +584,7 @@ __global__ void __launch_bounds__(256) shortlist_kernel(ShortlistArgs a) {
   const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long n = w0; n < a.n_rows; n += nw) {
     const float xn = sqrtf(a.norms[2 * n]) * 1.0001f, dn = sqrtf(a.norms[2 * n + 1]) * 1.0001f;
-    const float e_s = emax * scale, sum = xn + emax;
-    const float slack = 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * (float)(a.D + 8) * 2.4e-7f * sum * sum
-                      + 1.0e-6f * e_s * emax;                                 // (see assign_tc4_kernel's epilogue)
+    const float slack = filter_slack(xn, dn, emax, de_max, scale, (int)a.D, a.slack_t2);   // (common.cuh)
     bool overflow = !(slack < 3.0e38f) || bad_blob;
     const float* sc = a.scores + n * (long long)a.K_pad;
     float m = __int_as_float(0x7f800000);

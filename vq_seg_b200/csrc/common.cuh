@@ -206,6 +206,23 @@ inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 // predecessors); for the big kernels (filter -> rescoring -> gather, round 1) it was slower and is not used
 inline bool pdl_enabled() { return true; }
 
+// Slack of the tensor-core filters: how far a code's fp16 score may lie above the row minimum and still be the
+// reference's argmin.  |approx - exact| <= |dx| |e^| + |x| |de| (Cauchy-Schwarz on the ACTUAL operand rounding errors,
+// both measured: dx by the converters, de by the codebook preparation), two-sided, + the |e|^2 limb residual + the fp32
+// accumulation error of the tensor core and of the reference's chain.  The last part in two forms, whichever is
+// smaller: (D + 8) 4u (|x| + |e|)^2 (round 1), or -- the reference adds |x|^2 only AFTER the D products
+// (_euclidean_dist's term order), so the D-fold error grows with |x||e| and |e|^2 alone --
+// (D + 12) 4u |e| (4|x| + |e|) + t2 (|x| + |e|)^2, where t2 = (3 nb + 9) u covers the nb + 1 roundings at the
+// magnitude of |x|^2 (two final additions, nb - 1 K-block combines; both sides) and the codes sqrt() merges.  For the
+// reference's default codebook init (uniform(-1/K, 1/K), i.e. |e| << |x|) the second form is ~500x tighter: the
+// short-lists stay short where the first form sent every row to the overflow kernel (0.8 ms on the config-2 map).
+__device__ __forceinline__ float filter_slack(float xn, float dn, float emax, float de_max, float scale, int D, float t2) {
+  const float e_s = emax * scale, sum = xn + emax;
+  const float chain_a = (float)(D + 8) * 2.4e-7f * sum * sum;
+  const float chain_b = (float)(D + 12) * 2.4e-7f * emax * (4.f * xn + emax) + t2 * sum * sum;
+  return 2.002f * (dn * 2.002f * e_s + xn * de_max) + scale * fminf(chain_a, chain_b) + 1.0e-6f * e_s * emax;
+}
+
 #define VQSEG_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
 }  // namespace vqseg

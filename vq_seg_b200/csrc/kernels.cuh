@@ -39,6 +39,7 @@ struct TcArgs {
   // outputs
   long long* idx_out; unsigned long long* counts_out; long long code_base;
   int force_rescore;              // 1 -> every row goes to the exact pass (sharded mode needs exact distances)
+  float slack_t2;                 // coefficient of the |x|^2-magnitude roundings in the filter's slack (common.cuh filter_slack)
   WorkRec* work; int* work_count;
   long long* trace;               // optional (dev tool): [cta][role][256] clock64 stamps
 };
@@ -56,6 +57,7 @@ struct Tc2Args {
   float tau;
   long long* idx_out; unsigned long long* counts_out; long long code_base;
   int force_rescore;
+  float slack_t2;                 // coefficient of the |x|^2-magnitude roundings in the filter's slack (common.cuh filter_slack)
   WorkRec* work; int* work_count;
   long long* trace;
 };
@@ -73,6 +75,7 @@ struct Tc3Args {
   unsigned long long off_image, off_aug, off_enorm;
   long long* idx_out; unsigned long long* counts_out; long long code_base;
   int force_rescore;
+  float slack_t2;                 // coefficient of the |x|^2-magnitude roundings in the filter's slack (common.cuh filter_slack)
   WorkRec* work; int* work_count;
   long long* trace;
 };
@@ -95,6 +98,7 @@ struct Tc4Args {
   unsigned long long off_image, off_aug, off_enorm;
   long long* idx_out; unsigned long long* counts_out; long long code_base;
   int force_rescore;
+  float slack_t2;                 // coefficient of the |x|^2-magnitude roundings in the filter's slack (common.cuh filter_slack)
   WorkRec* work; int* work_count;
   long long* trace;
 };
@@ -102,7 +106,7 @@ struct Tc4Args {
 struct ShortlistArgs {
   const float* scores; const float* norms; long long n_rows; int K, K_pad, D;
   const unsigned char* blob;
-  long long* idx_out; unsigned long long* counts_out; long long code_base; int force_rescore;
+  long long* idx_out; unsigned long long* counts_out; long long code_base; int force_rescore; float slack_t2;
   WorkRec* work; int* work_count;
 };
 int launch_shortlist(const ShortlistArgs& a, cudaStream_t st);
