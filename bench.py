@@ -150,6 +150,20 @@ def extras_c1(dev):
             torch.autograd.backward((q, loss), (gq, one))
             x.grad = None
         us = _ev_time(step, 30, 5) * 1e3
+        # the same training forward + backward captured by torch.cuda.make_graphed_callables (the codebook gets no
+        # gradient in training, hence allow_unused_input): GPU time instead of host time, results bit-equal to eager
+        us_train_graph = None
+        try:
+            xs = x.detach().clone().requires_grad_(True)
+            gm = torch.cuda.make_graphed_callables(m, (xs,), allow_unused_input=True)
+
+            def gstep():
+                q, idx, loss, usage = gm(x)
+                torch.autograd.backward((q, loss), (gq, one))
+                x.grad = None
+            us_train_graph = _ev_time(gstep, 50, 5) * 1e3
+        except Exception as exc:  # noqa: BLE001 -- an extra, never fatal to the bench line
+            us_train_graph = "failed: %s" % (str(exc)[:120],)
         with torch.no_grad():
             m.eval()
             us_eval = _ev_time(lambda: m(x), 30, 5) * 1e3
@@ -157,7 +171,7 @@ def extras_c1(dev):
             xd = x.detach()
             us_graph = _ev_time(lambda: m(xd), 50, 5) * 1e3
         n = b * h * w
-        out[name] = {"shape": [b, c, h, w], "train_fwd_bwd_us": us, "eval_fwd_us": us_eval, "eval_fwd_cuda_graph_us": us_graph,
+        out[name] = {"shape": [b, c, h, w], "train_fwd_bwd_us": us, "train_fwd_bwd_cuda_graph_us": us_train_graph, "eval_fwd_us": us_eval, "eval_fwd_cuda_graph_us": us_graph,
                      "train_vectors_per_s": n / (us * 1e-6)}
     return out
 

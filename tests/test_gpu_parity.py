@@ -860,6 +860,37 @@ def test_random_shape_fuzz(dev):
         assert near_tie_ok(x.reshape(b, c, hw, 1), e, i_ex.cpu(), ref_idx), (it, b, c, hw, k)
 
 
+def test_training_step_is_graph_capturable(dev):
+    """The training forward + backward of the module under torch.cuda.make_graphed_callables (nothing on the path
+    allocates through the driver, synchronises or reads back): outputs and the input gradient bit-equal to eager."""
+    import vq_seg_b200 as V
+    torch.manual_seed(11)
+    m = V.VectorQuantizer(dim=96, num_embeddings=64).to(dev).train()
+    m.codebook.embedding.weight.data.normal_()
+    x = torch.randn(2, 96, 24, 24, device=dev).requires_grad_(True)
+    gy = torch.randn(2, 96, 24, 24, device=dev)
+    one = torch.ones(1, device=dev)
+
+    def step(fn):
+        q, idx, loss, usage = fn(x)
+        torch.autograd.backward((q, loss), (gy, one))
+        g = x.grad.clone()
+        x.grad = None
+        return q.detach().clone(), idx.clone(), loss.detach().clone(), usage.clone(), g
+
+    eager = step(m)
+    gm = torch.cuda.make_graphed_callables(m, (x.detach().clone().requires_grad_(True),), allow_unused_input=True)
+    for _ in range(2):                                      # replays
+        graphed = step(gm)
+        for a, b in zip(eager, graphed):
+            assert torch.equal(a, b)
+    m.codebook.embedding.weight.data.mul_(0.5)              # the captured graph follows weight updates (codebook guard)
+    e2, g2 = step(m), step(gm)
+    assert not torch.equal(e2[0], eager[0])
+    for a, b in zip(e2, g2):
+        assert torch.equal(a, b)
+
+
 def test_filter_slack_over_operand_scales(dev):
     """The filters' slack (common.cuh filter_slack) must stay a rigorous bound at every ratio of |e| to |x|: the
     reference's default uniform(-1/K, 1/K) init against unit-scale features (|e| << |x|, where the slack is governed
