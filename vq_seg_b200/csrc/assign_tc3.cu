@@ -232,7 +232,8 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
       float m_run = __int_as_float(0x7f800000);
       float slack = 0.f;
       int cnt = 0;
-      bool overflow = false;
+      bool overflow = false;          // the short-list of this half ran over its capacity (cleared when a new minimum drops the list)
+      bool bad = false;               // the row cannot be bounded at all (non-finite slack, unusable blob): every code is rescored
       for (int cc = 0; cc < a.n_cc; ++cc, ++u) {
         if (warp == 8) VQ3_TRACE(2, 4 * u);
         mbar_wait(bar_tfull + 8 * cc, (uint32_t)tt & 1);
@@ -244,7 +245,7 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
           // |approx - exact| <= |dx| |e^| + |x| |de| (Cauchy-Schwarz on the ACTUAL operand rounding errors, see
           // assign_tc.cu), two-sided, + fp32 accumulation / exact-chain error + limb residual of |e|^2
           slack = filter_slack(xn, dn, emax, de_max, scale, (int)a.D, a.slack_t2);
-          if (!(slack < 3.0e38f) || bad_blob) overflow = true;
+          if (!(slack < 3.0e38f) || bad_blob) bad = true;
         }
         const uint32_t tb = lane_addr + cc * 256;
 #pragma unroll 1
@@ -258,7 +259,7 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
             m1 = fminf(m1, fminf(__uint_as_float(v[j + 1]), __uint_as_float(v[j + 3])));
           }
           const float m_new = fminf(m_run, fminf(m0, m1));
-          if (m_run > m_new + slack) cnt = 0;          // every earlier entry scored >= the old minimum
+          if (m_run > m_new + slack) { cnt = 0; overflow = false; }   // every earlier entry (listed or dropped) scored >= the old minimum
           m_run = m_new;
           const float thr = m_run + slack;
           uint32_t mka = 0u, mkb = 0u, mkc = 0u, mkd = 0u;
@@ -270,7 +271,7 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
             mkd = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v[j + 24])), mkd, 1);
           }
           uint32_t mk = ~((mka << 24) | ((mkb & 0xffu) << 16) | ((mkc & 0xffu) << 8) | (mkd & 0xffu));
-          if (overflow) mk = 0u;
+          if (overflow || bad) mk = 0u;
           while (mk) {
             const int j = __clz(mk);
             mk &= ~(0x80000000u >> j);
@@ -284,16 +285,19 @@ assign_tc3_kernel(const __grid_constant__ CUtensorMap tmap, Tc3Args a) {
         if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * cc);      // this warp's columns are drained
       }
       // ---- tile done: the two column halves of each row meet (named barrier per lane quarter) ----
-      if (half == 1) *xchg = make_float2(m_run, __int_as_float(overflow ? -1 : cnt));
+      if (half == 1) *xchg = make_float2(m_run, __int_as_float(bad ? -2 : (overflow ? -1 : cnt)));
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
       if (half == 0) {
         const float2 o = *xchg;
         int cnt1 = __float_as_int(o.y);
         const float m = fminf(m_run, o.x);
-        if (cnt1 < 0) overflow = true;
+        bool ov1 = cnt1 == -1;
+        if (cnt1 == -2) bad = true;
         // a half whose own minimum is out of range contributes nothing (all its entries scored >= that minimum)
-        if (m_run > m + slack) cnt = 0;
-        if (o.x > m + slack) cnt1 = 0;
+        if (m_run > m + slack) { cnt = 0; overflow = false; }
+        if (o.x > m + slack) { cnt1 = 0; ov1 = false; }
+        if (cnt1 < 0) cnt1 = 0;
+        overflow = overflow || ov1 || bad;
         const int tot = overflow ? 0 : cnt + cnt1;
         const int last = (!overflow && tot == 1) ? (cnt == 1 ? (int)cand[0] : (int)cand_hi[0]) : 0;
         const bool unique = !overflow && tot == 1 && !a.force_rescore && last < a.K;
