@@ -164,7 +164,11 @@ int    vqseg_gather_bwd_codebook_f32(const float* g_q, int64_t B, int64_t P, int
  * counts (K int64) and sums (K*D fp32) must be zeroed by the caller (so ranks can accumulate).
  * deterministic=1: per-code sums are accumulated in ascending row order, one fp32 chain per
  * (code, d) -- the order of the reference's sequential CPU scatter_add_ -- via a stable counting
- * sort; deterministic=0: warp-aggregated fp32 atomics (fast, order not fixed).                  */
+ * sort (clusters far above the mean size stream through a shared-memory ring, one warp per 32 dims);
+ * deterministic=0: order not fixed -- vector fp32 reductions per row, or, for packed inputs of
+ * 2^18 rows and more, the same sort followed by register sums over windows of 64 sorted rows
+ * (one reduction per code met: no hot addresses whatever the clustering).  The workspace size
+ * depends on the mode: always ask vqseg_code_stats_workspace_bytes.                              */
 size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int deterministic);
 int    vqseg_code_stats_f32(const float* x, int64_t B, int64_t P, int64_t D,
                             int64_t sB, int64_t sP, int64_t sD,
