@@ -166,7 +166,7 @@ int    vqseg_gather_bwd_codebook_f32(const float* g_q, int64_t B, int64_t P, int
  * (code, d) -- the order of the reference's sequential CPU scatter_add_ -- via a stable counting
  * sort (clusters far above the mean size stream through a shared-memory ring, one warp per 32 dims);
  * deterministic=0: order not fixed -- vector fp32 reductions per row, or, for packed inputs of
- * 2^18 rows and more, the same sort followed by register sums over windows of 64 sorted rows
+ * 2^18 rows and more with K <= 1536, the same sort followed by register sums over windows of 64 sorted rows
  * (one reduction per code met: no hot addresses whatever the clustering).  The workspace size
  * depends on the mode: always ask vqseg_code_stats_workspace_bytes.                              */
 size_t vqseg_code_stats_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int deterministic);

@@ -1202,7 +1202,8 @@ static long long stats_rows_per_chunk(long long D) {
 }
 static bool stats_sorted_eligible(long long n_rows, long long D, long long K) {
   const long long n_chunks = (n_rows + stats_rows_per_chunk(D) - 1) / stats_rows_per_chunk(D);
-  return n_rows >= kSortedMinRows && K * (long long)sizeof(int) <= 200 * 1024 && n_chunks * K < (1ll << 31);
+  // (K <= 1536: the counting sort costs n_rows / 1024 x K histogram words and needs the table scatter to be cheap)
+  return n_rows >= kSortedMinRows && K <= 1536 && n_chunks * K < (1ll << 31);
 }
 static size_t stats_sort_ws_bytes(long long n_rows, long long D, long long K, int deterministic) {
   if (!deterministic && !stats_sorted_eligible(n_rows, D, K)) return 256;
