@@ -209,46 +209,51 @@ __device__ __forceinline__ void rescore_two_rows(const Rows& x, const float* __r
   __syncwarp();
   for (int g0 = 0; g0 < n_list_w || g0 == 0; g0 += stage_cap) {
     // ---- stage candidates [g0, g0 + stage_cap) of each half (and, the first time round, the row itself)
-    if (vec4 && D <= 256 && stage_cap <= 4) {
-      // common case: the row (16 strided words per lane) and up to four code rows (4 float4 each, two at a time in
-      // registers) are all requested before the first shared-memory store
-      float t[16];
+    if (vec4 && D <= 512 && stage_cap <= 4) {
+      // common case, per 256-dim half: the row (16 strided words per lane) and up to four code rows (4 float4 each,
+      // two at a time in registers) are all requested before the first shared-memory store.  (Extending this path from
+      // D <= 256 to D <= 512 left config 4's rescoring at 2.8 ms: the stall samples ncu shows on the stores behind
+      // the loads are the first batch's latency, not a lack of batching.)
       const bool contig = x.sD == 1 && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0);
-      if (g0 == 0) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int j = contig ? (4 * hl + 64 * (u >> 2) + (u & 3)) : (hl + 16 * u);
-          t[u] = (valid && j < D) ? __ldg(xr + (long long)j * x.sD) : 0.f;
-        }
-      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < stage_cap; c0 += 2) {
-        float4 ev[2][4];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int ci = g0 + c0 + c;                                     // index in the half's short-list
-          const bool on = c0 + c < stage_cap && ci < n_list;
-          const float* er = E + (long long)__shfl_sync(0xffffffffu, my_k, hw * 16 + (ci & 7), 32) * D;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 4 * hl + 64 * i;
-            ev[c][i] = (on && j < D) ? __ldg(reinterpret_cast<const float4*>(er + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        if (g0 == 0 && c0 == 0 && valid) {
+      for (int dh = 0; dh < D; dh += 256) {
+        float t[16];
+        if (g0 == 0) {
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const int j = contig ? (4 * hl + 64 * (u >> 2) + (u & 3)) : (hl + 16 * u);
-            if (j < D) xs[j] = t[u];
+            const int j = dh + (contig ? (4 * hl + 64 * (u >> 2) + (u & 3)) : (hl + 16 * u));
+            t[u] = (valid && j < D) ? __ldg(xr + (long long)j * x.sD) : 0.f;
           }
         }
+#pragma unroll 1
+        for (int c0 = 0; c0 < stage_cap; c0 += 2) {
+          float4 ev[2][4];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const bool on = c0 + c < stage_cap && g0 + c0 + c < n_list;
+          for (int c = 0; c < 2; ++c) {
+            const int ci = g0 + c0 + c;                                     // index in the half's short-list
+            const bool on = c0 + c < stage_cap && ci < n_list;
+            const float* er = E + (long long)__shfl_sync(0xffffffffu, my_k, hw * 16 + (ci & 7), 32) * D;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 4 * hl + 64 * i;
-            if (on && j < D) *reinterpret_cast<float4*>(es + (c0 + c) * es_stride + j) = ev[c][i];
+            for (int i = 0; i < 4; ++i) {
+              const int j = dh + 4 * hl + 64 * i;
+              ev[c][i] = (on && j < D) ? __ldg(reinterpret_cast<const float4*>(er + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (g0 == 0 && c0 == 0 && valid) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int j = dh + (contig ? (4 * hl + 64 * (u >> 2) + (u & 3)) : (hl + 16 * u));
+              if (j < D) xs[j] = t[u];
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const bool on = c0 + c < stage_cap && g0 + c0 + c < n_list;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = dh + 4 * hl + 64 * i;
+              if (on && j < D) *reinterpret_cast<float4*>(es + (c0 + c) * es_stride + j) = ev[c][i];
+            }
           }
         }
       }
