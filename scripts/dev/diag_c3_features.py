@@ -44,7 +44,7 @@ for i, m in enumerate(model.codebook):
     ws = ops._last_assign_ws
     n = b * h * w
     flagged = ws[:4].view(torch.int32).item()
-    recs = ws[256:256 + 48 * n].view(torch.int32).reshape(n, 12)[:flagged]
+    recs = ws[256 + 8192:256 + 8192 + 48 * n].view(torch.int32).reshape(n, 12)[:flagged]
     cnt = recs[:, 1]
     over = int((cnt > 8).sum())
     i_ex, _ = ops.assign(xv, e, None, ops.ALGO_EXACT)

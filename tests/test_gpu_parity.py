@@ -114,6 +114,31 @@ def test_short_list_overflow_rows(dev, shape, metric):
     assert torch.equal(c_ex, c_tc)
 
 
+@pytest.mark.parametrize("k,d", [(8192, 64), (65536, 32), (600, 256)])
+def test_few_overflow_rows_are_split_over_blocks(dev, k, d):
+    """A handful of overflow rows against many codes (zero feature vectors whose nearest codes are a dozen codes of
+    equal norm): each row's code slices are spread over several blocks of the overflow kernel that meet in a packed
+    atomicMin -- indices, counts and the sharded mode's (distance, index) keys must equal the exact scorer's."""
+    from vq_seg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(k + d)
+    x = torch.randn(1, d, 2048, generator=g, device=dev)
+    x[0, :, [7, 900, 2047]] = 0.0
+    xv = x.permute(0, 2, 1)
+    e = torch.randn(k, d, generator=g, device=dev)
+    # a dozen codes of one norm, just below every other code's: nearest to the zero vectors only
+    e[100:112] = 0.8 * float(e.norm(dim=-1).min()) * torch.nn.functional.normalize(e[100:112], dim=-1)
+    e[105] = e[101]                                                    # an exact duplicate: the lower index must win
+    e = e.contiguous()
+    blob = ops.prepare_codebook(e)
+    i_ex, c_ex = ops.assign(xv, e, None, ops.ALGO_EXACT)
+    i_tc, c_tc = ops.assign(xv, e, blob, ops.ALGO_AUTO)
+    n_ovf = ops._last_assign_ws[4:8].view(torch.int32).item()
+    assert 3 <= n_ovf <= 16, n_ovf
+    assert torch.equal(i_ex, i_tc) and torch.equal(c_ex, c_tc)
+    assert int(i_tc[0, 7]) in range(100, 112) and int(i_tc[0, 7]) != 105
+    assert torch.equal(ops.assign_keys(xv, e, blob, 1000, ops.ALGO_AUTO), ops.assign_keys(xv, e, None, 1000, ops.ALGO_EXACT))
+
+
 @pytest.mark.parametrize("metric", ["euclidean", "cosine"])
 @pytest.mark.parametrize("shape,layout", [((2, 1024, 32, 32, 512), "nchw"), ((2, 2048, 16, 16, 512), "nchw"),
                                           ((4, 1024, 32, 32, 512), "nchw"), ((1, 768, 20, 24, 700), "nchw"),

@@ -207,9 +207,10 @@ static size_t splitd_scratch_bytes(long long n_rows, long long K) {
   return (size_t)round_up(bytes, 256) + (size_t)round_up(n_rows * 8, 256);
 }
 
+constexpr size_t kOvfScratchBytes = (size_t)kOvfSplitCap * (sizeof(unsigned long long) + sizeof(int)) + 2048;   // 8 KiB
 size_t vqseg_assign_workspace_bytes(int64_t n_rows, int64_t D, int64_t K, int algo) {
   (void)D; (void)algo;
-  size_t b = 256;                                                     // work counter + tickets
+  size_t b = 256 + kOvfScratchBytes;                                  // work counter + tickets, minima / tickets of split overflow rows
   b += (size_t)round_up(n_rows * (long long)sizeof(WorkRec), 256);    // one record per undecided row (worst case: all)
   b += (size_t)round_up(n_rows * (long long)sizeof(int), 256);        // rows whose short-list overflowed (worst case: all)
   b += (size_t)round_up(round_up(K, 256) * sizeof(float), 256);       // enorm when no blob is given
@@ -238,6 +239,8 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
 
   char* p = (char*)ws;
   int* work_count = (int*)p;   p += 256;                       // [0] undecided rows, [1] overflow rows, [2] gather ticket, [3] spare
+  unsigned long long* ovf_keys = (unsigned long long*)p; int* ovf_tickets = (int*)(p + kOvfSplitCap * sizeof(unsigned long long));
+  p += kOvfScratchBytes;
   WorkRec* work = (WorkRec*)p; p += round_up(n_rows * (long long)sizeof(WorkRec), 256);
   int* ovf_rows = (int*)p;     p += round_up(n_rows * (long long)sizeof(int), 256);
   float* enorm_ws = (float*)p; p += round_up(round_up(K, 256) * sizeof(float), 256);
@@ -399,6 +402,7 @@ static int assign_internal(const float* x, int64_t B, int64_t P, int64_t D, int6
   prof_record(prof_events, 1, st);
   if (rc) return rc;
   ea.work = work; ea.work_count = work_count;
+  ea.ovf_keys = ovf_keys; ea.ovf_tickets = ovf_tickets;
   ea.ovf_rows = ovf_rows; ea.ovf_count = work_count + 1;               // ([1] is zeroed by the prologue with the counter)
   ea.trace = dev_trace() ? dev_trace() + 148 * 4 * 256 : nullptr;      // dev tool: 8 int64 after the filter's trace area
   prof_record(prof_events, 2, st);

@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(kExactWarps * 32) exact_score_kernel(ExactArgs
 __global__ void __launch_bounds__(kExactWarps * 32) rescore_kernel(ExactArgs a, int stage_cap, long long rec_cap) {
   extern __shared__ __align__(16) float smem_x[];
   pdl_trigger();                                  // the overflow kernel behind may become resident (it waits for us)
+  if (blockIdx.x == 0 && a.ovf_keys) {            // minima / tickets of the overflow kernel's split mode start from scratch
+    for (int i = threadIdx.x; i < kOvfSplitCap; i += blockDim.x) { a.ovf_keys[i] = ~0ull; a.ovf_tickets[i] = 0; }
+  }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int hw = lane >> 4, hl = lane & 15;
   const int D = (int)a.x.D;
@@ -144,7 +147,15 @@ __global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactA
   int kb = a.kblock;
   if (kb <= 0 || kb > L) kb = L;
   const int n_slices = (K + 31) / 32;
-  for (int r = blockIdx.x; r < n_ovf; r += gridDim.x) {
+  // few rows, many codes (ONE overflow row at K = 65536 kept a single SM busy for 2-5 ms): the row's code slices are
+  // split over `split` blocks that meet in a packed (ordered score bits, code) atomicMin; the block that draws the
+  // row's last ticket writes the result
+  int split = 1;
+  if (a.ovf_keys && n_ovf > 0 && n_ovf <= kOvfSplitCap && 2 * n_ovf <= (int)gridDim.x)
+    split = min((int)gridDim.x / n_ovf, (n_slices + kOvfWarps - 1) / kOvfWarps);
+  if (split < 1) split = 1;
+  for (int w = blockIdx.x; w < n_ovf * split; w += gridDim.x) {
+    const int r = w / split, part = w - r * split;
     const int row = a.ovf_rows[r];
     const float* xr = a.x.row(row);
     __syncthreads();                                                    // the previous row's xs / s_best are done with
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactA
     const float xnorm = ip ? 0.f : s_xnorm;
     float best = __int_as_float(0x7f800000);
     int best_k = 0x7fffffff;
-    for (int s = wib; s < n_slices; s += kOvfWarps) {
+    for (int s = part * kOvfWarps + wib; s < n_slices; s += split * kOvfWarps) {
       const int k = s * 32 + lane;
       float c = 0.f;
       bool first = true;
@@ -208,7 +219,22 @@ __global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactA
     if (lane == 0) { s_best[wib] = best; s_bestk[wib] = best_k; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < kOvfWarps; ++w) lexmin(best, best_k, s_best[w], s_bestk[w]);
+      for (int w2 = 1; w2 < kOvfWarps; ++w2) lexmin(best, best_k, s_best[w2], s_bestk[w2]);
+      if (split > 1) {
+        // order-preserving bits of the score (-0 counts as +0, like lexmin's ==), the code in the low word: the
+        // 64-bit minimum is lexmin over all blocks of the row
+        if (best == 0.f) best = 0.f;
+        uint32_t u = __float_as_uint(best);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        atomicMin(a.ovf_keys + r, ((unsigned long long)u << 32) | (unsigned long long)(uint32_t)best_k);
+        __threadfence();
+        if (atomicAdd(a.ovf_tickets + r, 1) != split - 1) continue;      // (thread 0 only: the block's other threads wait at the next row's barrier)
+        __threadfence();
+        const unsigned long long key = atomicMin(a.ovf_keys + r, ~0ull);
+        u = (uint32_t)(key >> 32);
+        best = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+        best_k = (int)(uint32_t)key;
+      }
       if (best_k == 0x7fffffff) best_k = 0;
       if (a.idx_out) a.idx_out[row] = (long long)best_k + a.code_base;
       if (a.counts_out) atomicAdd(a.counts_out + best_k, 1ull);

@@ -12,6 +12,7 @@ constexpr int kWorkCandCap = 8;
 struct alignas(16) WorkRec { int row; int cnt; int pad0; int pad1; int cand[kWorkCandCap]; };
 
 // ---- exact.cu: exact fp32 scorer (brute force over all codes, or the rescoring pass over the filter's short-lists)
+constexpr int kOvfSplitCap = 512;   // overflow rows up to which each row's codes are split over several blocks
 struct ExactArgs {
   Rows x;
   const float* E; int K;
@@ -21,6 +22,7 @@ struct ExactArgs {
   // candidate mode (null -> all rows x all codes)
   const WorkRec* work; const int* work_count;         // undecided rows + device counter
   int* ovf_rows; int* ovf_count;                      // rows whose short-list overflowed: deferred to overflow_rows_kernel
+  unsigned long long* ovf_keys; int* ovf_tickets;     // kOvfSplitCap packed (score, code) minima + block tickets: few overflow rows are split over blocks
   long long* idx_out; unsigned long long* counts_out; unsigned long long* key_out; long long code_base;
   long long* trace;     // dev tool: [0] min start ns, [1] max end ns
 };
