@@ -130,16 +130,19 @@ __global__ void __launch_bounds__(kExactWarps * 32) rescore_kernel(ExactArgs a, 
 // one feeds the chains), so each lane runs its code's chain -- the same terms in the same order and the same K-blocking
 // as chain_dist2 -- from conflict-free shared memory.
 constexpr int kOvfWarps = 8;
-__global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactArgs a) {
+constexpr int kOvfRows = 4;        // rows a block scores against one pass over the codebook when MANY rows overflow
+__global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactArgs a, int rows_per_block) {
   extern __shared__ __align__(16) float smem_x[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int D = (int)a.x.D, K = a.K;
   const bool ip = a.ip != 0;
-  float* xs = smem_x;                                                   // [D rounded to 4]
-  float* tile = smem_x + ((D + 3) & ~3) + (size_t)wib * (32 * 33);      // this warp's [32 codes][33]
-  __shared__ float s_best[kOvfWarps];
-  __shared__ int s_bestk[kOvfWarps];
-  __shared__ float s_xnorm;
+  const int Dp = (D + 3) & ~3;
+  float* xs = smem_x;                                                   // [rows_per_block][D rounded to 4]
+  float* tile = smem_x + (size_t)rows_per_block * Dp + (size_t)wib * (32 * 33);      // this warp's [32 codes][33]
+  __shared__ float s_best[kOvfRows][kOvfWarps];
+  __shared__ int s_bestk[kOvfRows][kOvfWarps];
+  __shared__ float s_xn[kOvfRows];
+  __shared__ int s_rows[kOvfRows];
   pdl_trigger();                                  // the gather behind may become resident ...
   pdl_wait();                                     // ... and we need the rescoring pass's overflow list
   const int n_ovf = *reinterpret_cast<volatile const int*>(a.ovf_count);
@@ -154,6 +157,117 @@ __global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactA
   if (a.ovf_keys && n_ovf > 0 && n_ovf <= kOvfSplitCap && 2 * n_ovf <= (int)gridDim.x)
     split = min((int)gridDim.x / n_ovf, (n_slices + kOvfWarps - 1) / kOvfWarps);
   if (split < 1) split = 1;
+  if (split == 1 && rows_per_block == kOvfRows && n_ovf >= 2 * (int)gridDim.x) {
+    // MANY rows overflow (a collapsed codebook: every row): one pass over the codebook per row re-reads K x D floats
+    // from L2 for each of them (17 GB on the config-2 map, 4.1 ms).  Here a block scores kOvfRows rows against each
+    // code tile: every lane keeps one chain per row, same terms in the same order as below.
+    const int n_groups = (n_ovf + kOvfRows - 1) / kOvfRows;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+      __syncthreads();                                                  // the previous group's xs / s_best are done with
+      if (threadIdx.x < kOvfRows) s_rows[threadIdx.x] = g * kOvfRows + (int)threadIdx.x < n_ovf ? a.ovf_rows[g * kOvfRows + threadIdx.x] : -1;
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kOvfRows; ++r) {
+        const int row = s_rows[r];
+        const float* xr = a.x.row(row < 0 ? 0 : row);
+        for (int j = threadIdx.x; j < Dp; j += blockDim.x) xs[r * Dp + j] = (row >= 0 && j < D) ? __ldg(xr + (long long)j * a.x.sD) : 0.f;
+      }
+      __syncthreads();
+      if (wib < kOvfRows && !ip) {
+        const float* xw = xs + wib * Dp;
+        const float xn = torch_order_sumsq_warp([&](long long j) { float v = xw[j]; return __fmul_rn(v, v); }, D, lane);
+        if (lane == 0) s_xn[wib] = xn;
+      }
+      __syncthreads();
+      float best[kOvfRows];
+      int best_k[kOvfRows];
+#pragma unroll
+      for (int r = 0; r < kOvfRows; ++r) { best[r] = __int_as_float(0x7f800000); best_k[r] = 0x7fffffff; }
+      for (int s = wib; s < n_slices; s += kOvfWarps) {
+        const int k = s * 32 + lane;
+        float c[kOvfRows];
+        bool first = true;
+        for (int blk = 0; blk < L; blk += kb) {
+          const int end = min(blk + kb, L), dend = min(end, D);
+          float t[kOvfRows];
+#pragma unroll
+          for (int r = 0; r < kOvfRows; ++r) t[r] = 0.f;
+          for (int d0 = blk; d0 < dend; d0 += 32) {
+            // (no register double-buffering here: four chains per lane keep the warp busy four times as long per
+            // tile, and the sixteen warps of an SM cover each other's tile loads)
+            __syncwarp();
+            {
+              float nxt[32];                                            // tile rows = codes, lane = dim d0 + lane
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc) {
+                const int kc = s * 32 + cc;
+                nxt[cc] = (kc < K && d0 + lane < dend) ? __ldg(a.E + (long long)kc * D + d0 + lane) : 0.f;
+              }
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc) tile[cc * 33 + lane] = nxt[cc];
+            }
+            __syncwarp();
+            const int w = min(32, dend - d0);
+            const float* tr = tile + lane * 33;
+            if (w == 32 && (d0 & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float e0 = tr[j], e1 = tr[j + 1], e2 = tr[j + 2], e3 = tr[j + 3];
+#pragma unroll
+                for (int r = 0; r < kOvfRows; ++r) {
+                  const float4 xv = *reinterpret_cast<const float4*>(xs + r * Dp + d0 + j);
+                  t[r] = __fmaf_rn(xv.x, e0, t[r]); t[r] = __fmaf_rn(xv.y, e1, t[r]);
+                  t[r] = __fmaf_rn(xv.z, e2, t[r]); t[r] = __fmaf_rn(xv.w, e3, t[r]);
+                }
+              }
+            } else {
+              for (int j = 0; j < w; ++j) {
+                const float e = tr[j];
+#pragma unroll
+                for (int r = 0; r < kOvfRows; ++r) t[r] = __fmaf_rn(xs[r * Dp + d0 + j], e, t[r]);
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < kOvfRows; ++r) {
+            float sc = ip ? -t[r] : -2.f * t[r];                         // exact
+            if (end > D) {
+              if (blk <= D) sc = __fadd_rn(sc, ip ? 0.f : s_xn[r]);      // term D   : |x|^2 * 1
+              if (end > D + 1) sc = __fadd_rn(sc, k < K ? a.enorm[k] : 0.f); // term D+1 : 1 * |e|^2
+            }
+            c[r] = first ? sc : __fadd_rn(c[r], sc);
+          }
+          first = false;
+        }
+#pragma unroll
+        for (int r = 0; r < kOvfRows; ++r)
+          if (k < K) lexmin(best[r], best_k[r], score_key(c[r], ip), k);
+      }
+#pragma unroll
+      for (int r = 0; r < kOvfRows; ++r) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const float d2 = __shfl_xor_sync(0xffffffffu, best[r], o);
+          const int k2 = __shfl_xor_sync(0xffffffffu, best_k[r], o);
+          lexmin(best[r], best_k[r], d2, k2);
+        }
+        if (lane == 0) { s_best[r][wib] = best[r]; s_bestk[r][wib] = best_k[r]; }
+      }
+      __syncthreads();
+      if (threadIdx.x < kOvfRows && s_rows[threadIdx.x] >= 0) {
+        const int r = threadIdx.x, row = s_rows[r];
+        float b = s_best[r][0];
+        int bk = s_bestk[r][0];
+        for (int w2 = 1; w2 < kOvfWarps; ++w2) lexmin(b, bk, s_best[r][w2], s_bestk[r][w2]);
+        if (bk == 0x7fffffff) bk = 0;
+        if (a.idx_out) a.idx_out[row] = (long long)bk + a.code_base;
+        if (a.counts_out) atomicAdd(a.counts_out + bk, 1ull);
+        if (a.key_out)
+          a.key_out[row] = ((unsigned long long)__float_as_uint(b) << 32) | (unsigned long long)(uint32_t)(bk + a.code_base);
+      }
+    }
+    return;
+  }
   for (int w = blockIdx.x; w < n_ovf * split; w += gridDim.x) {
     const int r = w / split, part = w - r * split;
     const int row = a.ovf_rows[r];
@@ -163,10 +277,10 @@ __global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactA
     __syncthreads();
     if (wib == 0 && !ip) {
       const float xn = torch_order_sumsq_warp([&](long long j) { float v = xs[j]; return __fmul_rn(v, v); }, D, lane);
-      if (lane == 0) s_xnorm = xn;
+      if (lane == 0) s_xn[0] = xn;
     }
     __syncthreads();
-    const float xnorm = ip ? 0.f : s_xnorm;
+    const float xnorm = ip ? 0.f : s_xn[0];
     float best = __int_as_float(0x7f800000);
     int best_k = 0x7fffffff;
     for (int s = part * kOvfWarps + wib; s < n_slices; s += split * kOvfWarps) {
@@ -216,10 +330,10 @@ __global__ void __launch_bounds__(kOvfWarps * 32, 2) overflow_rows_kernel(ExactA
       const int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
       lexmin(best, best_k, d2, k2);
     }
-    if (lane == 0) { s_best[wib] = best; s_bestk[wib] = best_k; }
+    if (lane == 0) { s_best[0][wib] = best; s_bestk[0][wib] = best_k; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w2 = 1; w2 < kOvfWarps; ++w2) lexmin(best, best_k, s_best[w2], s_bestk[w2]);
+      for (int w2 = 1; w2 < kOvfWarps; ++w2) lexmin(best, best_k, s_best[0][w2], s_bestk[0][w2]);
       if (split > 1) {
         // order-preserving bits of the score (-0 counts as +0, like lexmin's ==), the code in the low word: the
         // 64-bit minimum is lexmin over all blocks of the row
@@ -291,12 +405,15 @@ int launch_exact(const ExactArgs& a, long long max_work, cudaStream_t st) {
   rescore_kernel<<<(unsigned)blocks, nwarps * 32, smem, st>>>(a, stage_cap, max_work);
   VQSEG_LAUNCH_CHECK();
   if (a.ovf_rows) {
-    const size_t osmem = xs_bytes + (size_t)kOvfWarps * 32 * 33 * sizeof(float);
+    // (kOvfRows rows per block when their staging leaves room for two blocks per SM)
+    const size_t tiles_bytes = (size_t)kOvfWarps * 32 * 33 * sizeof(float);
+    const int rows_per_block = kOvfRows * xs_bytes + tiles_bytes <= 100 * 1024 ? kOvfRows : 1;
+    const size_t osmem = rows_per_block * xs_bytes + tiles_bytes;
     if (osmem > 200 * 1024) return VQSEG_EUNSUPPORTED;
     static size_t oconf[kMaxDevices] = {0};
     if (int rc = ensure_dynamic_smem(overflow_rows_kernel, osmem, oconf)) return rc;
     long long ob = max_work < 2ll * num_sms() ? max_work : 2ll * num_sms();
-    cudaError_t le = launch_dependent(overflow_rows_kernel, dim3((unsigned)ob), dim3(kOvfWarps * 32), osmem, st, pdl_enabled(), a);
+    cudaError_t le = launch_dependent(overflow_rows_kernel, dim3((unsigned)ob), dim3(kOvfWarps * 32), osmem, st, pdl_enabled(), a, rows_per_block);
     if (le != cudaSuccess) return (int)le;
     VQSEG_LAUNCH_CHECK();
   }
