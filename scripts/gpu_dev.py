@@ -67,10 +67,9 @@ def stage_tc():
         ws = ops._last_assign_ws
         flagged = ws[:4].view(torch.int32).item()
         nrows = gi.numel()
-        r256 = lambda v: (v + 255) // 256 * 256
-        wr = ws[256:256 + 4 * nrows].view(torch.int32)[:flagged].long()
-        cc = ws[256 + r256(4 * nrows):256 + r256(4 * nrows) + 4 * nrows].view(torch.int32)
-        hist = torch.bincount(cc[wr].clamp(0, 9), minlength=10).tolist() if flagged else []
+        # workspace: 256 B counters | 8 KiB overflow-split scratch | one 48-byte record per undecided row {row, n, -, -, cand[8]}
+        recs = ws[256 + 8192:256 + 8192 + 48 * nrows].view(torch.int32).reshape(nrows, 12)[:flagged]
+        hist = torch.bincount(recs[:, 1].long().clamp(0, 9), minlength=10).tolist() if flagged else []
         print("      candidate-count histogram of rescored rows (9 = all codes):", hist)
         print(f"[tc] {name:16s} vs golden {mism}/{gi.numel()}  vs exact {mism_e}  counts mism {cm}  rescored rows {flagged} ({100.0 * flagged / gi.numel():.1f}%)  {'PASS' if mism_e == 0 and cm == 0 else 'FAIL'}", flush=True)
 
