@@ -39,6 +39,12 @@ def test_error_strings_and_sizes(native):
     assert lib.vqseg_assign_workspace_bytes(32768, 256, 512, 0) >= 32768 * 48        # one 48-byte work record per row
     # atomic statistics: 256 bytes + the packed-row scratch of one chunk (strided maps are packed before the row kernels)
     assert lib.vqseg_code_stats_workspace_bytes(1000, 64, 32, 0) == 256 + 1000 * 64 * 4
+    # large packed inputs with K <= 1536 take the counting sort in the unordered mode too (+ one code per sorted position)
+    n = 1 << 18
+    det, unord = lib.vqseg_code_stats_workspace_bytes(n, 64, 1024, 1), lib.vqseg_code_stats_workspace_bytes(n, 64, 1024, 0)
+    assert unord == det + n * 4
+    assert lib.vqseg_code_stats_workspace_bytes(n, 64, 2048, 0) == 256 + n * 64 * 4
+    assert lib.vqseg_code_stats_workspace_bytes(n - 1, 64, 1024, 0) == 256 + (n - 1) * 64 * 4
 
 
 def test_sass_is_blackwell_native():
